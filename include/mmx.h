@@ -1,0 +1,178 @@
+/*
+ * mmx.h - C ABI of libmmx.so, the B200-native (sm_100a) gradient-weighted attention-relevancy engine.
+ *
+ * The reference (hila-chefer/Transformer-MM-Explainability) is 100 % Python/PyTorch and defines NO FFI or
+ * plugin layer: its boundary is a set of Python call signatures.  This header is therefore
+ * the contract a maintainer of the reference would bind (ctypes stub shown in INTEGRATION.md); each entry
+ * point cites the reference function (file:line under the reference tree) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers (fp32 unless said otherwise), explicit sizes / leading dimensions, a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).  No torch / C++ types.
+ *   - every function returns 0 on success, non-zero on error; mmx_last_error() returns the text (thread-local).
+ *   - the caller allocates all outputs; kernels never allocate.  The only hidden allocations are the engine
+ *     objects (mmx_clip_create), which own their weight arena and activation workspace.
+ *   - "ld*" arguments are row strides in ELEMENTS; "plane" strides are computed as rows*ld.
+ *   - nothing here falls back to the CPU: if no sm_100 device is present the calls fail.
+ */
+#ifndef MMX_H_
+#define MMX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMX_VERSION 1
+
+const char* mmx_last_error(void);
+int mmx_version(void);
+/* Number of kernels this library has launched since load (all streams); the bench reports it as gpu_launches. */
+uint64_t mmx_launch_count(void);
+/* Selects the GEMM backend for the transformer linears: 0 = fp32 FFMA (bisecting reference),
+ * 1 = tcgen05 3xTF32 (default when available).  Returns the backend in effect. */
+int mmx_set_gemm_backend(int backend);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Rule kernels
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Rule 5:  Abar[b,t,s] = (1/H) * sum_h max(dA[b,h,t,s] * A[b,h,t,s], 0).
+ * Replaces avg_heads (DETR/modules/ExplanationGenerator.py:19-24; lxmert/lxmert/src/ExplanationGenerator.py:18-23)
+ * and the inline batched form of CLIP_explainability.ipynb:176-181 (head index b*H+h).
+ * A, dA: [B,H,T,S] with row stride ld_in; Abar: [B,T,S] with row stride ld_out.  HBM-bound. */
+int mmx_avg_heads(const float* A, const float* dA, float* Abar, int B, int H, int T, int S,
+                  int ld_in, int ld_out, void* stream);
+
+/* Rules 6+7:  R_ss_out = R_ss + Abar*R_ss ;  R_sq_out = R_sq + Abar*R_sq  (both from the PRE-update state).
+ * Replaces apply_self_attention_rules + the caller's "+=" (DETR/modules/ExplanationGenerator.py:27-30,118,
+ * 127-129) and "R = R + torch.bmm(cam, R)" (CLIP_explainability.ipynb:182,205).
+ * Abar [B,S,S] (ld_a), R_ss [B,S,S] (ld_ss), R_sq [B,S,Q] (ld_sq) or NULL.  Outputs may not alias inputs. */
+int mmx_self_update(const float* Abar, int ld_a, const float* R_ss, float* R_ss_out, int ld_ss,
+                    const float* R_sq, float* R_sq_out, int ld_sq, int B, int S, int Q, void* stream);
+
+/* Eq. 8-9:  out = (R - I) / rowsum(R - I) + I.  Replaces handle_residual
+ * (DETR/modules/ExplanationGenerator.py:46-53).  The reference asserts diag(R-I) >= 0 on the host; here the
+ * minimum diagonal entry of R-I over the batch is written to *min_diag (device float, may be NULL) so the
+ * caller can raise the same AssertionError without a sync inside the kernel. */
+int mmx_handle_residual(const float* R, float* out, int ld, int B, int S, float* min_diag, void* stream);
+
+#define MMX_MM_NORMALIZE     1   /* apply_normalization=True  */
+#define MMX_MM_SELF_IN_10    2   /* apply_self_in_rule_10=True */
+#define MMX_MM_NAN_TO_ZERO   4   /* DETR's R_sq_addition[isnan]=0 (DETR/modules/ExplanationGenerator.py:42) */
+
+/* Rules 10+11.  R_sq_add = Rn_ss^T * (Abar_sq * Rn_qq)   (Rn = handle_residual(R) when MMX_MM_NORMALIZE, else R;
+ * R_sq_add = Abar_sq when !MMX_MM_SELF_IN_10);  R_ss_add = Abar_sq * R_qs  (only when R_qs != NULL).
+ * Replaces apply_mm_attention_rules (DETR/modules/ExplanationGenerator.py:33-43 - returns R_sq_add only, with
+ * NaN->0; lxmert/lxmert/src/ExplanationGenerator.py:32-42 - returns (R_sq_add, R_ss_add), no NaN guard).
+ * Shapes per sample: R_ss [T,T], R_qq [S,S], Abar_sq [T,S], R_qs [S,T]; outputs R_sq_add [T,S], R_ss_add [T,T].
+ * workspace: device scratch of mmx_mm_update_workspace(B,T,S) bytes.  min_diag: 2 device floats (ss, qq) or NULL. */
+size_t mmx_mm_update_workspace(int B, int T, int S);
+int mmx_mm_update(const float* R_ss, int ld_ss, const float* R_qq, int ld_qq, const float* R_qs, int ld_qs,
+                  const float* Abar_sq, int ld_a, float* R_sq_add, int ld_sq_add, float* R_ss_add, int ld_ss_add,
+                  int B, int T, int S, int flags, void* workspace, float* min_diag, void* stream);
+
+/* Rollout baseline: prod_l rownorm(mats[l] + I), l = start_layer .. L-1, later layers multiplied on the left.
+ * Replaces compute_rollout_attention (DETR/modules/ExplanationGenerator.py:5-16; normalize=0 gives the
+ * VisualBERT variant, VisualBERT/mmf/models/transformers/backends/ExplanationGenerator.py:5-17).
+ * mats: [L,B,S,S] contiguous (ld = S);  out: [B,S,S];  workspace: 2*B*S*S floats. */
+int mmx_rollout(const float* mats, int L, int B, int S, int start_layer, int normalize, float* out,
+                float* workspace, void* stream);
+
+/* Generic batched C[b] = beta_src[b] + op(A[b]) * B[b]  (fp32, used by the rule entry points above; exported
+ * for the host-side generators).  transA: 0 = A is [M,K], 1 = A is stored [K,M].  add may be NULL. */
+int mmx_bmm_add(const float* A, int lda, long long strideA, int transA, const float* Bm, int ldb, long long strideB,
+                const float* add, int ldadd, long long strideAdd, float* C, int ldc, long long strideC,
+                int batch, int M, int N, int K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Transformer primitives that produce A and dA.  Exported so the
+ * host-side generators for DETR / LXMERT / ViT can be assembled from the same kernels as the CLIP engine.
+ * ------------------------------------------------------------------------------------------------------- */
+
+#define MMX_ACT_NONE       0
+#define MMX_ACT_QUICKGELU  1   /* x*sigmoid(1.702x), CLIP/clip/model.py:162-164 */
+#define MMX_ACT_GELU       2   /* exact erf GELU (timm ViT, LXMERT) */
+#define MMX_ACT_RELU       3   /* DETR FFN, DETR/models/transformer.py:239 */
+
+/* C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (+ residual[M,N]);  if act != NONE and C_act != NULL also writes
+ * C_act = act(C).  F.linear of CLIP/clip/auxilary.py:77,255 and CLIP/clip/model.py:175-177. */
+int mmx_linear(const float* A, int lda, const float* W, int ldw, const float* bias, const float* residual,
+               int ldres, float* C, int ldc, float* C_act, int act, int M, int N, int K, void* stream);
+/* dX[M,K] = (dY[M,N] * W[N,K]) (.) act'(pre[M,K])   given Wt = W^T stored [K,N]:  the dgrad of mmx_linear,
+ * optionally continued through the activation that PRODUCED this linear's input (pre = that activation's
+ * pre-activation; NULL = none).  The reference obtains it through torch.autograd (CLIP_explainability.ipynb:175). */
+int mmx_linear_dgrad(const float* dY, int lddy, const float* Wt, int ldwt, const float* pre, int ldpre, int act,
+                     float* dX, int lddx, int M, int N, int K, void* stream);
+
+/* LayerNorm over the last dim (eps 1e-5), optional row gather: out row r reads x row row_map[r].
+ * CLIP/clip/model.py:153-159.  mean/rstd ([rows]) are saved for the backward. */
+int mmx_layernorm_fwd(const float* x, int ldx, const int* row_map, const float* gamma, const float* beta,
+                      float* y, int ldy, float* mean, float* rstd, int rows, int D, float eps, void* stream);
+/* dx[out_row] = (residual_grad ? residual_grad[out_row] : 0) + LN'(dy; x, mean, rstd, gamma);
+ * out row = row_map ? row_map[r] : r (x is read at the same mapped row). */
+int mmx_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const int* row_map, const float* gamma,
+                      const float* mean, const float* rstd, const float* residual_grad, int ldres, float* dx,
+                      int lddx, int rows, int D, void* stream);
+
+#define MMX_ATTN_CAUSAL        1   /* additive -inf above the diagonal, CLIP/clip/model.py:334-340 */
+#define MMX_ATTN_SCALE_SCORES  2   /* scores/sqrt(d) after QK^T (lxmert_lrp.py:398-399); default: q scaled first
+                                      (CLIP/clip/auxilary.py:153) */
+
+/* A = softmax(scale * Q K^T + mask) staged to HBM, O = A V.   Q [B,T,H*hd] (ldq), K,V [B,S,H*hd] (ldk, ldv),
+ * key_bias [B,S] additive or NULL, A [B,H,T,S] row stride ldA, O [B,T,H*hd] (ldo).
+ * Replaces the bmm/softmax/bmm of CLIP/clip/auxilary.py:225-252, DETR/modules/layers.py:753-762,
+ * lxmert/lxmert/src/lxmert_lrp.py:398-414, including the "save A" hook sites (:247-250 / :758 / :407). */
+int mmx_attention_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
+                      const float* key_bias, float* A, int ldA, float* O, int ldo,
+                      int B, int H, int T, int S, int hd, float scale, int flags, void* stream);
+/* Backward from dO: dA = dO V^T staged to HBM (the tensor the reference captures with register_hook,
+ * CLIP/clip/auxilary.py:250), then dS = A (.) (dA - rowsum(dA (.) A)), dQ, dK, dV.  dQ/dK/dV may all be NULL
+ * (stop after dA).  delta: scratch [B,H,T]. */
+int mmx_attention_bwd(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk,
+                      const float* V, int ldv, const float* A, float* dA, int ldA, float* delta,
+                      float* dQ, int lddq, float* dK, int lddk, float* dV, int lddv,
+                      int B, int H, int T, int S, int hd, float scale, int flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * CLIP engine: the north-star path, one call = interpret() for a batch.
+ * ------------------------------------------------------------------------------------------------------- */
+
+typedef struct mmx_clip_config {
+  /* constructor arguments of the reference CLIP (CLIP/clip/model.py:249-262), ViT image tower */
+  int embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size;
+  int context_length, vocab_size, transformer_width, transformer_heads, transformer_layers;
+} mmx_clip_config;
+
+typedef struct mmx_clip mmx_clip;
+
+/* max_batch = largest number of (image,text) pairs processed in one pass; larger batches are micro-batched. */
+int mmx_clip_create(const mmx_clip_config* cfg, int max_batch, mmx_clip** out);
+void mmx_clip_destroy(mmx_clip* h);
+/* Load one tensor of the reference state_dict by its key (e.g. "visual.transformer.resblocks.0.attn.in_proj_weight",
+ * CLIP/clip/model.py:405-442).  data: HOST fp32, numel elements. */
+int mmx_clip_load_tensor(mmx_clip* h, const char* name, const float* data, size_t numel);
+/* Checks that every tensor was loaded and builds the derived copies (transposes for dgrad, TF32 hi/lo splits). */
+int mmx_clip_finalize(mmx_clip* h);
+
+/* interpret() (CLIP_explainability.ipynb:151-208).  images: [n_images,3,R,R] fp32 with n_images == B or 1 (the
+ * notebook's image.repeat, :153); tokens: [B,context] int32.  start_layer / start_layer_text as in the notebook
+ * (-1 = last block only).  R_text: [B,ctx,ctx], R_image: [B,S_v-1].  *_device: all pointers are device memory,
+ * work is enqueued on `stream` (NULL: the engine's own stream, synchronised before return).  *_host: pointers
+ * are host memory (pinned or pageable); copies happen inside the call, which returns after the results landed. */
+int mmx_clip_interpret_device(mmx_clip* h, const float* images, int n_images, const int32_t* tokens, int B,
+                              int start_layer, int start_layer_text, float* R_text, float* R_image, void* stream);
+int mmx_clip_interpret_host(mmx_clip* h, const float* images, int n_images, const int32_t* tokens, int B,
+                            int start_layer, int start_layer_text, float* R_text, float* R_image);
+
+/* Test taps: device pointers into the engine workspace after the last interpret (valid for batch <= max_batch,
+ * first micro-batch).  what: "A" / "dA" / "Abar" (tower 0 = vision, 1 = text, layer index), "logits" ([B,B]).
+ * Writes the pointer, the dims (up to 4) and the row stride of the last dim. */
+int mmx_clip_tap(mmx_clip* h, const char* what, int tower, int layer, const float** ptr, int dims[4], int* ld);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMX_H_ */

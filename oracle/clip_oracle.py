@@ -1,0 +1,253 @@
+"""Oracle restatement of the CLIP (ViT image tower + text tower) relevancy path.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Plain PyTorch + autograd on CPU.  It follows the
+reference line by line but is written functionally over a ``state_dict`` (same key names as the reference
+``CLIP`` module, CLIP/clip/model.py:248-303) so the same weights can be fed to the reference, to this oracle
+and to the CUDA engine.
+
+Reference lines followed:
+  * model forward ............ CLIP/clip/model.py:195-198 (block), :229-246 (vision), :349-362 (text), :364-378
+  * attention + hook site .... CLIP/clip/auxilary.py:72 (scaling), :153 (q*scaling), :194-198 (head split,
+                               index b*H+h), :225-244 (bmm, additive mask, softmax), :247-255
+  * causal mask .............. CLIP/clip/model.py:334-340
+  * interpret() .............. CLIP_explainability.ipynb:151-208 (cell 6)
+The only deliberate difference: the notebook calls ``torch.autograd.grad`` once per block; here all dA_l come
+from ONE ``autograd.grad`` call (same values).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .rules import avg_heads_batched
+
+
+@dataclass(frozen=True)
+class ClipConfig:
+    """Constructor arguments of the reference ``CLIP`` (CLIP/clip/model.py:249-262), ViT image tower only."""
+    embed_dim: int = 512
+    image_resolution: int = 224
+    vision_layers: int = 12
+    vision_width: int = 768
+    vision_patch_size: int = 32
+    context_length: int = 77
+    vocab_size: int = 49408
+    transformer_width: int = 512
+    transformer_heads: int = 8
+    transformer_layers: int = 12
+
+    @property
+    def vision_heads(self) -> int:  # CLIP/clip/model.py:276
+        return self.vision_width // 64
+
+    @property
+    def grid(self) -> int:
+        return self.image_resolution // self.vision_patch_size
+
+    @property
+    def vision_tokens(self) -> int:
+        return self.grid * self.grid + 1
+
+    def ref_args(self) -> Tuple[int, ...]:
+        return (self.embed_dim, self.image_resolution, self.vision_layers, self.vision_width,
+                self.vision_patch_size, self.context_length, self.vocab_size, self.transformer_width,
+                self.transformer_heads, self.transformer_layers)
+
+    def to_dict(self):
+        return asdict(self)
+
+
+VIT_B32 = ClipConfig()
+VIT_L14_336 = ClipConfig(768, 336, 24, 1024, 14, 77, 49408, 768, 12, 12)
+TINY = ClipConfig(32, 32, 2, 64, 16, 8, 64, 32, 2, 2)           # golden-fixture size
+SMALL = ClipConfig(64, 64, 3, 128, 16, 16, 512, 64, 2, 3)        # 17 vision tokens (odd), 16 text tokens
+
+
+def init_state_dict(cfg: ClipConfig, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Random-init weights with the distributions of the reference constructor + ``initialize_parameters``
+    (CLIP/clip/model.py:211-227 vision scale init, :305-332 text init; vision blocks keep
+    nn.MultiheadAttention / nn.Linear defaults).  Not bit-identical to the reference RNG order - weights are
+    always passed explicitly, so that does not matter."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def normal(*shape, std=1.0):
+        return torch.randn(*shape, generator=g, dtype=torch.float32) * std
+
+    def uniform(*shape, bound):
+        return (torch.rand(*shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+
+    W, Wt = cfg.vision_width, cfg.transformer_width
+    sc = W ** -0.5
+    sd["visual.conv1.weight"] = uniform(W, 3, cfg.vision_patch_size, cfg.vision_patch_size,
+                                        bound=1.0 / math.sqrt(3 * cfg.vision_patch_size ** 2))
+    sd["visual.class_embedding"] = normal(W, std=sc)
+    sd["visual.positional_embedding"] = normal(cfg.vision_tokens, W, std=sc)
+    sd["visual.proj"] = normal(W, cfg.embed_dim, std=sc)
+    for nm in ("visual.ln_pre", "visual.ln_post", "ln_final"):
+        d = Wt if nm == "ln_final" else W
+        # non-trivial affine so the LayerNorm gamma/beta paths are exercised by parity tests
+        sd[nm + ".weight"] = 1.0 + 0.1 * normal(d)
+        sd[nm + ".bias"] = 0.05 * normal(d)
+
+    def block(prefix, d, attn_std=None, proj_std=None, fc_std=None):
+        if attn_std is None:      # vision tower: torch defaults (xavier_uniform in_proj, kaiming-uniform Linear)
+            sd[prefix + "attn.in_proj_weight"] = uniform(3 * d, d, bound=math.sqrt(6.0 / (3 * d + d)))
+            sd[prefix + "attn.out_proj.weight"] = uniform(d, d, bound=1 / math.sqrt(d))
+            sd[prefix + "mlp.c_fc.weight"] = uniform(4 * d, d, bound=1 / math.sqrt(d))
+            sd[prefix + "mlp.c_proj.weight"] = uniform(d, 4 * d, bound=1 / math.sqrt(4 * d))
+        else:
+            sd[prefix + "attn.in_proj_weight"] = normal(3 * d, d, std=attn_std)
+            sd[prefix + "attn.out_proj.weight"] = normal(d, d, std=proj_std)
+            sd[prefix + "mlp.c_fc.weight"] = normal(4 * d, d, std=fc_std)
+            sd[prefix + "mlp.c_proj.weight"] = normal(d, 4 * d, std=proj_std)
+        sd[prefix + "attn.in_proj_bias"] = 0.02 * normal(3 * d)
+        sd[prefix + "attn.out_proj.bias"] = 0.02 * normal(d)
+        sd[prefix + "mlp.c_fc.bias"] = uniform(4 * d, bound=1 / math.sqrt(d))
+        sd[prefix + "mlp.c_proj.bias"] = uniform(d, bound=1 / math.sqrt(4 * d))
+        for ln in ("ln_1", "ln_2"):
+            sd[prefix + ln + ".weight"] = 1.0 + 0.1 * normal(d)
+            sd[prefix + ln + ".bias"] = 0.05 * normal(d)
+
+    for i in range(cfg.vision_layers):
+        block(f"visual.transformer.resblocks.{i}.", W)
+    proj_std = (Wt ** -0.5) * ((2 * cfg.transformer_layers) ** -0.5)
+    for i in range(cfg.transformer_layers):
+        block(f"transformer.resblocks.{i}.", Wt, attn_std=Wt ** -0.5, proj_std=proj_std,
+              fc_std=(2 * Wt) ** -0.5)
+    sd["token_embedding.weight"] = normal(cfg.vocab_size, Wt, std=0.02)
+    sd["positional_embedding"] = normal(cfg.context_length, Wt, std=0.01)
+    sd["text_projection"] = normal(Wt, cfg.embed_dim, std=Wt ** -0.5)
+    sd["logit_scale"] = torch.tensor(math.log(1 / 0.07), dtype=torch.float32)
+    return {k: v.to(dtype) for k, v in sd.items()}
+
+
+def synthetic_inputs(cfg: ClipConfig, batch: int, seed: int = 1234):
+    """Seeded synthetic batch: N(0,1) pixels; token rows ``[SOT, U{1..V-3}.., EOT, 0..]`` with
+    EOT the unique row maximum so ``argmax`` finds it (CLIP/clip/model.py:360)."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(batch, 3, cfg.image_resolution, cfg.image_resolution, generator=g)
+    sot, eot = cfg.vocab_size - 2, cfg.vocab_size - 1
+    tokens = torch.zeros(batch, cfg.context_length, dtype=torch.int64)
+    lo, hi = 1, max(2, cfg.context_length - 2)
+    for b in range(batch):
+        n = int(torch.randint(lo, hi + 1, (1,), generator=g))
+        tokens[b, 0] = sot
+        tokens[b, 1:1 + n] = torch.randint(1, cfg.vocab_size - 2, (n,), generator=g)
+        tokens[b, 1 + n] = eot
+    return images, tokens
+
+
+def _mha(x, sd, prefix, heads, mask, stage: List[torch.Tensor]):
+    """x: [S,B,D] (LND like the reference).  CLIP/clip/auxilary.py:26-262, self-attention branch."""
+    S, B, D = x.shape
+    hd = D // heads
+    qkv = F.linear(x, sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"])      # :77
+    q, k, v = qkv.chunk(3, dim=-1)
+    q = q * (float(hd) ** -0.5)                                                           # :72,:153
+    q = q.contiguous().view(S, B * heads, hd).transpose(0, 1)                             # :194
+    k = k.contiguous().view(S, B * heads, hd).transpose(0, 1)
+    v = v.contiguous().view(S, B * heads, hd).transpose(0, 1)
+    w = torch.bmm(q, k.transpose(1, 2))                                                   # :225
+    if mask is not None:
+        w = w + mask.unsqueeze(0)                                                         # :228-232
+    w = F.softmax(w, dim=-1)                                                              # :243
+    stage.append(w)                                                                       # hook site :247-250
+    o = torch.bmm(w, v)                                                                   # :252
+    o = o.transpose(0, 1).contiguous().view(S, B, D)
+    return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])     # :254-255
+
+
+def _tower(x, sd, prefix, layers, heads, mask, stage):
+    for i in range(layers):
+        p = f"{prefix}resblocks.{i}."
+        d = x.shape[-1]
+        h = F.layer_norm(x, (d,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"])
+        x = x + _mha(h, sd, p + "attn.", heads, mask, stage)                              # model.py:196
+        h = F.layer_norm(x, (d,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"])
+        f = F.linear(h, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"])
+        f = f * torch.sigmoid(1.702 * f)                                                  # QuickGELU model.py:162-164
+        x = x + F.linear(f, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])      # model.py:197
+    return x
+
+
+def clip_forward(sd, cfg: ClipConfig, images, tokens):
+    """Returns (logits_per_image [B,B], A_vision list of [B*H,S,S], A_text list of [B*H,77,77],
+    image_features, text_features)."""
+    W = cfg.vision_width
+    x = F.conv2d(images, sd["visual.conv1.weight"], stride=cfg.vision_patch_size)        # model.py:230
+    x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+    cls = sd["visual.class_embedding"] + torch.zeros(x.shape[0], 1, W, dtype=x.dtype)
+    x = torch.cat([cls, x], dim=1) + sd["visual.positional_embedding"]
+    x = F.layer_norm(x, (W,), sd["visual.ln_pre.weight"], sd["visual.ln_pre.bias"])
+    A_v: List[torch.Tensor] = []
+    x = _tower(x.permute(1, 0, 2), sd, "visual.transformer.", cfg.vision_layers, cfg.vision_heads, None, A_v)
+    x = x.permute(1, 0, 2)
+    x = F.layer_norm(x[:, 0, :], (W,), sd["visual.ln_post.weight"], sd["visual.ln_post.bias"])
+    img_f = x @ sd["visual.proj"]                                                         # model.py:243-244
+
+    Wt = cfg.transformer_width
+    mask = torch.full((cfg.context_length, cfg.context_length), float("-inf"), dtype=images.dtype).triu_(1)
+    t = F.embedding(tokens, sd["token_embedding.weight"]) + sd["positional_embedding"]   # model.py:350-352
+    A_t: List[torch.Tensor] = []
+    t = _tower(t.permute(1, 0, 2), sd, "transformer.", cfg.transformer_layers, cfg.transformer_heads, mask, A_t)
+    t = t.permute(1, 0, 2)
+    t = F.layer_norm(t, (Wt,), sd["ln_final.weight"], sd["ln_final.bias"])
+    txt_f = t[torch.arange(t.shape[0]), tokens.argmax(dim=-1)] @ sd["text_projection"]   # model.py:360
+    img_n = img_f / img_f.norm(dim=-1, keepdim=True)
+    txt_n = txt_f / txt_f.norm(dim=-1, keepdim=True)
+    logits = sd["logit_scale"].exp() * img_n @ txt_n.t()                                  # model.py:373-374
+    return logits, A_v, A_t, img_f, txt_f
+
+
+def clip_interpret(sd, cfg: ClipConfig, images, tokens, start_layer: int = -1, start_layer_text: int = -1,
+                   dtype=torch.float32, return_stages: bool = False):
+    """Restatement of ``interpret()`` (CLIP_explainability.ipynb:151-208) for B distinct images (or one image
+    repeated when ``images.shape[0] == 1``, :153).  Returns ``(text_relevance [B,77,77], image_relevance
+    [B,S-1])`` and, with ``return_stages``, a dict with logits, A_l, dA_l, Abar_l per tower."""
+    sd = {k: v.detach().to(dtype) for k, v in sd.items()}
+    B = tokens.shape[0]
+    images = images.to(dtype)
+    if images.shape[0] == 1 and B > 1:
+        images = images.repeat(B, 1, 1, 1)
+    logits, A_v, A_t, _, _ = _with_grad(sd, cfg, images, tokens)
+    one_hot = logits.diagonal().sum()                                                     # ipynb:156-160
+    grads = torch.autograd.grad(one_hot, A_v + A_t)
+    G_v, G_t = grads[:len(A_v)], grads[len(A_v):]
+
+    def rule(A, G, start):
+        L = len(A)
+        if start == -1:
+            start = L - 1                                                                 # ipynb:165-167
+        S = A[0].shape[-1]
+        R = torch.eye(S, dtype=dtype).unsqueeze(0).expand(B, S, S)
+        bars = {}
+        for i in range(L):
+            if i < start:
+                continue
+            cam = avg_heads_batched(A[i].detach(), G[i], B)                               # ipynb:176-181
+            bars[i] = cam
+            R = R + torch.bmm(cam, R)                                                     # ipynb:182
+        return R, bars
+
+    R_img, bars_v = rule(A_v, G_v, start_layer)
+    R_txt, bars_t = rule(A_t, G_t, start_layer_text)
+    out = (R_txt, R_img[:, 0, 1:])                                                        # ipynb:183,206-208
+    if return_stages:
+        stages = dict(logits=logits.detach(), A_v=[a.detach() for a in A_v], A_t=[a.detach() for a in A_t],
+                      G_v=list(G_v), G_t=list(G_t), bar_v=bars_v, bar_t=bars_t, R_img=R_img)
+        return out + (stages,)
+    return out
+
+
+def _with_grad(sd, cfg, images, tokens):
+    with torch.enable_grad():
+        # make the A_l differentiable leaves-of-interest: the graph needs at least one grad-requiring input
+        images = images.detach().requires_grad_(True)
+        sd = dict(sd)
+        sd["token_embedding.weight"] = sd["token_embedding.weight"].detach().requires_grad_(True)
+        return clip_forward(sd, cfg, images, tokens)

@@ -1,0 +1,111 @@
+"""Generate the committed golden fixtures under ``tests/golden/`` by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs ``/root/reference``)::
+
+    python -m oracle.make_golden
+
+The reference ships no known-answer tests for the relevancy path, so these fixtures - outputs of
+the reference's own code on seeded inputs - are what pins the oracle restatement (and, through it, the CUDA
+engine).  Fixtures hold inputs, weights (tiny configs only) and the reference outputs, so they can be checked
+on the GPU box where the reference tree does not exist.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+
+import numpy as np
+import torch
+
+from . import clip_oracle as co
+from . import ref_shims as rs
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _load_module(name, relpath):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(rs.REFERENCE_ROOT, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def golden_clip(tag, cfg, batch, wseed, iseed):
+    sd = co.init_state_dict(cfg, seed=wseed)
+    images, tokens = co.synthetic_inputs(cfg, batch, seed=iseed)
+    model = rs.build_reference_clip(cfg, sd)
+    out = {"cfg": np.array(cfg.ref_args(), dtype=np.int64), "images": images.numpy(), "tokens": tokens.numpy()}
+    for k, v in sd.items():
+        out["sd." + k] = v.numpy()
+    for sl in (-1, 0, 1):
+        # B distinct images == per-sample calls of the reference (its interpret() repeats ONE image,
+        # CLIP_explainability.ipynb:153; samples are independent because only diag logits are summed, :156-160)
+        rts, ris = [], []
+        for b in range(batch):
+            rt, ri = rs.reference_interpret(images[b:b + 1], tokens[b:b + 1], model, "cpu", sl, sl)
+            rts.append(rt.detach())
+            ris.append(ri.detach())
+        out[f"distinct.sl{sl}.R_text"] = torch.cat(rts).numpy()
+        out[f"distinct.sl{sl}.R_image"] = torch.cat(ris).numpy()
+        rt, ri = rs.reference_interpret(images[:1], tokens, model, "cpu", sl, sl)
+        out[f"repeat.sl{sl}.R_text"] = rt.detach().numpy()
+        out[f"repeat.sl{sl}.R_image"] = ri.detach().numpy()
+    lpi, _ = model(images, tokens)      # hooks need grad mode (CLIP/clip/auxilary.py:250)
+    out["logits_per_image"] = lpi.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, f"clip_{tag}.npz"), **out)
+    print("wrote", tag, {k: v.shape for k, v in out.items() if not k.startswith("sd.")})
+
+
+def golden_rules():
+    detr = _load_module("ref_detr_eg", "DETR/modules/ExplanationGenerator.py")
+    lx = _load_module("ref_lxmert_eg", "lxmert/lxmert/src/ExplanationGenerator.py")
+    g = torch.Generator().manual_seed(99)
+    out = {}
+    H, T, S = 4, 10, 13
+    cam_ss = torch.softmax(torch.randn(H, T, T, generator=g), -1)
+    grad_ss = torch.randn(H, T, T, generator=g)
+    cam_sq = torch.softmax(torch.randn(H, T, S, generator=g), -1)
+    grad_sq = torch.randn(H, T, S, generator=g)
+    out["cam_ss"], out["grad_ss"], out["cam_sq"], out["grad_sq"] = (x.numpy() for x in (cam_ss, grad_ss, cam_sq, grad_sq))
+    abar_ss = detr.avg_heads(cam_ss, grad_ss)
+    abar_sq = lx.avg_heads(cam_sq, grad_sq)
+    out["abar_ss"], out["abar_sq"] = abar_ss.numpy(), abar_sq.numpy()
+    # relevancy state after one self-attention update (so that R-I has a positive diagonal, as in the path)
+    R_ss = torch.eye(T) + abar_ss
+    R_qq = torch.eye(S) + detr.avg_heads(torch.softmax(torch.randn(H, S, S, generator=g), -1),
+                                         torch.randn(H, S, S, generator=g))
+    R_sq = 0.1 * torch.rand(T, S, generator=g)
+    R_qs = 0.1 * torch.rand(S, T, generator=g)
+    out["R_ss"], out["R_qq"], out["R_sq"], out["R_qs"] = (x.numpy() for x in (R_ss, R_qq, R_sq, R_qs))
+    a, b = detr.apply_self_attention_rules(R_ss, R_sq, abar_ss)
+    out["self.R_ss_add"], out["self.R_sq_add"] = a.numpy(), b.numpy()
+    out["hr.R_ss"] = detr.handle_residual(R_ss).numpy()
+    out["hr.R_qq"] = lx.handle_residual(R_qq).numpy()
+    for norm in (True, False):
+        for self10 in (True, False):
+            key = f"n{int(norm)}s{int(self10)}"
+            out[f"mm_detr.{key}"] = detr.apply_mm_attention_rules(
+                R_ss, R_qq, abar_sq.clone(), apply_normalization=norm, apply_self_in_rule_10=self10).numpy()
+            x, y = lx.apply_mm_attention_rules(R_ss, R_qq, R_qs, abar_sq.clone(), apply_normalization=norm,
+                                               apply_self_in_rule_10=self10)
+            out[f"mm_lx.{key}.sq"], out[f"mm_lx.{key}.ss"] = x.numpy(), y.numpy()
+    # NaN -> 0 guard (DETR only): a state with an all-zero R-I row gives 0/0 in handle_residual
+    out["mm_detr.identity_state"] = detr.apply_mm_attention_rules(torch.eye(T), torch.eye(S), abar_sq.clone()).numpy()
+    mats = [torch.softmax(torch.randn(T, T, generator=g), -1) for _ in range(5)]
+    out["rollout.mats"] = torch.stack(mats).numpy()
+    for sl in (0, 2):
+        out[f"rollout.sl{sl}"] = detr.compute_rollout_attention([m.clone() for m in mats], sl).numpy()
+    np.savez_compressed(os.path.join(OUT, "rules.npz"), **out)
+    print("wrote rules", len(out))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    golden_rules()
+    golden_clip("tiny", co.TINY, 3, wseed=1, iseed=7)
+    golden_clip("small", co.SMALL, 4, wseed=2, iseed=11)
+
+
+if __name__ == "__main__":
+    main()

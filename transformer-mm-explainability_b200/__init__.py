@@ -1,0 +1,20 @@
+"""mmx_b200 - B200-native (sm_100a) gradient-weighted attention-relevancy engine.
+
+Host-side mirror of the reference's Python API (hila-chefer/Transformer-MM-Explainability) over the C ABI of
+libmmx.so (include/mmx.h).  Names, argument meaning and error behaviour follow the reference:
+
+  * ``interpret(image, texts, model, device, start_layer=-1, start_layer_text=-1)``  - CLIP_explainability.ipynb cell 6
+  * ``avg_heads``, ``apply_self_attention_rules``, ``apply_mm_attention_rules``, ``handle_residual``,
+    ``compute_rollout_attention``  - DETR/modules/ExplanationGenerator.py:5-53, lxmert/lxmert/src/ExplanationGenerator.py:5-54
+
+All arithmetic runs in hand-written CUDA kernels; there is no CPU or PyTorch fallback (``MmxError`` is raised when
+the library is missing or no sm_100 GPU is present).
+"""
+from ._lib import MmxError, lib, LIB_PATH, exported_symbols  # noqa: F401
+from .rules import (avg_heads, avg_heads_batched, apply_self_attention_rules, apply_mm_attention_rules,  # noqa: F401
+                    apply_mm_attention_rules_lxmert, handle_residual, compute_rollout_attention, self_update)
+from .clip import ClipConfig, ClipEngine, interpret, VIT_B32, VIT_L14_336  # noqa: F401
+
+__all__ = ["MmxError", "lib", "interpret", "ClipEngine", "ClipConfig", "avg_heads", "avg_heads_batched",
+           "apply_self_attention_rules", "apply_mm_attention_rules", "apply_mm_attention_rules_lxmert",
+           "handle_residual", "compute_rollout_attention", "self_update", "VIT_B32", "VIT_L14_336"]

@@ -1,0 +1,28 @@
+// GEMM backends shared declarations.
+#pragma once
+#include "mmx_common.cuh"
+
+namespace mmx {
+
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N]: added first
+  const float* pre = nullptr;       // [M,N]: multiply by act'(pre)  (dgrad through an activation)
+  int ldpre = 0;
+  const float* residual = nullptr;  // [M,N]: added last
+  int ldres = 0;
+  float* C_act = nullptr;           // [M,N] (row stride ldc): also store act(C)
+  int act = MMX_ACT_NONE;
+};
+
+// C[M,N] = A[M,K] * Bt[N,K]^T, both operands K-major.
+int gemm_nt_simt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t st);
+
+// Backend dispatch (tcgen05 3xTF32 when the shape qualifies and the backend is enabled, else fp32 FFMA).
+// A_lo / Bt_lo: optional precomputed TF32 residual planes for the tcgen05 path (null = not available).
+int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+            const GemmEpilogue& ep, cudaStream_t st);
+
+int gemm_backend();
+
+}  // namespace mmx

@@ -1,0 +1,107 @@
+// Shared helpers for libmmx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <atomic>
+
+#include "../../include/mmx.h"
+
+namespace mmx {
+
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+int sm_count();
+
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define MMX_CHECK_CUDA(expr)                                                                     \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      ::mmx::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ +    \
+                       ":" + std::to_string(__LINE__) + ")");                                    \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
+#define MMX_REQUIRE(cond, msg)                                                                   \
+  do {                                                                                           \
+    if (!(cond)) {                                                                               \
+      ::mmx::set_error(std::string("requirement failed: ") + #cond + " - " + (msg));             \
+      return 2;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
+#define MMX_LAUNCH_CHECK()                                                                       \
+  do {                                                                                           \
+    ::mmx::count_launch();                                                                       \
+    cudaError_t _e = cudaPeekAtLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                     \
+      ::mmx::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e) + " (" +          \
+                       __FILE__ + ":" + std::to_string(__LINE__) + ")");                         \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
+#define MMX_TRY(expr)                                                                            \
+  do {                                                                                           \
+    int _r = (expr);                                                                             \
+    if (_r != 0) return _r;                                                                      \
+  } while (0)
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return cdiv(a, b) * b; }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// streaming 128-bit load that does not pollute L1 (data touched once)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case MMX_ACT_QUICKGELU: return x / (1.f + expf(-1.702f * x));
+    case MMX_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case MMX_ACT_RELU: return fmaxf(x, 0.f);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_bwd(float x, int act) {  // d act(x) / dx
+  switch (act) {
+    case MMX_ACT_QUICKGELU: {
+      float s = 1.f / (1.f + expf(-1.702f * x));
+      return s + 1.702f * x * s * (1.f - s);
+    }
+    case MMX_ACT_GELU: {
+      float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+      float pdf = 0.39894228040143268f * expf(-0.5f * x * x);
+      return cdf + x * pdf;
+    }
+    case MMX_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    default: return 1.f;
+  }
+}
+
+}  // namespace mmx

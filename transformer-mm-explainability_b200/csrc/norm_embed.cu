@@ -1,0 +1,287 @@
+// Row-wise kernels around the GEMMs: LayerNorm forward/backward (one warp per row), CLIP token assembly
+// (patch im2col, class/positional embedding, token embedding) and the logit head with its analytic backward.
+#include "mmx_common.cuh"
+
+namespace mmx {
+
+// ------------------------------------------------------------------ LayerNorm
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, int ldx,
+                                                            const int* __restrict__ row_map,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ y, int ldy, float* __restrict__ mean,
+                                                            float* __restrict__ rstd, int rows, int D, float eps) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* xr = x + (long long)(row_map ? row_map[r] : r) * ldx;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) s += xr[i];
+  const float mu = warp_sum(s) / (float)D;
+  float v = 0.f;
+  for (int i = lane; i < D; i += 32) { const float d = xr[i] - mu; v = fmaf(d, d, v); }
+  const float rs = rsqrtf(warp_sum(v) / (float)D + eps);
+  float* yr = y + (long long)r * ldy;
+  for (int i = lane; i < D; i += 32) yr[i] = (xr[i] - mu) * rs * gamma[i] + beta[i];
+  if (lane == 0) {
+    if (mean) mean[r] = mu;
+    if (rstd) rstd[r] = rs;
+  }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ residual_grad)
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, int lddy,
+                                                            const float* __restrict__ x, int ldx,
+                                                            const int* __restrict__ row_map,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            const float* __restrict__ resid, int ldres,
+                                                            float* __restrict__ dx, int lddx, int rows, int D) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const long long xrow = row_map ? row_map[r] : r;
+  const float* xr = x + xrow * ldx;
+  const float* dyr = dy + (long long)r * lddy;
+  const float mu = mean[r], rs = rstd[r];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float g = gamma[i] * dyr[i];
+    s1 += g;
+    s2 = fmaf(g, (xr[i] - mu) * rs, s2);
+  }
+  s1 = warp_sum(s1) / (float)D;
+  s2 = warp_sum(s2) / (float)D;
+  float* dxr = dx + xrow * lddx;
+  const float* rr = resid ? resid + xrow * ldres : nullptr;
+  for (int i = lane; i < D; i += 32) {
+    const float g = gamma[i] * dyr[i];
+    float v = rs * (g - s1 - (xr[i] - mu) * rs * s2);
+    if (rr) v += rr[i];
+    dxr[i] = v;
+  }
+}
+
+int layernorm_fwd(const float* x, int ldx, const int* row_map, const float* gamma, const float* beta, float* y, int ldy,
+                  float* mean, float* rstd, int rows, int D, float eps, cudaStream_t st) {
+  if (rows == 0) return 0;
+  layernorm_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, D, eps);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const int* row_map, const float* gamma,
+                  const float* mean, const float* rstd, const float* resid, int ldres, float* dx, int lddx, int rows, int D,
+                  cudaStream_t st) {
+  if (rows == 0) return 0;
+  layernorm_bwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(dy, lddy, x, ldx, row_map, gamma, mean, rstd, resid, ldres, dx, lddx,
+                                                      rows, D);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ CLIP vision tokens
+// images [n_img,3,R,R] -> patches [n_img*G*G, 3*p*p] in conv-weight order (c, i, j)  (CLIP/clip/model.py:230-232)
+__global__ void __launch_bounds__(256) im2col_patch_kernel(const float* __restrict__ img, float* __restrict__ out, int n_img,
+                                                           int R, int p, int G) {
+  const int K = 3 * p * p;
+  const long long total = (long long)n_img * G * G * K / 4;   // p % 4 == 0 -> float4 along j
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+    const long long e = it * 4;
+    const int k = (int)(e % K);
+    const long long row = e / K;
+    const int gx = (int)(row % G), gy = (int)((row / G) % G);
+    const long long n = row / ((long long)G * G);
+    const int j = k % p, i = (k / p) % p, c = k / (p * p);
+    const float* src = img + ((n * 3 + c) * R + (gy * p + i)) * (long long)R + gx * p + j;
+    *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<const float4*>(src);
+  }
+}
+__global__ void __launch_bounds__(256) im2col_patch_scalar_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                                  int n_img, int R, int p, int G) {
+  const int K = 3 * p * p;
+  const long long total = (long long)n_img * G * G * K;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % K);
+    const long long row = e / K;
+    const int gx = (int)(row % G), gy = (int)((row / G) % G);
+    const long long n = row / ((long long)G * G);
+    const int j = k % p, i = (k / p) % p, c = k / (p * p);
+    out[e] = img[((n * 3 + c) * R + (gy * p + i)) * (long long)R + gx * p + j];
+  }
+}
+
+// x[b,0,:] = cls + pos[0];  x[b,1+g,:] = patch_emb[(b % n_img)*G*G + g,:] + pos[1+g]  (CLIP/clip/model.py:233-234),
+// one warp per token row; the ln_pre that follows (:235) is fused: writes LN(x) only.
+__global__ void __launch_bounds__(256) vision_tokens_lnpre_kernel(const float* __restrict__ patch_emb, int n_img,
+                                                                  const float* __restrict__ cls, const float* __restrict__ pos,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float* __restrict__ x, int B, int S, int D, float eps) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= B * S) return;
+  const int b = r / S, s = r % S;
+  const float* src = (s == 0) ? cls : patch_emb + ((long long)(b % n_img) * (S - 1) + (s - 1)) * D;
+  const float* pr = pos + (long long)s * D;
+  float sum = 0.f;
+  for (int i = lane; i < D; i += 32) sum += src[i] + pr[i];
+  const float mu = warp_sum(sum) / (float)D;
+  float v = 0.f;
+  for (int i = lane; i < D; i += 32) { const float d = src[i] + pr[i] - mu; v = fmaf(d, d, v); }
+  const float rs = rsqrtf(warp_sum(v) / (float)D + eps);
+  float* xr = x + (long long)r * D;
+  for (int i = lane; i < D; i += 32) xr[i] = (src[i] + pr[i] - mu) * rs * gamma[i] + beta[i];
+}
+
+// text: x[b,s,:] = tok_emb[tokens[b,s]] + pos[s]   (CLIP/clip/model.py:350-352); eot[b] = first argmax_s tokens[b,s] (:360)
+__global__ void __launch_bounds__(256) text_embed_kernel(const int* __restrict__ tokens, const float* __restrict__ emb,
+                                                         const float* __restrict__ pos, float* __restrict__ x,
+                                                         int* __restrict__ eot_row, int B, int S, int D, int vocab) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= B * S) return;
+  const int b = r / S, s = r % S;
+  int tok = tokens[r];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+  const float* er = emb + (long long)tok * D;
+  const float* pr = pos + (long long)s * D;
+  float* xr = x + (long long)r * D;
+  for (int i = lane; i < D; i += 32) xr[i] = er[i] + pr[i];
+  if (s == 0) {
+    int best = -2147483647 - 1, bi = 0;
+    for (int j = lane; j < S; j += 32) {
+      const int t = tokens[b * S + j];
+      if (t > best) { best = t; bi = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) eot_row[b] = b * S + bi;
+  }
+}
+
+__global__ void cls_rows_kernel(int* __restrict__ rows, int B, int S) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) rows[b] = b * S;
+}
+
+// logits head (CLIP/clip/model.py:368-374) and its analytic backward for y = sum_b logits[b,b]
+// (CLIP_explainability.ipynb:156-160).  One warp per sample.
+//   fi_n = fi/|fi|, ft_n = ft/|ft|, c = <fi_n, ft_n>, logit = s*c,
+//   d fi = s/|fi| * (ft_n - c*fi_n),  d ft = s/|ft| * (fi_n - c*ft_n)
+__global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict__ fi, const float* __restrict__ ft,
+                                                        float logit_scale_exp, float* __restrict__ fin,
+                                                        float* __restrict__ ftn, float* __restrict__ dfi,
+                                                        float* __restrict__ dft, float* __restrict__ diag, int B, int E) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* a = fi + (long long)b * E;
+  const float* t = ft + (long long)b * E;
+  float sa = 0.f, stt = 0.f;
+  for (int i = lane; i < E; i += 32) { sa = fmaf(a[i], a[i], sa); stt = fmaf(t[i], t[i], stt); }
+  const float na = sqrtf(warp_sum(sa)), nt = sqrtf(warp_sum(stt));
+  float c = 0.f;
+  for (int i = lane; i < E; i += 32) c = fmaf(a[i] / na, t[i] / nt, c);
+  c = warp_sum(c);
+  for (int i = lane; i < E; i += 32) {
+    const float an = a[i] / na, tn = t[i] / nt;
+    fin[(long long)b * E + i] = an;
+    ftn[(long long)b * E + i] = tn;
+    dfi[(long long)b * E + i] = logit_scale_exp / na * (tn - c * an);
+    dft[(long long)b * E + i] = logit_scale_exp / nt * (an - c * tn);
+  }
+  if (lane == 0 && diag) diag[b] = logit_scale_exp * c;
+}
+
+__global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= s;
+}
+
+// R[b] = I (S x S, row stride ld, pads zero)
+__global__ void __launch_bounds__(256) eye_kernel(float* __restrict__ R, int B, int S, int ld) {
+  const long long n = (long long)B * S * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld);
+    const int r = (int)((i / ld) % S);
+    R[i] = (c == r) ? 1.f : 0.f;
+  }
+}
+
+// strided copy-out: dst[b, r, c] (dense rows x cols) = src[b, r0 + r, c0 + c] (row stride ld, plane stride plane)
+__global__ void __launch_bounds__(256) slice_out_kernel(const float* __restrict__ src, long long plane, int ld, int r0, int c0,
+                                                        float* __restrict__ dst, int B, int rows, int cols) {
+  const long long n = (long long)B * rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const int r = (int)((i / cols) % rows);
+    const long long b = i / ((long long)cols * rows);
+    dst[i] = src[b * plane + (long long)(r0 + r) * ld + c0 + c];
+  }
+}
+
+static int grid_for(long long items) {
+  long long g = (items + 255) / 256, cap = (long long)sm_count() * 8;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+int im2col_patches(const float* img, float* out, int n_img, int R, int p, cudaStream_t st) {
+  const int G = R / p;
+  const long long total = (long long)n_img * G * G * 3 * p * p;
+  if (total == 0) return 0;
+  if (p % 4 == 0 && R % 4 == 0 && aligned16(img) && aligned16(out))
+    im2col_patch_kernel<<<grid_for(total / 4), 256, 0, st>>>(img, out, n_img, R, p, G);
+  else
+    im2col_patch_scalar_kernel<<<grid_for(total), 256, 0, st>>>(img, out, n_img, R, p, G);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int vision_tokens_lnpre(const float* patch_emb, int n_img, const float* cls, const float* pos, const float* gamma,
+                        const float* beta, float* x, int B, int S, int D, float eps, cudaStream_t st) {
+  vision_tokens_lnpre_kernel<<<cdiv(B * S, 8), 256, 0, st>>>(patch_emb, n_img, cls, pos, gamma, beta, x, B, S, D, eps);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int text_embed(const int* tokens, const float* emb, const float* pos, float* x, int* eot_row, int B, int S, int D, int vocab,
+               cudaStream_t st) {
+  text_embed_kernel<<<cdiv(B * S, 8), 256, 0, st>>>(tokens, emb, pos, x, eot_row, B, S, D, vocab);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int cls_rows(int* rows, int B, int S, cudaStream_t st) {
+  cls_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(rows, B, S);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int clip_head(const float* fi, const float* ft, float lse, float* fin, float* ftn, float* dfi, float* dft, float* diag, int B,
+              int E, cudaStream_t st) {
+  clip_head_kernel<<<cdiv(B, 8), 256, 0, st>>>(fi, ft, lse, fin, ftn, dfi, dft, diag, B, E);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int scale_inplace(float* x, long long n, float s, cudaStream_t st) {
+  scale_kernel<<<grid_for(n), 256, 0, st>>>(x, n, s);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int set_eye(float* R, int B, int S, int ld, cudaStream_t st) {
+  eye_kernel<<<grid_for((long long)B * S * ld), 256, 0, st>>>(R, B, S, ld);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int slice_out(const float* src, long long plane, int ld, int r0, int c0, float* dst, int B, int rows, int cols,
+              cudaStream_t st) {
+  slice_out_kernel<<<grid_for((long long)B * rows * cols), 256, 0, st>>>(src, plane, ld, r0, c0, dst, B, rows, cols);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmx
+
+using namespace mmx;
+extern "C" {
+int mmx_layernorm_fwd(const float* x, int ldx, const int* row_map, const float* gamma, const float* beta, float* y, int ldy,
+                      float* mean, float* rstd, int rows, int D, float eps, void* stream) {
+  return layernorm_fwd(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, D, eps, (cudaStream_t)stream);
+}
+int mmx_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const int* row_map, const float* gamma,
+                      const float* mean, const float* rstd, const float* residual_grad, int ldres, float* dx, int lddx,
+                      int rows, int D, void* stream) {
+  return layernorm_bwd(dy, lddy, x, ldx, row_map, gamma, mean, rstd, residual_grad, ldres, dx, lddx, rows, D,
+                       (cudaStream_t)stream);
+}
+}

@@ -1,0 +1,130 @@
+"""Reference-named rule functions (torch CUDA tensors in, torch CUDA tensors out) over the libmmx rule kernels.
+
+Signatures mirror DETR/modules/ExplanationGenerator.py:5-53 and lxmert/lxmert/src/ExplanationGenerator.py:5-54.
+Inputs must be fp32 CUDA tensors; nothing is computed by PyTorch - it only owns the memory and the stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import lib, check, ptr, current_stream, MmxError
+
+MM_NORMALIZE, MM_SELF_IN_10, MM_NAN_TO_ZERO = 1, 2, 4
+
+
+def _prep(t: torch.Tensor) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise MmxError("mmx_b200 rule functions need CUDA tensors (no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def avg_heads_batched(cam: torch.Tensor, grad: torch.Tensor, batch: int) -> torch.Tensor:
+    """Rule 5 for a batch; cam/grad [batch*H, T, S] or [batch, H, T, S] (head index b*H+h,
+    CLIP_explainability.ipynb:176-181).  Returns [batch, T, S]."""
+    cam, grad = _prep(cam), _prep(grad)
+    T, S = cam.shape[-2], cam.shape[-1]
+    H = cam.numel() // (batch * T * S)
+    out = torch.empty(batch, T, S, device=cam.device, dtype=torch.float32)
+    check(lib().mmx_avg_heads(ptr(cam), ptr(grad), ptr(out), batch, H, T, S, S, S, current_stream()))
+    return out
+
+
+def avg_heads(cam: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
+    """Rule 5 (DETR/modules/ExplanationGenerator.py:19-24): all leading dims are heads of ONE sample."""
+    return avg_heads_batched(cam, grad, 1)[0]
+
+
+def self_update(R_ss: torch.Tensor, cam_ss: torch.Tensor, R_sq: torch.Tensor | None = None):
+    """Fused rules 6+7 including the caller's ``+=``: returns (R_ss + cam*R_ss, R_sq + cam*R_sq).  Accepts [S,S] or
+    batched [B,S,S]."""
+    squeeze = R_ss.dim() == 2
+    R = _prep(R_ss if not squeeze else R_ss.unsqueeze(0))
+    Ab = _prep(cam_ss if not squeeze else cam_ss.unsqueeze(0))
+    B, S = R.shape[0], R.shape[-1]
+    out = torch.empty_like(R)
+    Rq = outq = None
+    Q = 0
+    if R_sq is not None:
+        Rq = _prep(R_sq if not squeeze else R_sq.unsqueeze(0))
+        Q = Rq.shape[-1]
+        outq = torch.empty_like(Rq)
+    check(lib().mmx_self_update(ptr(Ab), S, ptr(R), ptr(out), S, ptr(Rq), ptr(outq), max(Q, 1), B, S, Q, current_stream()))
+    if squeeze:
+        return out[0], (outq[0] if outq is not None else None)
+    return out, outq
+
+
+def apply_self_attention_rules(R_ss, R_sq, cam_ss):
+    """Rules 6+7, reference signature and return order ``(R_ss_addition, R_sq_addition)``
+    (DETR/modules/ExplanationGenerator.py:27-30)."""
+    R, Rq, Ab = _prep(R_ss).unsqueeze(0), _prep(R_sq).unsqueeze(0), _prep(cam_ss).unsqueeze(0)
+    S, Q = R.shape[-1], Rq.shape[-1]
+    add_ss = torch.empty_like(R)
+    add_sq = torch.empty_like(Rq)
+    l = lib()
+    check(l.mmx_bmm_add(ptr(Ab), S, S * S, 0, ptr(R), S, S * S, None, 0, 0, ptr(add_ss), S, S * S, 1, S, S, S, current_stream()))
+    check(l.mmx_bmm_add(ptr(Ab), S, S * S, 0, ptr(Rq), Q, S * Q, None, 0, 0, ptr(add_sq), Q, S * Q, 1, S, Q, S, current_stream()))
+    return add_ss[0], add_sq[0]
+
+
+def handle_residual(orig_self_attention: torch.Tensor) -> torch.Tensor:
+    """Eq. 8-9 (DETR/modules/ExplanationGenerator.py:46-53), including the reference's
+    ``assert diag(R - I).min() >= 0`` (one host sync, like the reference)."""
+    R = _prep(orig_self_attention)
+    squeeze = R.dim() == 2
+    if squeeze:
+        R = R.unsqueeze(0)
+    B, S = R.shape[0], R.shape[-1]
+    out = torch.empty_like(R)
+    md = torch.empty(1, device=R.device, dtype=torch.float32)
+    check(lib().mmx_handle_residual(ptr(R), ptr(out), S, B, S, ptr(md), current_stream()))
+    assert md.item() >= 0
+    return out[0] if squeeze else out
+
+
+def _mm(R_ss, R_qq, R_qs, cam_sq, flags):
+    Rs, Rq, Ab = _prep(R_ss).unsqueeze(0), _prep(R_qq).unsqueeze(0), _prep(cam_sq).unsqueeze(0)
+    T, S = Rs.shape[-1], Rq.shape[-1]
+    l = lib()
+    ws = torch.empty(l.mmx_mm_update_workspace(1, T, S) // 4 + 4, device=Rs.device, dtype=torch.float32)
+    sq_add = torch.empty(1, T, S, device=Rs.device, dtype=torch.float32)
+    Rqs = ss_add = None
+    if R_qs is not None:
+        Rqs = _prep(R_qs).unsqueeze(0)
+        ss_add = torch.empty(1, T, T, device=Rs.device, dtype=torch.float32)
+    md = torch.zeros(2, device=Rs.device, dtype=torch.float32)
+    check(l.mmx_mm_update(ptr(Rs), T, ptr(Rq), S, ptr(Rqs), T, ptr(Ab), S, ptr(sq_add), S, ptr(ss_add), T, 1, T, S, flags,
+                          ptr(ws), ptr(md), current_stream()))
+    if (flags & MM_NORMALIZE) and (flags & MM_SELF_IN_10):
+        assert md.min().item() >= 0          # the reference's assert in handle_residual
+    return sq_add[0], (ss_add[0] if ss_add is not None else None)
+
+
+def apply_mm_attention_rules(R_ss, R_qq, cam_sq, apply_normalization=True, apply_self_in_rule_10=True):
+    """Rule 10, DETR form (DETR/modules/ExplanationGenerator.py:33-43): returns ``R_sq_addition`` with NaN -> 0."""
+    flags = MM_NAN_TO_ZERO | (MM_NORMALIZE if apply_normalization else 0) | (MM_SELF_IN_10 if apply_self_in_rule_10 else 0)
+    return _mm(R_ss, R_qq, None, cam_sq, flags)[0]
+
+
+def apply_mm_attention_rules_lxmert(R_ss, R_qq, R_qs, cam_sq, apply_normalization=True, apply_self_in_rule_10=True):
+    """Rules 10+11, LXMERT form (lxmert/lxmert/src/ExplanationGenerator.py:32-42): returns
+    ``(R_sq_addition, R_ss_addition)``; no NaN guard."""
+    flags = (MM_NORMALIZE if apply_normalization else 0) | (MM_SELF_IN_10 if apply_self_in_rule_10 else 0)
+    return _mm(R_ss, R_qq, R_qs, cam_sq, flags)
+
+
+def compute_rollout_attention(all_layer_matrices, start_layer=0, normalize=True):
+    """Rollout (DETR/modules/ExplanationGenerator.py:5-16).  Matrices [S,S] (DETR/LXMERT form) or [B,S,S]
+    (VisualBERT form, which passes ``normalize=False``)."""
+    mats = torch.stack([_prep(m) for m in all_layer_matrices])
+    squeeze = mats.dim() == 3
+    if squeeze:
+        mats = mats.unsqueeze(1)
+    L, B, S = mats.shape[0], mats.shape[1], mats.shape[-1]
+    mats = mats.contiguous()
+    out = torch.empty(B, S, S, device=mats.device, dtype=torch.float32)
+    ws = torch.empty(2, B, S, S, device=mats.device, dtype=torch.float32)
+    check(lib().mmx_rollout(ptr(mats), L, B, S, start_layer, 1 if normalize else 0, ptr(out), ptr(ws), current_stream()))
+    return out[0] if squeeze else out
