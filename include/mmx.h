@@ -34,6 +34,13 @@ uint64_t mmx_launch_count(void);
 /* Selects the GEMM backend for the transformer linears: 0 = fp32 FFMA (bisecting reference),
  * 1 = tcgen05 3xTF32 (default when available).  Returns the backend in effect. */
 int mmx_set_gemm_backend(int backend);
+/* Per-launch CUDA-event timing of the transformer GEMMs (the dominant kernel): enable=1 opens a window, enable=0
+ * closes it; the report synchronises the device and returns the summed launch durations, the algorithmic FLOPs
+ * (2*M*N*K per launch) and the launch count of the window.  Used by bench.py for the roofline line. */
+int mmx_profile_gemm(int enable);
+int mmx_profile_gemm_report(double* total_ms, double* total_flops, int* launches);
+/* Device-to-device copy on `stream` (used by the test taps; avoids a second CUDA runtime binding on the host side). */
+int mmx_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Rule kernels

@@ -205,7 +205,7 @@ def clip_forward(sd, cfg: ClipConfig, images, tokens):
 
 
 def clip_interpret(sd, cfg: ClipConfig, images, tokens, start_layer: int = -1, start_layer_text: int = -1,
-                   dtype=torch.float32, return_stages: bool = False):
+                   dtype=torch.float32, return_stages: bool = False, per_layer_grad: bool = False):
     """Restatement of ``interpret()`` (CLIP_explainability.ipynb:151-208) for B distinct images (or one image
     repeated when ``images.shape[0] == 1``, :153).  Returns ``(text_relevance [B,77,77], image_relevance
     [B,S-1])`` and, with ``return_stages``, a dict with logits, A_l, dA_l, Abar_l per tower."""
@@ -216,8 +216,16 @@ def clip_interpret(sd, cfg: ClipConfig, images, tokens, start_layer: int = -1, s
         images = images.repeat(B, 1, 1, 1)
     logits, A_v, A_t, _, _ = _with_grad(sd, cfg, images, tokens)
     one_hot = logits.diagonal().sum()                                                     # ipynb:156-160
-    grads = torch.autograd.grad(one_hot, A_v + A_t)
-    G_v, G_t = grads[:len(A_v)], grads[len(A_v):]
+    if per_layer_grad:
+        # cost-faithful mode for the CPU baseline: one autograd.grad per relevant block, exactly the notebook's
+        # access pattern (ipynb:175,198); same values as the single call below
+        sv = cfg.vision_layers - 1 if start_layer == -1 else start_layer
+        stx = cfg.transformer_layers - 1 if start_layer_text == -1 else start_layer_text
+        G_v = [torch.autograd.grad(one_hot, [a], retain_graph=True)[0] if i >= sv else None for i, a in enumerate(A_v)]
+        G_t = [torch.autograd.grad(one_hot, [a], retain_graph=True)[0] if i >= stx else None for i, a in enumerate(A_t)]
+    else:
+        grads = torch.autograd.grad(one_hot, A_v + A_t)
+        G_v, G_t = grads[:len(A_v)], grads[len(A_v):]
 
     def rule(A, G, start):
         L = len(A)

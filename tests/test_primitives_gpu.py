@@ -42,23 +42,24 @@ def test_linear_and_dgrad(L, backend, M, N, K):
             Ca = torch.empty(M, N, device="cuda") if act else None
             check(lib.mmx_linear(ptr(Ad), K, ptr(Wd), K, ptr(bd), ptr(rd), N, ptr(Cd), N, ptr(Ca), act, M, N, K, st()))
             ref = (A.double() @ W.double().t() + bias.double() + res.double())
-            assert rel_err(Cd, ref) < 2e-6
+            assert rel_err(Cd, ref) < 5e-6
             if act:
-                assert rel_err(Ca, ACTS[act](ref)) < 2e-6
+                assert rel_err(Ca, ACTS[act](ref)) < 5e-6
         # dgrad through an activation: dX = (dY W) . act'(pre)
         dY = torch.randn(M, N, generator=gen)
         pre = torch.randn(M, K, generator=gen)
         Wt = W.t().contiguous()
+        dYd, Wtd, pred = dY.cuda(), Wt.cuda(), pre.cuda()      # keep device tensors alive across the call
         for act in (0, 1, 2, 3):
             dX = torch.empty(M, K, device="cuda")
-            check(lib.mmx_linear_dgrad(ptr(dY.cuda()), N, ptr(Wt.cuda()), N, ptr(pre.cuda()) if act else None, K, act,
+            check(lib.mmx_linear_dgrad(ptr(dYd), N, ptr(Wtd), N, ptr(pred) if act else None, K, act,
                                        ptr(dX), K, M, N, K, st()))
             p = pre.double().requires_grad_(True)
             y = ACTS[act](p) @ W.double().t()
             y.backward(dY.double())
             base = dY.double() @ W.double()
             ref = p.grad if act else base
-            assert rel_err(dX, ref, base=base) < 2e-6
+            assert rel_err(dX, ref, base=base) < 5e-6      # fp32 accumulation over up to 3072 terms
     finally:
         lib.mmx_set_gemm_backend(1)
 
@@ -72,27 +73,28 @@ def test_layernorm_fwd_bwd(L, rows, D):
     b = 0.1 * torch.randn(D, generator=gen)
     dy = torch.randn(rows, D, generator=gen)
     resid = torch.randn(rows, D, generator=gen)
-    xd = x.cuda()
+    xd, gd, bd, dyd, resd = x.cuda(), g.cuda(), b.cuda(), dy.cuda(), resid.cuda()   # kept alive across the calls
     y = torch.empty_like(xd); mean = torch.empty(rows, device="cuda"); rstd = torch.empty(rows, device="cuda")
-    check(lib.mmx_layernorm_fwd(ptr(xd), D, None, ptr(g.cuda()), ptr(b.cuda()), ptr(y), D, ptr(mean), ptr(rstd), rows, D,
+    check(lib.mmx_layernorm_fwd(ptr(xd), D, None, ptr(gd), ptr(bd), ptr(y), D, ptr(mean), ptr(rstd), rows, D,
                                 C.c_float(1e-5), st()))
     xr = x.double().requires_grad_(True)
     yr = F.layer_norm(xr, (D,), g.double(), b.double(), 1e-5)
     assert rel_err(y, yr.detach()) < 2e-6
     yr.backward(dy.double())
     dx = torch.empty_like(xd)
-    check(lib.mmx_layernorm_bwd(ptr(dy.cuda()), D, ptr(xd), D, None, ptr(g.cuda()), ptr(mean), ptr(rstd), ptr(resid.cuda()),
+    check(lib.mmx_layernorm_bwd(ptr(dyd), D, ptr(xd), D, None, ptr(gd), ptr(mean), ptr(rstd), ptr(resd),
                                 D, ptr(dx), D, rows, D, st()))
     assert rel_err(dx, xr.grad + resid.double()) < 2e-6
     # gathered rows (the pooled cls / eot token): output row r reads x[row_map[r]], dx scatters back to it
     if rows >= 3:
         rm = torch.tensor([rows - 1, 0, rows // 2], dtype=torch.int32)
+        rmd, dy3 = rm.cuda(), dy[:3].contiguous().cuda()
         yg = torch.empty(3, D, device="cuda"); mg = torch.empty(3, device="cuda"); rg = torch.empty(3, device="cuda")
-        check(lib.mmx_layernorm_fwd(ptr(xd), D, ptr(rm.cuda()), ptr(g.cuda()), ptr(b.cuda()), ptr(yg), D, ptr(mg), ptr(rg), 3,
+        check(lib.mmx_layernorm_fwd(ptr(xd), D, ptr(rmd), ptr(gd), ptr(bd), ptr(yg), D, ptr(mg), ptr(rg), 3,
                                     D, C.c_float(1e-5), st()))
         assert rel_err(yg, yr.detach()[rm.long()]) < 2e-6
         dxs = torch.zeros_like(xd)
-        check(lib.mmx_layernorm_bwd(ptr(dy[:3].cuda()), D, ptr(xd), D, ptr(rm.cuda()), ptr(g.cuda()), ptr(mg), ptr(rg), None,
+        check(lib.mmx_layernorm_bwd(ptr(dy3), D, ptr(xd), D, ptr(rmd), ptr(gd), ptr(mg), ptr(rg), None,
                                     0, ptr(dxs), D, 3, D, st()))
         x2 = x.double().requires_grad_(True)
         F.layer_norm(x2, (D,), g.double(), b.double(), 1e-5)[rm.long()].backward(dy[:3].double())
@@ -133,9 +135,10 @@ def test_attention_fwd_bwd(L, B, H, T, S, hd, causal, bias, ss):
     scale = 1.0 / math.sqrt(hd)
     flags = (1 if causal else 0) | (2 if ss else 0)
     ldA = (S + 3) // 4 * 4
-    qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
+    qd, kd, vd, dOd = q.cuda(), k.cuda(), v.cuda(), dO.cuda()
+    kbd = kb.cuda() if bias else None
     A = torch.full((B, H, T, ldA), 7.0, device="cuda"); O = torch.empty(B, T, Dm, device="cuda")
-    check(lib.mmx_attention_fwd(ptr(qd), Dm, ptr(kd), Dm, ptr(vd), Dm, ptr(kb.cuda()) if bias else None, ptr(A), ldA, ptr(O), Dm,
+    check(lib.mmx_attention_fwd(ptr(qd), Dm, ptr(kd), Dm, ptr(vd), Dm, ptr(kbd), ptr(A), ldA, ptr(O), Dm,
                                 B, H, T, S, hd, C.c_float(scale), flags, st()))
     q64, k64, v64 = (t.double().requires_grad_(True) for t in (q, k, v))
     Ar, Or = _attn_ref(q64, k64, v64, H, scale, causal, kb.double() if bias else None, ss)
@@ -145,13 +148,13 @@ def test_attention_fwd_bwd(L, B, H, T, S, hd, causal, bias, ss):
     Or.backward(dO.double())
     dA = torch.full((B, H, T, ldA), 7.0, device="cuda"); delta = torch.empty(B, H, T, device="cuda")
     dq, dk, dv = (torch.empty_like(t) for t in (qd, kd, vd))
-    check(lib.mmx_attention_bwd(ptr(dO.cuda()), Dm, ptr(qd), Dm, ptr(kd), Dm, ptr(vd), Dm, ptr(A), ptr(dA), ldA, ptr(delta),
+    check(lib.mmx_attention_bwd(ptr(dOd), Dm, ptr(qd), Dm, ptr(kd), Dm, ptr(vd), Dm, ptr(A), ptr(dA), ldA, ptr(delta),
                                 ptr(dq), Dm, ptr(dk), Dm, ptr(dv), Dm, B, H, T, S, hd, C.c_float(scale), flags, st()))
     assert rel_err(dA[..., :S], Ar.grad) < 2e-6          # the tensor the reference's backward hook captures
     assert (dA[..., S:] == 0).all()
     assert rel_err(dq, q64.grad) < 5e-6 and rel_err(dk, k64.grad) < 5e-6 and rel_err(dv, v64.grad) < 5e-6
     # stop-after-dA form (last relevant block)
     dA2 = torch.empty_like(dA)
-    check(lib.mmx_attention_bwd(ptr(dO.cuda()), Dm, ptr(qd), Dm, ptr(kd), Dm, ptr(vd), Dm, ptr(A), ptr(dA2), ldA, None,
+    check(lib.mmx_attention_bwd(ptr(dOd), Dm, ptr(qd), Dm, ptr(kd), Dm, ptr(vd), Dm, ptr(A), ptr(dA2), ldA, None,
                                 None, 0, None, 0, None, 0, B, H, T, S, hd, C.c_float(scale), flags, st()))
     assert torch.equal(dA2, dA)

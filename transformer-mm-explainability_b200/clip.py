@@ -140,9 +140,8 @@ class ClipEngine:
             n_lead *= d
         flat = torch.empty(n_lead * ld.value, device=self.device, dtype=torch.float32)
         torch.cuda.synchronize(self.device)
-        err = torch.cuda.cudart().cudaMemcpy(flat.data_ptr(), p.value, flat.numel() * 4, 3)
-        if int(err) != 0:
-            raise MmxError(f"cudaMemcpy failed: {err}")
+        check(self._lib.mmx_memcpy_d2d(ptr(flat), p, flat.numel() * 4, current_stream()))
+        torch.cuda.synchronize(self.device)
         return flat.view(n_lead, ld.value)[:, :shape[-1]].reshape(shape).clone()
 
 

@@ -1,6 +1,7 @@
 // GEMM backend dispatch + the exported linear / linear_dgrad entry points and library-wide state.
 #include "gemm.cuh"
 #include <mutex>
+#include <vector>
 
 namespace mmx {
 
@@ -35,14 +36,42 @@ int gemm_backend() {
   return b;
 }
 
-int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
-            const GemmEpilogue& ep, cudaStream_t st) {
+static int gemm_nt_impl(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+                        const GemmEpilogue& ep, cudaStream_t st) {
   if (gemm_backend() == 1) {
     bool taken = false;
     MMX_TRY(gemm_nt_tc(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st, &taken));
     if (taken) return 0;
   }
   return gemm_nt_simt(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
+}
+
+// Optional per-launch CUDA-event timing of the GEMMs (the dominant kernel) for bench.py's roofline line.
+struct ProfRec { cudaEvent_t s, e; double flops; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;       // records of the current profiling window
+static std::vector<cudaEvent_t> g_pool;   // reusable events
+static std::atomic<int> g_prof_on{0};
+
+int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+            const GemmEpilogue& ep, cudaStream_t st) {
+  if (!g_prof_on.load(std::memory_order_relaxed) || M == 0 || N == 0)
+    return gemm_nt_impl(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
+  ProfRec r;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (cudaEvent_t* ev : {&r.s, &r.e}) {
+      if (!g_pool.empty()) { *ev = g_pool.back(); g_pool.pop_back(); }
+      else MMX_CHECK_CUDA(cudaEventCreate(ev));
+    }
+  }
+  r.flops = 2.0 * (double)M * (double)N * (double)K;
+  MMX_CHECK_CUDA(cudaEventRecord(r.s, st));
+  MMX_TRY(gemm_nt_impl(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st));
+  MMX_CHECK_CUDA(cudaEventRecord(r.e, st));
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  return 0;
 }
 
 }  // namespace mmx
@@ -56,6 +85,35 @@ int mmx_set_gemm_backend(int backend) {
   if (backend == 1 && !gemm_tc_available()) backend = 0;
   g_backend.store(backend ? 1 : 0);
   return g_backend.load();
+}
+
+int mmx_profile_gemm(int enable) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (enable) {
+    for (ProfRec& r : g_prof) { g_pool.push_back(r.s); g_pool.push_back(r.e); }
+    g_prof.clear();
+  }
+  g_prof_on.store(enable ? 1 : 0);
+  return 0;
+}
+int mmx_profile_gemm_report(double* total_ms, double* total_flops, int* launches) {
+  MMX_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0, fl = 0;
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    MMX_CHECK_CUDA(cudaEventElapsedTime(&t, r.s, r.e));
+    ms += t; fl += r.flops;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (int)g_prof.size();
+  return 0;
+}
+
+int mmx_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+  MMX_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
 }
 
 int mmx_linear(const float* A, int lda, const float* W, int ldw, const float* bias, const float* residual, int ldres, float* C,

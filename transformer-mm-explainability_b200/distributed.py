@@ -1,0 +1,61 @@
+"""Multi-GPU sharding of the relevancy path: one process per GPU, per-sample units sharded contiguously across
+ranks (weights replicated), no data-path collective, ONE all-gather of the final maps.
+
+The reference has no multi-GPU relevancy path (its runs are single-GPU, batch 1); per-sample independence follows
+from the objective being the sum of the DIAGONAL logits only (CLIP_explainability.ipynb:156-160)."""
+from __future__ import annotations
+
+from typing import Callable, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of n units for `rank`; the first n % world ranks get one extra unit."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_maps(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather of per-sample maps [n_local, ...] -> [n_total, ...] in rank order.  Equal shards use a single
+    all_gather_into_tensor (NCCL: one ncclAllGather); ragged shards are padded to the largest shard."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    counts = [hi - lo for lo, hi in sizes]
+    assert local.shape[0] == counts[rank], (local.shape, counts, rank)
+    if world == 1:
+        return local
+    mx = max(counts)
+    tail = local.shape[1:]
+    if min(counts) == mx:
+        out = torch.empty((world * mx,) + tuple(tail), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    padded = torch.zeros((mx,) + tuple(tail), dtype=local.dtype, device=local.device)
+    padded[:counts[rank]] = local
+    out = torch.empty((world * mx,) + tuple(tail), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(world)], dim=0)
+
+
+def interpret_sharded(interpret_fn: Callable, images: torch.Tensor, tokens: torch.Tensor, start_layer: int = -1,
+                      start_layer_text: int = -1, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Every rank holds the same global batch; rank r computes samples shard_range(B, r, world) with
+    ``interpret_fn(images, tokens, start_layer, start_layer_text)`` (e.g. ``engine.interpret``) and all ranks
+    receive the full ``(R_text [B,ctx,ctx], R_image [B,S-1])``."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = tokens.shape[0]
+    lo, hi = shard_range(B, rank, world)
+    img = images if images.shape[0] == 1 else images[lo:hi]
+    if hi > lo:
+        rt, ri = interpret_fn(img, tokens[lo:hi], start_layer, start_layer_text)
+    else:   # more ranks than samples: contribute an empty shard with the right trailing shape
+        rt0, ri0 = interpret_fn(images[:1], tokens[:1], start_layer, start_layer_text)
+        rt, ri = rt0[:0], ri0[:0]
+    if world == 1:
+        return rt, ri
+    return all_gather_maps(rt, B, group), all_gather_maps(ri, B, group)
