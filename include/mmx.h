@@ -161,7 +161,7 @@ void mmx_clip_destroy(mmx_clip* h);
 /* Load one tensor of the reference state_dict by its key (e.g. "visual.transformer.resblocks.0.attn.in_proj_weight",
  * CLIP/clip/model.py:405-442).  data: HOST fp32, numel elements. */
 int mmx_clip_load_tensor(mmx_clip* h, const char* name, const float* data, size_t numel);
-/* Checks that every tensor was loaded and builds the derived copies (transposes for dgrad, TF32 hi/lo splits). */
+/* Checks that every tensor was loaded and builds the derived copies (transposed weights for the dgrad GEMMs). */
 int mmx_clip_finalize(mmx_clip* h);
 
 /* interpret() (CLIP_explainability.ipynb:151-208).  images: [n_images,3,R,R] fp32 with n_images == B or 1 (the

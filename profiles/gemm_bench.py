@@ -1,0 +1,55 @@
+"""Micro-benchmark of the linear GEMM through the C ABI (both backends) on the CLIP ViT-B/32 batch-64 shapes.
+usage (GPU box): python profiles/gemm_bench.py"""
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mmx_b200  # noqa: E402
+from mmx_b200._lib import lib, check, ptr, current_stream  # noqa: E402
+
+SHAPES = [(3200, 2304, 768), (3200, 768, 768), (3200, 3072, 768), (3200, 768, 3072),
+          (4928, 1536, 512), (4928, 512, 512), (4928, 2048, 512), (4928, 512, 2048), (3136, 768, 3072)]
+
+
+def main():
+    l = lib()
+    out = []
+    global SHAPES
+    backends = (0, 1)
+    if "--only" in sys.argv:            # e.g. --only 3200,2304,768  (tcgen05 backend only; for ncu captures)
+        SHAPES = [tuple(int(v) for v in sys.argv[sys.argv.index("--only") + 1].split(","))]
+        backends = (1,)
+    for backend in backends:
+        if l.mmx_set_gemm_backend(backend) != backend:
+            continue
+        for M, N, K in SHAPES:
+            g = torch.Generator(device="cuda").manual_seed(1)
+            A = torch.randn(M, K, device="cuda", generator=g)
+            W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+            bias = torch.randn(N, device="cuda", generator=g)
+            Cm = torch.empty(M, N, device="cuda")
+            for _ in range(3):
+                check(l.mmx_linear(ptr(A), K, ptr(W), K, ptr(bias), None, 0, ptr(Cm), N, None, 0, M, N, K, current_stream()))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record()
+            for _ in range(reps):
+                check(l.mmx_linear(ptr(A), K, ptr(W), K, ptr(bias), None, 0, ptr(Cm), N, None, 0, M, N, K, current_stream()))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            ref = (A[:256].double() @ W.double().t() + bias.double())
+            err = ((Cm[:256].double() - ref).abs().max() / ref.abs().max()).item()
+            out.append(dict(backend=backend, M=M, N=N, K=K, us=ms * 1e3, tflops=2.0 * M * N * K / (ms * 1e-3) / 1e12, rel_err=err))
+            print(out[-1], flush=True)
+    l.mmx_set_gemm_backend(1)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

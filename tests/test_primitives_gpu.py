@@ -31,6 +31,9 @@ def test_linear_and_dgrad(L, backend, M, N, K):
     if got != backend:
         pytest.skip("tcgen05 backend not available")
     try:
+        # fp32 FFMA: plain fp32 rounding.  tcgen05 3xTF32: the tensor core accumulates with truncation, measured
+        # ~2e-6 (K=768) .. 6e-6 (K=3072) of max|C|; both far inside the 1e-4 budget of the maps.
+        tol = 5e-6 if backend == 0 else 2e-5
         gen = torch.Generator().manual_seed(M + N + K)
         A = torch.randn(M, K, generator=gen)
         W = torch.randn(N, K, generator=gen) / math.sqrt(K)
@@ -42,9 +45,9 @@ def test_linear_and_dgrad(L, backend, M, N, K):
             Ca = torch.empty(M, N, device="cuda") if act else None
             check(lib.mmx_linear(ptr(Ad), K, ptr(Wd), K, ptr(bd), ptr(rd), N, ptr(Cd), N, ptr(Ca), act, M, N, K, st()))
             ref = (A.double() @ W.double().t() + bias.double() + res.double())
-            assert rel_err(Cd, ref) < 5e-6
+            assert rel_err(Cd, ref) < tol
             if act:
-                assert rel_err(Ca, ACTS[act](ref)) < 5e-6
+                assert rel_err(Ca, ACTS[act](ref)) < tol
         # dgrad through an activation: dX = (dY W) . act'(pre)
         dY = torch.randn(M, N, generator=gen)
         pre = torch.randn(M, K, generator=gen)
@@ -59,7 +62,7 @@ def test_linear_and_dgrad(L, backend, M, N, K):
             y.backward(dY.double())
             base = dY.double() @ W.double()
             ref = p.grad if act else base
-            assert rel_err(dX, ref, base=base) < 5e-6      # fp32 accumulation over up to 3072 terms
+            assert rel_err(dX, ref, base=base) < tol
     finally:
         lib.mmx_set_gemm_backend(1)
 

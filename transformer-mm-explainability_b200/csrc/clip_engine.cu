@@ -52,11 +52,22 @@ static int transpose(const float* in, float* out, int rows, int cols, cudaStream
   return 0;
 }
 
+// a K-major GEMM "B" operand [N,K]
+struct Mat {
+  float* w = nullptr;
+  int N = 0, K = 0;
+};
+
 struct LayerW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-  float *Wqkv, *bqkv, *Wo, *bo, *Wfc, *bfc, *Wproj, *bproj;
-  float *WqkvT, *WoT, *WfcT, *WprojT;   // dgrad operands (W^T, K-major for the NT GEMM)
+  float *bqkv, *bo, *bfc, *bproj;
+  Mat Wqkv, Wo, Wfc, Wproj;             // forward operands [out, in]
+  Mat WqkvT, WoT, WfcT, WprojT;         // dgrad operands (W^T, K-major for the NT GEMM)
 };
+
+static inline int mm(const float* A, int lda, const Mat& B, float* C, int ldc, int M, const GemmEpilogue& ep, cudaStream_t st) {
+  return gemm_nt(A, lda, B.w, B.K, C, ldc, M, B.N, B.K, ep, st);
+}
 
 struct Tower {
   int L = 0, D = 0, H = 0, S = 0, ld = 0, hd = 0, act = MMX_ACT_QUICKGELU, causal = 0;
@@ -75,7 +86,7 @@ struct Tower {
   int* rows = nullptr;      // [Bm] pooled row per sample (cls / eot)
   float *pool_ln = nullptr, *pool_mean = nullptr, *pool_rstd = nullptr, *dpool = nullptr;  // [Bm,D], [Bm]
   float *lnf_g = nullptr, *lnf_b = nullptr;  // ln_post / ln_final
-  float *proj = nullptr, *projT = nullptr;   // [D,E], [E,D]
+  Mat proj, projT;                           // [D,E] (as stored: the dgrad operand), [E,D] (forward operand)
   float *feat = nullptr, *featn = nullptr, *dfeat = nullptr;  // [Bm,E]
   cudaStream_t st = nullptr;
   long long M(int B) const { return (long long)B * S; }
@@ -97,7 +108,8 @@ struct mmx_clip {
   std::vector<void*> allocs;
   bool finalized = false;
   // vision pre
-  float *conv_w = nullptr, *cls = nullptr, *pos_v = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr;
+  Mat conv_w;
+  float *cls = nullptr, *pos_v = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr;
   float *patches = nullptr, *patch_emb = nullptr;
   // text pre
   float *tok_emb = nullptr, *pos_t = nullptr;
@@ -139,18 +151,23 @@ int alloc_tower(mmx_clip* h, Tower& T, const std::string& prefix, int Bm, int E)
     MMX_TRY(reg(h, p + "ln_1.bias", &w.ln1_b, D));
     MMX_TRY(reg(h, p + "ln_2.weight", &w.ln2_g, D));
     MMX_TRY(reg(h, p + "ln_2.bias", &w.ln2_b, D));
-    MMX_TRY(reg(h, p + "attn.in_proj_weight", &w.Wqkv, 3 * D * D));
+    MMX_TRY(reg(h, p + "attn.in_proj_weight", &w.Wqkv.w, 3 * D * D));
     MMX_TRY(reg(h, p + "attn.in_proj_bias", &w.bqkv, 3 * D));
-    MMX_TRY(reg(h, p + "attn.out_proj.weight", &w.Wo, D * D));
+    MMX_TRY(reg(h, p + "attn.out_proj.weight", &w.Wo.w, D * D));
     MMX_TRY(reg(h, p + "attn.out_proj.bias", &w.bo, D));
-    MMX_TRY(reg(h, p + "mlp.c_fc.weight", &w.Wfc, 4 * D * D));
+    MMX_TRY(reg(h, p + "mlp.c_fc.weight", &w.Wfc.w, 4 * D * D));
     MMX_TRY(reg(h, p + "mlp.c_fc.bias", &w.bfc, 4 * D));
-    MMX_TRY(reg(h, p + "mlp.c_proj.weight", &w.Wproj, 4 * D * D));
+    MMX_TRY(reg(h, p + "mlp.c_proj.weight", &w.Wproj.w, 4 * D * D));
     MMX_TRY(reg(h, p + "mlp.c_proj.bias", &w.bproj, D));
-    MMX_TRY(dallocT(h, &w.WqkvT, 3 * D * D));
-    MMX_TRY(dallocT(h, &w.WoT, D * D));
-    MMX_TRY(dallocT(h, &w.WfcT, 4 * D * D));
-    MMX_TRY(dallocT(h, &w.WprojT, 4 * D * D));
+    MMX_TRY(dallocT(h, &w.WqkvT.w, 3 * D * D));
+    MMX_TRY(dallocT(h, &w.WoT.w, D * D));
+    MMX_TRY(dallocT(h, &w.WfcT.w, 4 * D * D));
+    MMX_TRY(dallocT(h, &w.WprojT.w, 4 * D * D));
+    const int Di = (int)D;
+    w.Wqkv.N = 3 * Di; w.Wqkv.K = Di; w.WqkvT.N = Di; w.WqkvT.K = 3 * Di;
+    w.Wo.N = Di; w.Wo.K = Di; w.WoT.N = Di; w.WoT.K = Di;
+    w.Wfc.N = 4 * Di; w.Wfc.K = Di; w.WfcT.N = Di; w.WfcT.K = 4 * Di;
+    w.Wproj.N = Di; w.Wproj.K = 4 * Di; w.WprojT.N = 4 * Di; w.WprojT.K = Di;
   }
   MMX_TRY(dallocT(h, &T.x, (L + 1) * M * D));
   MMX_TRY(dallocT(h, &T.xmid, L * M * D));
@@ -175,7 +192,8 @@ int alloc_tower(mmx_clip* h, Tower& T, const std::string& prefix, int Bm, int E)
   MMX_TRY(dallocT(h, &T.pool_mean, (size_t)Bm));
   MMX_TRY(dallocT(h, &T.pool_rstd, (size_t)Bm));
   MMX_TRY(dallocT(h, &T.dpool, (size_t)Bm * D));
-  MMX_TRY(dallocT(h, &T.projT, (size_t)E * D));
+  MMX_TRY(dallocT(h, &T.projT.w, (size_t)E * D));
+  T.proj.N = (int)D; T.proj.K = E; T.projT.N = E; T.projT.K = (int)D;
   MMX_TRY(dallocT(h, &T.feat, (size_t)Bm * E));
   MMX_TRY(dallocT(h, &T.featn, (size_t)Bm * E));
   MMX_TRY(dallocT(h, &T.dfeat, (size_t)Bm * E));
@@ -200,16 +218,16 @@ int tower_forward(Tower& T, int B) {
     float* stt = T.stats + (size_t)l * 4 * M;
     MMX_TRY(layernorm_fwd(x_in, D, nullptr, w.ln1_g, w.ln1_b, T.h, D, stt, stt + M, M, D, 1e-5f, st));
     GemmEpilogue e1; e1.bias = w.bqkv;
-    MMX_TRY(gemm_nt(T.h, D, w.Wqkv, D, qkv, 3 * D, M, 3 * D, D, e1, st));
+    MMX_TRY(mm(T.h, D, w.Wqkv, qkv, 3 * D, M, e1, st));
     MMX_TRY(attention_fwd(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, nullptr, T.A + l * plane, T.ld, T.o, D, B, T.H, T.S,
                           T.S, T.hd, scale, T.causal ? MMX_ATTN_CAUSAL : 0, st));
     GemmEpilogue e2; e2.bias = w.bo; e2.residual = x_in; e2.ldres = D;
-    MMX_TRY(gemm_nt(T.o, D, w.Wo, D, x_mid, D, M, D, D, e2, st));
+    MMX_TRY(mm(T.o, D, w.Wo, x_mid, D, M, e2, st));
     MMX_TRY(layernorm_fwd(x_mid, D, nullptr, w.ln2_g, w.ln2_b, T.h, D, stt + 2 * M, stt + 3 * M, M, D, 1e-5f, st));
     GemmEpilogue e3; e3.bias = w.bfc; e3.C_act = T.g; e3.act = T.act;
-    MMX_TRY(gemm_nt(T.h, D, w.Wfc, D, f, 4 * D, M, 4 * D, D, e3, st));
+    MMX_TRY(mm(T.h, D, w.Wfc, f, 4 * D, M, e3, st));
     GemmEpilogue e4; e4.bias = w.bproj; e4.residual = x_mid; e4.ldres = D;
-    MMX_TRY(gemm_nt(T.g, 4 * D, w.Wproj, 4 * D, x_out, D, M, D, 4 * D, e4, st));
+    MMX_TRY(mm(T.g, 4 * D, w.Wproj, x_out, D, M, e4, st));
   }
   return 0;
 }
@@ -220,7 +238,7 @@ int tower_pool(Tower& T, int B, int E) {
   const float* xL = T.x + (size_t)T.L * MD;
   MMX_TRY(layernorm_fwd(xL, T.D, T.rows, T.lnf_g, T.lnf_b, T.pool_ln, T.D, T.pool_mean, T.pool_rstd, B, T.D, 1e-5f, T.st));
   GemmEpilogue e;
-  MMX_TRY(gemm_nt(T.pool_ln, T.D, T.projT, T.D, T.feat, E, B, E, T.D, e, T.st));
+  MMX_TRY(mm(T.pool_ln, T.D, T.projT, T.feat, E, B, e, T.st));
   return 0;
 }
 
@@ -232,7 +250,7 @@ int tower_backward(Tower& T, int B, int E, int stop) {
   const size_t plane = (size_t)B * T.H * T.S * T.ld;
   const float scale = 1.f / sqrtf((float)T.hd);
   GemmEpilogue e0;
-  MMX_TRY(gemm_nt(T.dfeat, E, T.proj, E, T.dpool, D, B, D, E, e0, st));          // d(LN out) = dfeat @ proj^T
+  MMX_TRY(mm(T.dfeat, E, T.proj, T.dpool, D, B, e0, st));                          // d(LN out) = dfeat @ proj^T
   float* dx_out = T.dx0;
   float* dx_mid = T.dx1;
   MMX_CHECK_CUDA(cudaMemsetAsync(dx_out, 0, MD * sizeof(float), st));
@@ -246,17 +264,17 @@ int tower_backward(Tower& T, int B, int E, int stop) {
     const float* f = T.f + l * MD * 4;
     const float* stt = T.stats + (size_t)l * 4 * M;
     GemmEpilogue e1; e1.pre = f; e1.ldpre = 4 * D; e1.act = T.act;
-    MMX_TRY(gemm_nt(dx_out, D, w.WprojT, D, T.g, 4 * D, M, 4 * D, D, e1, st));        // df = (dx W_proj) . act'(f)
+    MMX_TRY(mm(dx_out, D, w.WprojT, T.g, 4 * D, M, e1, st));                        // df = (dx W_proj) . act'(f)
     GemmEpilogue e2;
-    MMX_TRY(gemm_nt(T.g, 4 * D, w.WfcT, 4 * D, T.h, D, M, D, 4 * D, e2, st));         // dh2 = df W_fc
+    MMX_TRY(mm(T.g, 4 * D, w.WfcT, T.h, D, M, e2, st));                             // dh2 = df W_fc
     MMX_TRY(layernorm_bwd(T.h, D, x_mid, D, nullptr, w.ln2_g, stt + 2 * M, stt + 3 * M, dx_out, D, dx_mid, D, M, D, st));
-    MMX_TRY(gemm_nt(dx_mid, D, w.WoT, D, T.o, D, M, D, D, e2, st));                   // d(attn out) = dx_mid W_o
+    MMX_TRY(mm(dx_mid, D, w.WoT, T.o, D, M, e2, st));                               // d(attn out) = dx_mid W_o
     const bool last = (l == stop);
     MMX_TRY(attention_bwd(T.o, D, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, T.A + l * plane, T.dA + l * plane, T.ld,
                           T.delta, last ? nullptr : T.dqkv, 3 * D, last ? nullptr : T.dqkv + D, 3 * D,
                           last ? nullptr : T.dqkv + 2 * D, 3 * D, B, T.H, T.S, T.S, T.hd, scale, 0, st));
     if (last) break;
-    MMX_TRY(gemm_nt(T.dqkv, 3 * D, w.WqkvT, 3 * D, T.h, D, M, D, 3 * D, e2, st));     // dh1 = dqkv W_qkv
+    MMX_TRY(mm(T.dqkv, 3 * D, w.WqkvT, T.h, D, M, e2, st));                          // dh1 = dqkv W_qkv
     MMX_TRY(layernorm_bwd(T.h, D, x_in, D, nullptr, w.ln1_g, stt, stt + M, dx_mid, D, dx_out, D, M, D, st));
   }
   return 0;
@@ -295,7 +313,7 @@ int run_chunk(mmx_clip* h, const float* images, int n_images, const int32_t* tok
     const int p = c.vision_patch_size, G = h->G, Kp = 3 * p * p;
     MMX_TRY(im2col_patches(images, h->patches, n_images, c.image_resolution, p, V.st));
     GemmEpilogue e;
-    MMX_TRY(gemm_nt(h->patches, Kp, h->conv_w, Kp, h->patch_emb, V.D, n_images * G * G, V.D, Kp, e, V.st));
+    MMX_TRY(mm(h->patches, Kp, h->conv_w, h->patch_emb, V.D, n_images * G * G, e, V.st));
     MMX_TRY(vision_tokens_lnpre(h->patch_emb, n_images, h->cls, h->pos_v, h->lnpre_g, h->lnpre_b, V.x, B, V.S, V.D, 1e-5f, V.st));
     MMX_TRY(cls_rows(V.rows, B, V.S, V.st));
     MMX_TRY(tower_forward(V, B));
@@ -374,19 +392,20 @@ int mmx_clip_create(const mmx_clip_config* cfg, int max_batch, mmx_clip** out) {
   if ((rc = alloc_tower(h, T, "transformer.", max_batch, h->E))) return fail(rc);
 #define REG(name, ptr, n) if ((rc = reg(h, name, ptr, n))) return fail(rc)
 #define ALLOC(ptr, n) if ((rc = dallocT(h, ptr, n))) return fail(rc)
-  REG("visual.conv1.weight", &h->conv_w, (size_t)V.D * Kp);
+  REG("visual.conv1.weight", &h->conv_w.w, (size_t)V.D * Kp);
+  h->conv_w.N = V.D; h->conv_w.K = Kp;
   REG("visual.class_embedding", &h->cls, V.D);
   REG("visual.positional_embedding", &h->pos_v, (size_t)V.S * V.D);
   REG("visual.ln_pre.weight", &h->lnpre_g, V.D);
   REG("visual.ln_pre.bias", &h->lnpre_b, V.D);
   REG("visual.ln_post.weight", &V.lnf_g, V.D);
   REG("visual.ln_post.bias", &V.lnf_b, V.D);
-  REG("visual.proj", &V.proj, (size_t)V.D * h->E);
+  REG("visual.proj", &V.proj.w, (size_t)V.D * h->E);
   REG("token_embedding.weight", &h->tok_emb, (size_t)cfg->vocab_size * T.D);
   REG("positional_embedding", &h->pos_t, (size_t)T.S * T.D);
   REG("ln_final.weight", &T.lnf_g, T.D);
   REG("ln_final.bias", &T.lnf_b, T.D);
-  REG("text_projection", &T.proj, (size_t)T.D * h->E);
+  REG("text_projection", &T.proj.w, (size_t)T.D * h->E);
   ALLOC(&h->patches, (size_t)max_batch * h->G * h->G * Kp);
   ALLOC(&h->patch_emb, (size_t)max_batch * h->G * h->G * V.D);
   ALLOC(&h->logits, (size_t)max_batch * max_batch);
@@ -444,12 +463,12 @@ int mmx_clip_finalize(mmx_clip* h) {
   for (Tower* T : {&h->v, &h->t}) {
     const int D = T->D;
     for (LayerW& w : T->w) {
-      MMX_TRY(transpose(w.Wqkv, w.WqkvT, 3 * D, D, st));    // [3D,D] -> [D,3D]
-      MMX_TRY(transpose(w.Wo, w.WoT, D, D, st));
-      MMX_TRY(transpose(w.Wfc, w.WfcT, 4 * D, D, st));      // [4D,D] -> [D,4D]
-      MMX_TRY(transpose(w.Wproj, w.WprojT, D, 4 * D, st));  // [D,4D] -> [4D,D]
+      MMX_TRY(transpose(w.Wqkv.w, w.WqkvT.w, 3 * D, D, st));    // [3D,D] -> [D,3D]
+      MMX_TRY(transpose(w.Wo.w, w.WoT.w, D, D, st));
+      MMX_TRY(transpose(w.Wfc.w, w.WfcT.w, 4 * D, D, st));      // [4D,D] -> [D,4D]
+      MMX_TRY(transpose(w.Wproj.w, w.WprojT.w, D, 4 * D, st));  // [D,4D] -> [4D,D]
     }
-    MMX_TRY(transpose(T->proj, T->projT, D, h->E, st));     // [D,E] -> [E,D]
+    MMX_TRY(transpose(T->proj.w, T->projT.w, D, h->E, st));     // [D,E] -> [E,D]
   }
   MMX_CHECK_CUDA(cudaStreamSynchronize(st));
   h->finalized = true;

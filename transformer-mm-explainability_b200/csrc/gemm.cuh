@@ -18,11 +18,12 @@ struct GemmEpilogue {
 int gemm_nt_simt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t st);
 
-// Backend dispatch (tcgen05 3xTF32 when the shape qualifies and the backend is enabled, else fp32 FFMA).
-// A_lo / Bt_lo: optional precomputed TF32 residual planes for the tcgen05 path (null = not available).
+// Backend dispatch: tcgen05 3xTF32 when the backend is enabled and the shape qualifies (the rule depends on N, K and
+// alignment only - never on M - so one sample alone and inside a batch take the same arithmetic path), else fp32 FFMA.
 int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
             const GemmEpilogue& ep, cudaStream_t st);
 
+int gemm_tc_available();
 int gemm_backend();
 
 }  // namespace mmx

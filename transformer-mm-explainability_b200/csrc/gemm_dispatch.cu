@@ -23,9 +23,11 @@ int sm_count() {
   return n;
 }
 
-int gemm_tc_available();  // gemm_tcgen05.cu
+// gemm_tcgen05.cu
+bool gemm_tc_shape_ok(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int N, int K,
+                      const GemmEpilogue& ep);
 int gemm_nt_tc(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
-               const GemmEpilogue& ep, cudaStream_t st, bool* taken);
+               const GemmEpilogue& ep, cudaStream_t st);
 
 int gemm_backend() {
   int b = g_backend.load();
@@ -38,11 +40,8 @@ int gemm_backend() {
 
 static int gemm_nt_impl(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
                         const GemmEpilogue& ep, cudaStream_t st) {
-  if (gemm_backend() == 1) {
-    bool taken = false;
-    MMX_TRY(gemm_nt_tc(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st, &taken));
-    if (taken) return 0;
-  }
+  if (gemm_backend() == 1 && gemm_tc_shape_ok(A, lda, Bt, ldb, C, ldc, N, K, ep))
+    return gemm_nt_tc(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
   return gemm_nt_simt(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
 }
 

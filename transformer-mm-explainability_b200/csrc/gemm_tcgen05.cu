@@ -1,9 +1,439 @@
-// tcgen05 (5th-gen tensor core) 3xTF32 GEMM backend - placeholder until the kernel lands.
+// tcgen05 (5th-gen tensor core) GEMM with fp32-faithful numerics:  C[M,N] = A[M,K] * Bt[N,K]^T  (+ epilogue).
+//
+// Why 3xTF32: the relevancy maps must match the fp32 reference to 1e-4 after ~100 chained GEMMs (forward +
+// dgrad), which rules out plain TF32/BF16 inputs.  Each fp32 operand x is split exactly into
+//      x = hi + lo,   hi = x with the low 13 mantissa bits cleared (a TF32 value),  lo = x - hi (exact in fp32)
+// and the product is A_hi*B_hi + (A_lo*B_hi + A_hi*B_lo); the dropped lo*lo term and the TF32 rounding of lo are both
+// ~2^-21 relative.  The tensor core adds into its fp32 accumulator with truncation (measured: error grows linearly
+// with the number of accumulating MMAs), so the two small cross products go to their OWN TMEM accumulator (their
+// truncation error is 2^-11 smaller) and are added to the hi*hi accumulator once, in the epilogue, with RN.
+//
+// A 3-pass fp32 GEMM is limited by operand movement, not by the tensor pipe: measured on B200, L2->SM delivers
+// ~24 B/clk/SM with all 148 SMs pulling, and shared memory serves 128 B/clk/SM to TMA writes, LSU traffic and the
+// UMMA operand fetch together.  So both operands cross L2 ONCE as raw fp32 and are split on the SM:
+//   * A (activations): raw tile -> registers -> hi/lo -> TMEM (tcgen05.st); the MMAs take A from TMEM (.ts form),
+//     so A costs one shared-memory read instead of three operand fetches;
+//   * B (weights): raw tile split in shared memory (hi in place, lo beside it), fetched by the MMAs from there.
+//
+// Structure (one CTA per SM, persistent over 128x128 output tiles, 4-stage ring of 128x32 K-slabs):
+//   warp 0      TMA producer: raw fp32 A and B tiles -> shared memory (128-byte swizzle), mbarrier complete_tx
+//   warps 12-15 splitters: A tile (smem) -> hi/lo -> TMEM columns of this
+//               stage; B tile -> hi/lo planes in smem
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (3 per k-step), tcgen05.commit
+//   warp 2      TMEM allocator (512 columns: 128 main + 128 cross accumulator + 4 stages x 64 columns of A)
+//   warps 4-11  epilogue: tcgen05.ld (main + cross, added with RN) -> registers, TMEM released at once, then
+//               bias / act' / residual / act -> global from registers (overlaps the next tile's main loop)
 #include "gemm.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cstdlib>
+
 namespace mmx {
-int gemm_tc_available() { return 0; }
-int gemm_nt_tc(const float*, int, const float*, int, float*, int, int, int, int, const GemmEpilogue&, cudaStream_t, bool* taken) {
-  *taken = false;
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;    // BK fp32 = 128 bytes = one swizzle-128B row
+constexpr int SPLIT_GROUPS = 1;                // groups of 4 splitter warps (group g takes K-slabs g, g+G, ...)
+constexpr int THREADS = (12 + 4 * SPLIT_GROUPS) * 32;   // 4 control + 8 epilogue + splitter warps (<= 512: 128 regs/thread)
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, SPLIT_WARP0 = 12;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;           // 16 KB raw A slab
+constexpr int B_BYTES = BN * BK * 4;           // 16 KB per B plane
+constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TM_MAIN = 0, TM_CROSS = 128, TM_A = 256;   // TMEM column map; A stage s: hi at TM_A+64s, lo at +32
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug traps (kernel error) after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > (1ll << 32)) __trap();
+  }
+}
+// Spinning variant (no suspend / wake-up latency) for the single-thread producer and MMA-issuer roles.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  if (mbar_test(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test(bar, parity)) {
+    if (clock64() - t0 > (1ll << 32)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]   (A from tensor memory: .ts form)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows are 128 B, 8-row groups are 1024 B apart (SBO), LBO unused (=1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+struct Params {
+  int M, N, K, ldc;
+  int dbg;   // timing experiments only (results invalid): 1 = no MMAs, 2 = no splitter work, 4 = no TMA, 8 = no epilogue stores
+  float* C;
+  GemmEpilogue ep;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapB, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle-128B tiles need 1024 B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers (8 B each): full_tma[S], split_done[S], empty[S], tmem_full, tmem_empty, then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (3 * STAGES), tempty_bar = bar_base + 8u * (3 * STAGES + 1);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(split_bar(s), 4); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_spin(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          if (p.dbg & 4) { mbar_arrive(full_bar(stage)); }
+          else {
+          mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
+          tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      const uint32_t d_main = tmem_base + TM_MAIN, d_cross = tmem_base + TM_CROSS;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        mbar_spin(tempty_bar, (uint32_t)(it & 1) ^ 1);           // epilogue drained the accumulators
+        tc_fence_after();
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_spin(split_bar(stage), phase);                   // A hi/lo in TMEM (implies the TMA landed B too)
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t b_hi = make_desc(sa + A_BYTES), b_lo = make_desc(sa + A_BYTES + B_BYTES);
+          const uint32_t a_hi = tmem_base + TM_A + 64u * stage, a_lo = a_hi + 32u;
+          if (!(p.dbg & 1))
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {                    // UMMA_K = 8 (tf32): +32 B in smem (+2 in the descriptor), +8 TMEM columns
+            const uint64_t adv = (uint64_t)(2 * k);
+            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_tf32_ts(d_cross, a_lo + 8u * k, b_hi + adv, idesc, first);
+            umma_tf32_ts(d_cross, a_hi + 8u * k, b_lo + adv, idesc, 1u);
+            umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + adv, idesc, first);
+          }
+          umma_commit(empty_bar(stage));                        // frees the stage (smem + TMEM A slab) when these MMAs retire
+          if (kb == nk - 1) umma_commit(tfull_bar);             // accumulators complete -> epilogue
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= SPLIT_WARP0) {
+    // ------------------------------------------------------------------ splitter: A slab (smem) -> hi/lo -> TMEM
+    const int q = warp & 3;                                     // TMEM lane quarter this warp may write
+    const int grp = (warp - SPLIT_WARP0) >> 2;                  // splitter group: handles K-slabs grp, grp+2, grp+4, ...
+    const int gtid = threadIdx.x - (SPLIT_WARP0 + 4 * grp) * 32;  // 0..127 inside the group
+    const int row = q * 32 + lane;                              // tile row handled by this thread
+    const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    long long slab = 0;                                         // global K-slab counter of this CTA
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < nk; ++kb, ++slab) {
+        if ((int)(slab % SPLIT_GROUPS) != grp) continue;
+        const int stage = (int)(slab % STAGES);
+        const uint32_t phase = (uint32_t)((slab / STAGES) & 1);
+        if (lane == 0) mbar_spin(full_bar(stage), phase);       // one polling lane per warp, no suspend/wake-up latency
+        __syncwarp();
+        if (p.dbg & 2) { __syncwarp(); if (lane == 0) mbar_arrive(split_bar(stage)); continue; }
+        // B slab: raw -> hi (in place) + lo plane; elementwise, so the swizzle does not matter
+        uint4* braw = reinterpret_cast<uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES);
+        uint4* blo = reinterpret_cast<uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES + B_BYTES);
+#pragma unroll
+        for (int i0 = 0; i0 < B_BYTES / 16; i0 += 128 * 4) {
+          uint4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = braw[i0 + u * 128 + gtid];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 h, l;
+            h.x = x[u].x & 0xFFFFE000u; h.y = x[u].y & 0xFFFFE000u; h.z = x[u].z & 0xFFFFE000u; h.w = x[u].w & 0xFFFFE000u;
+            l.x = __float_as_uint(__uint_as_float(x[u].x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(x[u].y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(x[u].z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(x[u].w) - __uint_as_float(h.w));
+            braw[i0 + u * 128 + gtid] = h;
+            blo[i0 + u * 128 + gtid] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
+        // A slab: this thread's row (128 B, swizzled chunks) -> hi/lo -> 32 + 32 TMEM columns of the stage
+        const uint8_t* a_raw = smem_gen + stage * STAGE_BYTES + row_off;
+        const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * stage;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t chunk = (uint32_t)(half * 4 + c);    // 16-byte chunk = k 4*chunk .. 4*chunk+3, swizzled by row
+            const uint4 x = *reinterpret_cast<const uint4*>(a_raw + ((chunk ^ sw) << 4));
+            const uint32_t xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t h = xv[e] & 0xFFFFE000u;
+              hi[c * 4 + e] = h;
+              lo[c * 4 + e] = __float_as_uint(__uint_as_float(xv[e]) - __uint_as_float(h));
+            }
+          }
+          tmem_st16(t_hi + 16u * half, hi);
+          tmem_st16(t_hi + 32u + 16u * half, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(stage));
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
+    const int q = warp & 3;                                     // TMEM lane quarter this warp may read
+    const int ch = (warp - EPI_WARP0) >> 2;                     // column half: 64 of the 128 accumulator columns
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      if (lane == 0) mbar_spin(tfull_bar, (uint32_t)(it & 1));
+      __syncwarp();
+      tc_fence_after();
+      // drain main + cross accumulators into registers (RN add), then hand TMEM back before any global traffic
+      uint32_t acc[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32], x[32];
+        const uint32_t col = (uint32_t)(ch * 64 + c * 32);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TM_MAIN + col, r);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TM_CROSS + col, x);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);                  // next tile's MMAs may start
+      const int m = m0 + q * 32 + lane;
+      if (m < p.M && !(p.dbg & 8)) {
+        float* crow = p.C + (long long)m * p.ldc;
+        const float* prow = p.ep.pre ? p.ep.pre + (long long)m * p.ep.ldpre : nullptr;
+        const float* rrow = p.ep.residual ? p.ep.residual + (long long)m * p.ep.ldres : nullptr;
+        float* arow = p.ep.C_act ? p.ep.C_act + (long long)m * p.ldc : nullptr;
+        const int nbase = n0 + ch * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const int n = nbase + j;
+          if (n >= p.N) break;                                  // N % 4 == 0 is required by the host wrapper
+          float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                 __uint_as_float(acc[j + 3]));
+          if (p.ep.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          if (prow) {
+            const float4 f = *reinterpret_cast<const float4*>(prow + n);
+            v.x *= act_bwd(f.x, p.ep.act); v.y *= act_bwd(f.y, p.ep.act);
+            v.z *= act_bwd(f.z, p.ep.act); v.w *= act_bwd(f.w, p.ep.act);
+          }
+          if (rrow) {
+            const float4 b = *reinterpret_cast<const float4*>(rrow + n);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          *reinterpret_cast<float4*>(crow + n) = v;
+          if (arow) {
+            float4 a = make_float4(act_fwd(v.x, p.ep.act), act_fwd(v.y, p.ep.act), act_fwd(v.z, p.ep.act),
+                                   act_fwd(v.w, p.ep.act));
+            *reinterpret_cast<float4*>(arow + n) = a;
+          }
+        }
+      }
+    }
+  }
+  // ---------------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int g_avail = -1;
+
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return 1;
+  }
   return 0;
 }
+
+static int launch(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+                  const GemmEpilogue& ep, cudaStream_t st) {
+  CUtensorMap mapA, mapB;
+  MMX_TRY(make_map(&mapA, A, M, K, lda, BM));
+  MMX_TRY(make_map(&mapB, Bt, N, K, ldb, BN));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("MMX_TC_DBG"); dbg = e ? atoi(e) : 0; }
+  Params p{M, N, K, ldc, dbg, C, ep};
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tf32x3_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+
+int gemm_tc_available() {
+  if (tc::g_avail >= 0) return tc::g_avail;
+  tc::g_avail = 0;
+  const char* env = getenv("MMX_GEMM_BACKEND");
+  if (env && atoi(env) == 0) return 0;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  if (prop.major != 10) return 0;                         // tcgen05 / TMEM: sm_100 family only
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) return 0;
+  tc::g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  tc::g_avail = 1;
+  return 1;
+}
+
+// Which problems go to the tensor-core kernel.  Deliberately independent of M, so that a sample computed alone
+// and the same sample inside a batch take the same arithmetic path (bitwise-equal maps, sharded == single GPU).
+bool gemm_tc_shape_ok(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int N, int K,
+                      const GemmEpilogue& ep) {
+  if (!gemm_tc_available()) return false;
+  if (N < 128 || K < 64 || (K % 4) || (N % 4) || (lda % 4) || (ldb % 4) || (ldc % 4)) return false;
+  if (!aligned16(A) || !aligned16(Bt) || !aligned16(C)) return false;
+  if ((ep.bias && !aligned16(ep.bias)) || (ep.pre && (!aligned16(ep.pre) || ep.ldpre % 4)) ||
+      (ep.residual && (!aligned16(ep.residual) || ep.ldres % 4)) || (ep.C_act && !aligned16(ep.C_act)))
+    return false;
+  return true;
+}
+
+int gemm_nt_tc(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+               const GemmEpilogue& ep, cudaStream_t st) {
+  if (M == 0 || N == 0) return 0;
+  return tc::launch(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
+}
+
 }  // namespace mmx
