@@ -103,6 +103,7 @@ int mmx_bmm_add(const float* A, int lda, long long strideA, int transA, const fl
 #define MMX_ACT_QUICKGELU  1   /* x*sigmoid(1.702x), CLIP/clip/model.py:162-164 */
 #define MMX_ACT_GELU       2   /* exact erf GELU (timm ViT, LXMERT) */
 #define MMX_ACT_RELU       3   /* DETR FFN, DETR/models/transformer.py:239 */
+#define MMX_ACT_TANH       4   /* LXMERT pooler, lxmert/lxmert/src/lxmert_lrp.py:868-884 */
 
 /* C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (+ residual[M,N]);  if act != NONE and C_act != NULL also writes
  * C_act = act(C).  F.linear of CLIP/clip/auxilary.py:77,255 and CLIP/clip/model.py:175-177. */
@@ -113,6 +114,25 @@ int mmx_linear(const float* A, int lda, const float* W, int ldw, const float* bi
  * pre-activation; NULL = none).  The reference obtains it through torch.autograd (CLIP_explainability.ipynb:175). */
 int mmx_linear_dgrad(const float* dY, int lddy, const float* Wt, int ldwt, const float* pre, int ldpre, int act,
                      float* dX, int lddx, int M, int N, int K, void* stream);
+
+/* Small glue kernels for the host-side generators (DETR / LXMERT / ViT orchestration; row-major [rows, cols] with
+ * row strides in elements).  They replace elementwise torch ops of the reference models (positional-embedding adds
+ * DETR/models/transformer.py:236,378-390; residual adds; x[:,0] / embedding gathers). */
+/* out = a + alpha*b  (out may alias a) */
+int mmx_add(const float* a, int lda, const float* b, int ldb, float alpha, float* out, int ldo, long long rows, int cols,
+            void* stream);
+/* out[r,:] = src[row_map[r],:] */
+int mmx_gather_rows(const float* src, int lds, const int32_t* row_map, float* out, int ldo, int rows, int cols, void* stream);
+/* dst[row_map[r],:] += src[r,:]   (row_map entries must be distinct) */
+int mmx_scatter_add_rows(const float* src, int lds, const int32_t* row_map, float* dst, int ldd, int rows, int cols,
+                         void* stream);
+/* dx = dy (.) act'(pre)  and  y = act(x) as standalone elementwise passes */
+int mmx_act_bwd(const float* dy, int lddy, const float* pre, int ldpre, int act, float* dx, int lddx, long long rows, int cols,
+                void* stream);
+int mmx_act_fwd(const float* x, int ldx, int act, float* y, int ldy, long long rows, int cols, void* stream);
+/* images [n,3,R,R] -> patches [n*(R/p)^2, 3*p*p] in conv-weight order (the conv1 of CLIP/clip/model.py:230 and of the
+ * timm ViT patch embedding, as a GEMM operand) */
+int mmx_im2col_patches(const float* images, float* patches, int n_images, int resolution, int patch, void* stream);
 
 /* LayerNorm over the last dim (eps 1e-5), optional row gather: out row r reads x row row_map[r].
  * CLIP/clip/model.py:153-159.  mean/rstd ([rows]) are saved for the backward. */

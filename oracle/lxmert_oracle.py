@@ -1,0 +1,208 @@
+"""Oracle restatement of the LXMERT bi-modal relevancy path.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Plain PyTorch + autograd on CPU over a ``state_dict`` with the
+reference's key names (``lxmert.encoder.layer.0.attention.self.query.weight`` ...).  Reference lines followed
+(lxmert/lxmert/src/lxmert_lrp.py unless noted):
+  * LxmertEmbeddings.forward :285-310, LxmertVisualFeatureEncoder.forward :758-766
+  * LxmertAttention.forward :385-420 (scores / sqrt(d) AFTER q k^T, additive mask, save_attn BEFORE dropout)
+  * LxmertAttentionOutput :472-477, LxmertIntermediate :549-552 (exact GELU), LxmertOutput :568-573, LxmertLayer :592-599
+  * LxmertXLayer.cross_att :630-655 (the i->t direction runs through a deepcopy of the SAME weights), self_att,
+    output_fc, forward :701-733;  LxmertEncoder.forward :793-853;  LxmertPooler :876-884 (tanh);
+    LxmertVisualAnswerHead :941-953;  extended masks :1195-1201 ((1 - mask) * -10000)
+  * GeneratorOurs.generate_ours  lxmert/lxmert/src/ExplanationGenerator.py:131-211
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List
+
+import torch
+import torch.nn.functional as F
+
+from . import rules as R_
+
+
+@dataclass(frozen=True)
+class LxmertConfig:
+    hidden: int = 768
+    heads: int = 12
+    intermediate: int = 3072
+    l_layers: int = 9
+    x_layers: int = 5
+    r_layers: int = 5
+    vocab: int = 30522
+    max_pos: int = 512
+    feat_dim: int = 2048
+    pos_dim: int = 4
+    num_labels: int = 3129
+
+
+LXMERT_BASE = LxmertConfig()
+LXMERT_TINY = LxmertConfig(hidden=64, heads=2, intermediate=96, l_layers=2, x_layers=2, r_layers=2, vocab=50, max_pos=16,
+                           feat_dim=24, pos_dim=4, num_labels=11)
+
+
+def init_state_dict(cfg: LxmertConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    Hd = cfg.hidden
+
+    def lin(p, o, i, std=None):
+        sd[p + ".weight"] = torch.randn(o, i, generator=g) * (std if std else i ** -0.5)
+        sd[p + ".bias"] = torch.randn(o, generator=g) * 0.02
+
+    def ln(p, d):
+        sd[p + ".weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+        sd[p + ".bias"] = 0.05 * torch.randn(d, generator=g)
+
+    def att(p):
+        for n in ("query", "key", "value"):
+            lin(p + n, Hd, Hd)
+
+    def att_out(p):
+        lin(p + "dense", Hd, Hd); ln(p + "LayerNorm", Hd)
+
+    def ffn(pi, po):
+        lin(pi + "dense", cfg.intermediate, Hd); lin(po + "dense", Hd, cfg.intermediate); ln(po + "LayerNorm", Hd)
+
+    e = "lxmert.embeddings."
+    sd[e + "word_embeddings.weight"] = torch.randn(cfg.vocab, Hd, generator=g) * 0.5
+    sd[e + "position_embeddings.weight"] = torch.randn(cfg.max_pos, Hd, generator=g) * 0.5
+    sd[e + "token_type_embeddings.weight"] = torch.randn(2, Hd, generator=g) * 0.5
+    ln(e + "LayerNorm", Hd)
+    v = "lxmert.encoder.visn_fc."
+    lin(v + "visn_fc", Hd, cfg.feat_dim); ln(v + "visn_layer_norm", Hd); lin(v + "box_fc", Hd, cfg.pos_dim); ln(v + "box_layer_norm", Hd)
+    for name, n in (("layer", cfg.l_layers), ("r_layers", cfg.r_layers)):
+        for i in range(n):
+            p = f"lxmert.encoder.{name}.{i}."
+            att(p + "attention.self."); att_out(p + "attention.output."); ffn(p + "intermediate.", p + "output.")
+    for i in range(cfg.x_layers):
+        p = f"lxmert.encoder.x_layers.{i}."
+        att(p + "visual_attention.att."); att_out(p + "visual_attention.output.")
+        for s in ("lang_self_att", "visn_self_att"):
+            att(p + s + ".self."); att_out(p + s + ".output.")
+        ffn(p + "lang_inter.", p + "lang_output."); ffn(p + "visn_inter.", p + "visn_output.")
+    lin("lxmert.pooler.dense", Hd, Hd)
+    lin("answer_head.logit_fc.0", 2 * Hd, Hd); ln("answer_head.logit_fc.2", 2 * Hd); lin("answer_head.logit_fc.3", cfg.num_labels, 2 * Hd)
+    return sd
+
+
+def synthetic_inputs(cfg: LxmertConfig, B: int, T: int, I: int, seed: int = 0):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(3, cfg.vocab, (B, T), generator=g)
+    ids[:, 0] = 1
+    ids[:, -1] = 2
+    feats = torch.randn(B, I, cfg.feat_dim, generator=g)
+    boxes = torch.rand(B, I, cfg.pos_dim, generator=g)
+    return ids, feats, boxes
+
+
+def _lnorm(sd, p, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-12)
+
+
+def _lin(sd, p, x):
+    return F.linear(x, sd[p + ".weight"], sd[p + ".bias"])
+
+
+def _att(sd, p, hidden, context, mask, H, stage: List[torch.Tensor]):
+    B, T, D = hidden.shape
+    hd = D // H
+
+    def heads(x):
+        return x.view(B, -1, H, hd).permute(0, 2, 1, 3)
+    q, k, v = heads(_lin(sd, p + "query", hidden)), heads(_lin(sd, p + "key", context)), heads(_lin(sd, p + "value", context))
+    s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(hd)
+    if mask is not None:
+        s = s + mask
+    probs = s.softmax(dim=-1)
+    stage.append(probs)
+    return torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, T, D)
+
+
+def _att_layer(sd, p, att_name, x, ctx, mask, H, stage):
+    o = _att(sd, p + att_name + ".", x, ctx, mask, H, stage)
+    return _lnorm(sd, p + "output.LayerNorm", _lin(sd, p + "output.dense", o) + x)
+
+
+def _ffn(sd, pi, po, x):
+    return _lnorm(sd, po + "LayerNorm", _lin(sd, po + "dense", F.gelu(_lin(sd, pi + "dense", x))) + x)
+
+
+def lxmert_forward(sd, cfg: LxmertConfig, ids, feats, boxes, lang_mask=None, vis_mask=None):
+    """Returns (answer logits [B, num_labels], dict of staged A lists: lang, vis, x_lang (t->i), x_vis (i->t),
+    x_lang_self, x_vis_self), each A [B,H,T,S]."""
+    B, T = ids.shape
+    H = cfg.heads
+    e = "lxmert.embeddings."
+    pos_ids = torch.arange(T)
+    emb = sd[e + "token_type_embeddings.weight"][torch.zeros_like(ids)] + sd[e + "position_embeddings.weight"][pos_ids] \
+        + sd[e + "word_embeddings.weight"][ids]
+    lang = _lnorm(sd, e + "LayerNorm", emb)
+    lm = None if lang_mask is None else ((1.0 - lang_mask.to(lang.dtype)) * -10000.0)[:, None, None, :]
+    vm = None if vis_mask is None else ((1.0 - vis_mask.to(lang.dtype)) * -10000.0)[:, None, None, :]
+    v = "lxmert.encoder.visn_fc."
+    vis = (_lnorm(sd, v + "visn_layer_norm", _lin(sd, v + "visn_fc", feats)) + _lnorm(sd, v + "box_layer_norm", _lin(sd, v + "box_fc", boxes))) / 2
+    st = {k: [] for k in ("lang", "vis", "x_lang", "x_vis", "x_lang_self", "x_vis_self")}
+    for i in range(cfg.l_layers):
+        p = f"lxmert.encoder.layer.{i}."
+        lang = _ffn(sd, p + "intermediate.", p + "output.", _att_layer(sd, p + "attention.", "self", lang, lang, lm, H, st["lang"]))
+    for i in range(cfg.r_layers):
+        p = f"lxmert.encoder.r_layers.{i}."
+        vis = _ffn(sd, p + "intermediate.", p + "output.", _att_layer(sd, p + "attention.", "self", vis, vis, vm, H, st["vis"]))
+    for i in range(cfg.x_layers):
+        p = f"lxmert.encoder.x_layers.{i}."
+        l2 = _att_layer(sd, p + "visual_attention.", "att", lang, vis, vm, H, st["x_lang"])
+        v2 = _att_layer(sd, p + "visual_attention.", "att", vis, lang, lm, H, st["x_vis"])     # the deepcopy: same weights
+        l3 = _att_layer(sd, p + "lang_self_att.", "self", l2, l2, lm, H, st["x_lang_self"])
+        v3 = _att_layer(sd, p + "visn_self_att.", "self", v2, v2, vm, H, st["x_vis_self"])
+        lang, vis = _ffn(sd, p + "lang_inter.", p + "lang_output.", l3), _ffn(sd, p + "visn_inter.", p + "visn_output.", v3)
+    pooled = torch.tanh(_lin(sd, "lxmert.pooler.dense", lang[:, 0]))
+    h = _lin(sd, "answer_head.logit_fc.0", pooled)
+    h = F.layer_norm(F.gelu(h), (h.shape[-1],), sd["answer_head.logit_fc.2.weight"], sd["answer_head.logit_fc.2.bias"], 1e-12)
+    return _lin(sd, "answer_head.logit_fc.3", h), st
+
+
+def generate_ours(sd, cfg: LxmertConfig, ids, feats, boxes, index=None, normalize_self_attention=True,
+                  apply_self_in_rule_10=True, dtype=torch.float32):
+    """GeneratorOurs.generate_ours(use_lrp=False) per sample.  Returns (R_t_t [B,T,T], R_t_i [B,T,I], logits)."""
+    sd = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd.items()}
+    feats, boxes = feats.to(dtype), boxes.to(dtype)
+    logits, st = lxmert_forward(sd, cfg, ids, feats, boxes)
+    B, T = ids.shape
+    I = feats.shape[1]
+    idx = logits.argmax(-1) if index is None else torch.as_tensor(index).reshape(B)
+    y = logits[torch.arange(B), idx].sum()
+    names = ["lang", "vis", "x_lang", "x_vis", "x_lang_self", "x_vis_self"]
+    flat = [a for n in names for a in st[n]]
+    grads = torch.autograd.grad(y, flat, allow_unused=True)
+    G, k = {}, 0
+    for n in names:
+        G[n] = grads[k:k + len(st[n])]
+        k += len(st[n])
+    nx = cfg.x_layers
+    norm, s10 = normalize_self_attention, apply_self_in_rule_10
+    Rtt, Rti = [], []
+    for b in range(B):
+        cam = lambda n, i: R_.avg_heads(st[n][i][b].detach(), G[n][i][b])
+        R_tt, R_ii = torch.eye(T, dtype=dtype), torch.eye(I, dtype=dtype)
+        R_ti, R_it = torch.zeros(T, I, dtype=dtype), torch.zeros(I, T, dtype=dtype)
+        for i in range(cfg.l_layers):                                               # EG:61-71
+            a, c = R_.apply_self_attention_rules(R_tt, R_ti, cam("lang", i)); R_tt, R_ti = R_tt + a, R_ti + c
+        for i in range(cfg.r_layers):                                               # EG:73-83
+            a, c = R_.apply_self_attention_rules(R_ii, R_it, cam("vis", i)); R_ii, R_it = R_ii + a, R_it + c
+        for i in range(nx):
+            last = i == nx - 1
+            ti_add, tt_add = R_.apply_mm_attention_rules_lxmert(R_tt, R_ii, R_it, cam("x_lang", i), norm, s10)   # EG:107-116
+            if not last:
+                it_add, ii_add = R_.apply_mm_attention_rules_lxmert(R_ii, R_tt, R_ti, cam("x_vis", i), norm, s10)  # EG:118-129
+            R_ti, R_tt = R_ti + ti_add, R_tt + tt_add
+            if not last:
+                R_it, R_ii = R_it + it_add, R_ii + ii_add
+            a, c = R_.apply_self_attention_rules(R_tt, R_ti, cam("x_lang_self", i)); R_tt, R_ti = R_tt + a, R_ti + c
+            if not last:
+                a, c = R_.apply_self_attention_rules(R_ii, R_it, cam("x_vis_self", i)); R_ii, R_it = R_ii + a, R_it + c
+        R_tt[0, 0] = 0                                                               # EG:210
+        Rtt.append(R_tt); Rti.append(R_ti)
+    return torch.stack(Rtt), torch.stack(Rti), logits.detach()

@@ -99,12 +99,52 @@ def golden_rules():
     print("wrote rules", len(out))
 
 
+def golden_detr():
+    from . import detr_oracle as do, ref_detr
+    cfg = do.DETR_TINY
+    sd = do.init_state_dict(cfg, 5)
+    src, pos, tq = do.synthetic_inputs(cfg, 3, 3, 4, seed=1)
+    out = {"cfg": np.array([cfg.d_model, cfg.nhead, cfg.enc_layers, cfg.dec_layers, cfg.dim_ff, cfg.queries, cfg.classes]),
+           "src": src.numpy(), "pos": pos.numpy(), "tq": tq.numpy()}
+    for k, v in sd.items():
+        out["sd." + k] = v.numpy()
+    for norm in (True, False):
+        for s10 in (True, False):
+            r = ref_detr.generate_ours(cfg, sd, src, pos, tq, normalize_self_attention=norm, apply_self_in_rule_10=s10)
+            out[f"R.n{int(norm)}s{int(s10)}"] = r.numpy()
+    np.savez_compressed(os.path.join(OUT, "detr_tiny.npz"), **out)
+    print("wrote detr_tiny", out["R.n1s1"].shape)
+
+
+def golden_lxmert():
+    from . import lxmert_oracle as lo, ref_lxmert
+    cfg = lo.LXMERT_TINY
+    sd = lo.init_state_dict(cfg, 3)
+    ids, feats, boxes = lo.synthetic_inputs(cfg, 3, 6, 5, seed=2)
+    out = {"ids": ids.numpy(), "feats": feats.numpy(), "boxes": boxes.numpy()}
+    for k, v in sd.items():
+        out["sd." + k] = v.numpy()
+    for norm in (True, False):
+        for s10 in (True, False):
+            rtt, rti = ref_lxmert.generate_ours(cfg, sd, ids, feats, boxes, normalize_self_attention=norm,
+                                                apply_self_in_rule_10=s10)
+            out[f"Rtt.n{int(norm)}s{int(s10)}"], out[f"Rti.n{int(norm)}s{int(s10)}"] = rtt.numpy(), rti.numpy()
+    np.savez_compressed(os.path.join(OUT, "lxmert_tiny.npz"), **out)
+    print("wrote lxmert_tiny", out["Rtt.n1s1"].shape, out["Rti.n1s1"].shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-new" in __import__("sys").argv:
+        golden_detr()
+        golden_lxmert()
+        return
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     golden_rules()
     golden_clip("tiny", co.TINY, 3, wseed=1, iseed=7)
     golden_clip("small", co.SMALL, 4, wseed=2, iseed=11)
+    golden_detr()
+    golden_lxmert()
 
 
 if __name__ == "__main__":

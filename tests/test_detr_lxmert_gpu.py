@@ -1,0 +1,91 @@
+"""GPU: DETR Generator.generate_ours and LXMERT GeneratorOurs.generate_ours through the
+libmmx kernels vs the committed reference goldens and the oracle at the BASELINE.json shapes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import detr_oracle as do, lxmert_oracle as lo
+from util import rel_err, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd(g):
+    return {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+
+
+@pytest.mark.parametrize("norm,s10", [(True, True), (False, True), (True, False)])
+def test_detr_golden(golden_dir, norm, s10):
+    import mmx_b200
+    g = np.load(os.path.join(golden_dir, "detr_tiny.npz"))
+    eng = mmx_b200.DetrEngine(_sd(g), nhead=do.DETR_TINY.nhead, device="cuda:0")
+    gen = mmx_b200.Generator(eng)
+    src, pos, tq = (torch.from_numpy(g[k]) for k in ("src", "pos", "tq"))
+    out = gen.generate_ours((src.cuda(), pos.cuda()), tq, use_lrp=False, normalize_self_attention=norm,
+                            apply_self_in_rule_10=s10)
+    assert rel_err(out, g[f"R.n{int(norm)}s{int(s10)}"]) < TOL
+    # single-sample call: the reference's return shapes (tensor index -> [1,1,1,S], int -> [1,1,S])
+    one = gen.generate_ours((src[:1].cuda(), pos[:1].cuda()), torch.tensor([int(tq[0])]), use_lrp=False,
+                            normalize_self_attention=norm, apply_self_in_rule_10=s10)
+    assert one.shape == (1, 1, 1, src.shape[2] * src.shape[3])
+    assert rel_err(one.reshape(-1), g[f"R.n{int(norm)}s{int(s10)}"][0]) < TOL
+    assert gen.generate_ours((src[:1].cuda(), pos[:1].cuda()), int(tq[0]), use_lrp=False).shape == (1, 1, src.shape[2] * src.shape[3])
+    with pytest.raises(NotImplementedError):
+        gen.generate_ours((src.cuda(), pos.cuda()), tq)            # API default use_lrp=True: not silently ignored
+
+
+def test_detr_r50_shape_vs_oracle():
+    """DETR-R50 transformer dims (d=256, 8 heads, 6+6 layers, 100 queries) on a 10x12 feature map, batch 2, checkpoint
+    (packed in_proj) key format."""
+    import mmx_b200
+    cfg = do.DETR_R50
+    sd = do.init_state_dict(cfg, seed=9)
+    src, pos, tq = do.synthetic_inputs(cfg, 2, 10, 12, seed=4)
+    ref, stg = do.generate_ours(sd, cfg, src, pos, tq, return_stages=True)
+    packed = {k: v for k, v in do.to_checkpoint_format(sd).items() if "q_proj" not in k and "k_proj" not in k and "v_proj" not in k}
+    eng = mmx_b200.DetrEngine(packed, nhead=cfg.nhead, device="cuda:0")
+    out = mmx_b200.Generator(eng).generate_ours((src.cuda(), pos.cuda()), tq, use_lrp=False)
+    assert rel_err(eng.pred_logits, stg["logits"]) < TOL
+    rec = eng.decoder[-1].multihead_attn["rec"]
+    B, H = 2, cfg.nhead
+    assert rel_err(rec.get_attn(), stg["A_dc"][-1].reshape(B, H, cfg.queries, -1)) < TOL
+    assert rel_err(rec.get_attn_gradients(), stg["G_dc"][-1].reshape(B, H, cfg.queries, -1)) < TOL
+    assert rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("norm,s10", [(True, True), (False, True), (True, False)])
+def test_lxmert_golden(golden_dir, norm, s10):
+    import mmx_b200
+    g = np.load(os.path.join(golden_dir, "lxmert_tiny.npz"))
+    eng = mmx_b200.LxmertEngine(_sd(g), num_heads=lo.LXMERT_TINY.heads, device="cuda:0")
+    gen = mmx_b200.GeneratorOurs(eng)
+    ids, feats, boxes = (torch.from_numpy(g[k]) for k in ("ids", "feats", "boxes"))
+    rtt, rti = gen.generate_ours((ids.cuda(), feats.cuda(), boxes.cuda()), use_lrp=False, normalize_self_attention=norm,
+                                 apply_self_in_rule_10=s10)
+    key = f"n{int(norm)}s{int(s10)}"
+    assert rel_err(rtt, g["Rtt." + key]) < TOL and rel_err(rti, g["Rti." + key]) < TOL
+    rtt1, rti1 = gen.generate_ours((ids[:1].cuda(), feats[:1].cuda(), boxes[:1].cuda()), use_lrp=False,
+                                   normalize_self_attention=norm, apply_self_in_rule_10=s10)
+    assert rtt1.shape == (ids.shape[1], ids.shape[1]) and rti1.shape == (ids.shape[1], feats.shape[1])   # reference shapes
+    assert rel_err(rtt1, g["Rtt." + key][0]) < TOL and rel_err(rti1, g["Rti." + key][0]) < TOL
+    assert gen.R_i_i.shape == (feats.shape[1], feats.shape[1])       # left on self like the reference
+    # the last cross layer's image->text copy never receives a gradient
+    assert eng.x_layers[-1].cross.recs[1].get_attn_gradients() is None
+    with pytest.raises(NotImplementedError):
+        gen.generate_ours((ids.cuda(), feats.cuda(), boxes.cuda()))
+
+
+def test_lxmert_base_shape_vs_oracle():
+    """LXMERT base dims (768 hidden, 12 heads, 9/5/5 layers), 20 tokens x 36 boxes, batch 2 (BASELINE.json config 4)."""
+    import mmx_b200
+    cfg = lo.LxmertConfig(vocab=2000, num_labels=300)
+    sd = lo.init_state_dict(cfg, seed=1)
+    ids, feats, boxes = lo.synthetic_inputs(cfg, 2, 20, 36, seed=8)
+    ott, oti, logits = lo.generate_ours(sd, cfg, ids, feats, boxes)
+    eng = mmx_b200.LxmertEngine(sd, num_heads=cfg.heads, device="cuda:0")
+    rtt, rti = mmx_b200.GeneratorOurs(eng).generate_ours((ids.cuda(), feats.cuda(), boxes.cuda()), use_lrp=False)
+    assert rel_err(eng.question_answering_score, logits) < TOL
+    assert rel_err(rtt, ott) < TOL and rel_err(rti, oti) < TOL
+    assert (rtt[:, 0, 0] == 0).all()

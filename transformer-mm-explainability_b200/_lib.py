@@ -46,6 +46,12 @@ _SIGS = {
                              c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_linear_dgrad": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, C.c_int, c_float_p, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_add": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, C.c_float, c_float_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "mmx_gather_rows": (C.c_int, [c_float_p, C.c_int, c_int_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_scatter_add_rows": (C.c_int, [c_float_p, C.c_int, c_int_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_act_bwd": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, C.c_int, c_float_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "mmx_act_fwd": (C.c_int, [c_float_p, C.c_int, C.c_int, c_float_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "mmx_im2col_patches": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_layernorm_fwd": (C.c_int, [c_float_p, C.c_int, c_int_p, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p,
                                     c_float_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "mmx_layernorm_bwd": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_int_p, c_float_p, c_float_p, c_float_p,

@@ -8,6 +8,7 @@ namespace mmx {
 
 constexpr int TM = 128, TN = 128, TK = 16;
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restrict__ A, int lda,
                                                            const float* __restrict__ Bt, int ldb, float* __restrict__ C,
                                                            int ldc, int M, int N, int K, GemmEpilogue ep) {
@@ -26,8 +27,25 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
       const int gk = k0 + lk;
       ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + r < M && gk < K) ra[i] = *reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + gk);
-      if (n0 + r < N && gk < K) rb[i] = *reinterpret_cast<const float4*>(Bt + (long long)(n0 + r) * ldb + gk);
+      if (VEC) {
+        if (m0 + r < M && gk < K) ra[i] = *reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + gk);
+        if (n0 + r < N && gk < K) rb[i] = *reinterpret_cast<const float4*>(Bt + (long long)(n0 + r) * ldb + gk);
+      } else {   // arbitrary K / leading dims / alignment (e.g. the 3129-way LXMERT answer head)
+        if (m0 + r < M) {
+          const float* p = A + (long long)(m0 + r) * lda + gk;
+          if (gk + 0 < K) ra[i].x = p[0];
+          if (gk + 1 < K) ra[i].y = p[1];
+          if (gk + 2 < K) ra[i].z = p[2];
+          if (gk + 3 < K) ra[i].w = p[3];
+        }
+        if (n0 + r < N) {
+          const float* p = Bt + (long long)(n0 + r) * ldb + gk;
+          if (gk + 0 < K) rb[i].x = p[0];
+          if (gk + 1 < K) rb[i].y = p[1];
+          if (gk + 2 < K) rb[i].z = p[2];
+          if (gk + 3 < K) rb[i].w = p[3];
+        }
+      }
     }
   };
   auto store_smem = [&](int buf) {
@@ -89,11 +107,11 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
 
 int gemm_nt_simt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t st) {
-  MMX_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, "fp32 GEMM needs K, lda, ldb multiples of 4");
-  MMX_REQUIRE(aligned16(A) && aligned16(Bt), "fp32 GEMM operands must be 16-byte aligned");
   if (M == 0 || N == 0) return 0;
   dim3 grid(cdiv(N, TN), cdiv(M, TM));
-  gemm_nt_simt_kernel<<<grid, 256, 0, st>>>(A, lda, Bt, ldb, C, ldc, M, N, K, ep);
+  const bool vec = K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(Bt);
+  if (vec) gemm_nt_simt_kernel<true><<<grid, 256, 0, st>>>(A, lda, Bt, ldb, C, ldc, M, N, K, ep);
+  else gemm_nt_simt_kernel<false><<<grid, 256, 0, st>>>(A, lda, Bt, ldb, C, ldc, M, N, K, ep);
   MMX_LAUNCH_CHECK();
   return 0;
 }

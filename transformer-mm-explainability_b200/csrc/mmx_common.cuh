@@ -85,6 +85,7 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
     case MMX_ACT_QUICKGELU: return x / (1.f + expf(-1.702f * x));
     case MMX_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
     case MMX_ACT_RELU: return fmaxf(x, 0.f);
+    case MMX_ACT_TANH: return tanhf(x);
     default: return x;
   }
 }
@@ -100,6 +101,7 @@ __device__ __forceinline__ float act_bwd(float x, int act) {  // d act(x) / dx
       return cdf + x * pdf;
     }
     case MMX_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    case MMX_ACT_TANH: { const float t = tanhf(x); return 1.f - t * t; }
     default: return 1.f;
   }
 }

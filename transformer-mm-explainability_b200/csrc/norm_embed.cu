@@ -214,6 +214,35 @@ __global__ void __launch_bounds__(256) slice_out_kernel(const float* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                                   float alpha, float* __restrict__ out, int ldo, long long rows, int cols) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    out[r * ldo + c] = a[r * lda + c] + alpha * b[r * ldb + c];
+  }
+}
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int lds, const int* __restrict__ map,
+                                                          float* __restrict__ out, int ldo, int rows, int cols, int scatter_add) {
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    if (scatter_add) out[(long long)map[r] * ldo + c] += src[(long long)r * lds + c];
+    else out[(long long)r * ldo + c] = src[(long long)map[r] * lds + c];
+  }
+}
+__global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ pre, int ldpre,
+                                                  int act, float* __restrict__ out, int ldo, long long rows, int cols, int bwd) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float x = pre[r * ldpre + c];
+    out[r * ldo + c] = bwd ? dy[r * lddy + c] * act_bwd(x, act) : act_fwd(x, act);
+  }
+}
+
 static int grid_for(long long items) {
   long long g = (items + 255) / 256, cap = (long long)sm_count() * 8;
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
@@ -274,6 +303,43 @@ int slice_out(const float* src, long long plane, int ld, int r0, int c0, float* 
 
 using namespace mmx;
 extern "C" {
+int mmx_add(const float* a, int lda, const float* b, int ldb, float alpha, float* out, int ldo, long long rows, int cols,
+            void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  add_kernel<<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, alpha, out, ldo, rows, cols);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int mmx_gather_rows(const float* src, int lds, const int32_t* row_map, float* out, int ldo, int rows, int cols, void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  gather_rows_kernel<<<grid_for((long long)rows * cols), 256, 0, (cudaStream_t)stream>>>(src, lds, row_map, out, ldo, rows, cols, 0);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int mmx_scatter_add_rows(const float* src, int lds, const int32_t* row_map, float* dst, int ldd, int rows, int cols,
+                         void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  gather_rows_kernel<<<grid_for((long long)rows * cols), 256, 0, (cudaStream_t)stream>>>(src, lds, row_map, dst, ldd, rows, cols, 1);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int mmx_act_bwd(const float* dy, int lddy, const float* pre, int ldpre, int act, float* dx, int lddx, long long rows, int cols,
+                void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  act_kernel<<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(dy, lddy, pre, ldpre, act, dx, lddx, rows, cols, 1);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int mmx_act_fwd(const float* x, int ldx, int act, float* y, int ldy, long long rows, int cols, void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  act_kernel<<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(nullptr, 0, x, ldx, act, y, ldy, rows, cols, 0);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+int mmx_im2col_patches(const float* images, float* patches, int n_images, int resolution, int patch, void* stream) {
+  MMX_REQUIRE(patch > 0 && resolution % patch == 0, "resolution must be a multiple of patch");
+  return im2col_patches(images, patches, n_images, resolution, patch, (cudaStream_t)stream);
+}
 int mmx_layernorm_fwd(const float* x, int ldx, const int* row_map, const float* gamma, const float* beta, float* y, int ldy,
                       float* mean, float* rstd, int rows, int D, float eps, void* stream) {
   return layernorm_fwd(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, D, eps, (cudaStream_t)stream);

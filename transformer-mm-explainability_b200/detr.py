@@ -1,0 +1,185 @@
+"""DETR encoder-decoder relevancy: ``Generator(model).generate_ours(...)`` with the
+reference signature (DETR/modules/ExplanationGenerator.py:142-195) over the libmmx kernels.
+
+``DetrEngine`` holds the DETR transformer + class head (DETR/models/transformer.py, DETR/models/detr.py:46-77) built
+from a reference / official-checkpoint ``state_dict`` and runs on backbone features: ``img`` is ``(src, pos)`` with
+``src`` [B, d_model, h, w] (after ``input_proj``) and ``pos`` the sine embedding [B or 1, d_model, h, w].  The ResNet
+backbone sits below every attention layer (no gradient needed) and is outside the hot-path scope of this round.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from ._lib import lib, check, ptr, current_stream, MmxError
+from .nn import Tape, Var, Weight, AttnRecord, ACT_RELU, _f32
+from . import rules
+
+
+def _split_mha(sd, p, device):
+    """q/k/v/out projections of one attention module; accepts split keys or the packed ``in_proj_weight`` of the
+    official checkpoints (split by the reference in DETR/modules/layers.py:711-726)."""
+    if p + "q_proj.weight" in sd:
+        q, k, v = ((sd[p + n + ".weight"], sd[p + n + ".bias"]) for n in ("q_proj", "k_proj", "v_proj"))
+    else:
+        w, b = sd[p + "in_proj_weight"], sd[p + "in_proj_bias"]
+        d = w.shape[1]
+        q, k, v = ((w[i * d:(i + 1) * d], b[i * d:(i + 1) * d]) for i in range(3))
+    return dict(q=Weight(*q, device), k=Weight(*k, device), v=Weight(*v, device),
+                o=Weight(sd[p + "out_proj.weight"], sd[p + "out_proj.bias"], device), rec=AttnRecord())
+
+
+class _Layer:
+    pass
+
+
+class DetrEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], nhead: int = 8, device=None):
+        if not torch.cuda.is_available():
+            raise MmxError("mmx_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
+        self.device = d = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        sd = {(k if k.startswith(("transformer.", "class_embed", "query_embed")) else "transformer." + k): v
+              for k, v in state_dict.items()}
+        self.nhead = nhead
+        n_enc = len({k.split(".")[3] for k in sd if k.startswith("transformer.encoder.layers.")})
+        n_dec = len({k.split(".")[3] for k in sd if k.startswith("transformer.decoder.layers.")})
+        ln = lambda p: (_f32(sd[p + ".weight"], d), _f32(sd[p + ".bias"], d))
+        self.encoder, self.decoder = [], []
+        for i in range(n_enc):
+            p = f"transformer.encoder.layers.{i}."
+            L = _Layer()
+            L.self_attn = _split_mha(sd, p + "self_attn.", d)
+            L.l1 = Weight(sd[p + "linear1.weight"], sd[p + "linear1.bias"], d)
+            L.l2 = Weight(sd[p + "linear2.weight"], sd[p + "linear2.bias"], d)
+            L.n1, L.n2 = ln(p + "norm1"), ln(p + "norm2")
+            self.encoder.append(L)
+        for i in range(n_dec):
+            p = f"transformer.decoder.layers.{i}."
+            L = _Layer()
+            L.self_attn = _split_mha(sd, p + "self_attn.", d)
+            L.multihead_attn = _split_mha(sd, p + "multihead_attn.", d)
+            L.l1 = Weight(sd[p + "linear1.weight"], sd[p + "linear1.bias"], d)
+            L.l2 = Weight(sd[p + "linear2.weight"], sd[p + "linear2.bias"], d)
+            L.n1, L.n2, L.n3 = ln(p + "norm1"), ln(p + "norm2"), ln(p + "norm3")
+            self.decoder.append(L)
+        self.dec_norm = ln("transformer.decoder.norm")
+        self.query_embed = _f32(sd["query_embed.weight"], d)
+        self.class_embed = Weight(sd["class_embed.weight"], sd["class_embed.bias"], d)
+        self.d_model = self.query_embed.shape[1]
+        self.queries = self.query_embed.shape[0]
+        self.pred_logits: Optional[torch.Tensor] = None
+
+    def eval(self):
+        return self
+
+    def zero_grad(self):
+        return None
+
+    def _mha(self, tape: Tape, m, query: Var, key: Var, value: Var, B, T, S) -> Var:
+        """DETR/modules/layers.py:728-768: separate projections, q scaled before q k^T, masks ignored."""
+        H = self.nhead
+        q, k, v = tape.linear(query, m["q"]), tape.linear(key, m["k"]), tape.linear(value, m["v"])
+        o = tape.attention(q, k, v, B, H, T, S, float(self.d_model // H) ** -0.5, 0, None, m["rec"])
+        return tape.linear(o, m["o"])
+
+    def forward_backward(self, src: torch.Tensor, pos: torch.Tensor, target_index, index=None):
+        """Forward staging every A, one-hot on pred_logits[b, target_b, class_b], backward staging every dA."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            B, d, h, w = src.shape
+            S, Q = h * w, self.queries
+            tape = Tape(dev)
+            x = Var(_f32(src, dev).flatten(2).permute(0, 2, 1).reshape(B * S, d).contiguous())
+            pe = _f32(pos, dev).expand(B, d, h, w).flatten(2).permute(0, 2, 1).reshape(B * S, d).contiguous()
+            qe = self.query_embed.repeat(B, 1)                                    # [B*Q, d]
+            for L in self.encoder:                                                # transformer.py:230-254
+                qk = tape.add_const(x, pe)
+                x = tape.layernorm(tape.add(x, self._mha(tape, L.self_attn, qk, qk, x, B, S, S)), *L.n1, 1e-5)
+                ff = tape.linear(tape.linear(x, L.l1, ACT_RELU), L.l2)
+                x = tape.layernorm(tape.add(x, ff), *L.n2, 1e-5)
+            memory = x
+            mem_pe = tape.add_const(memory, pe)
+            t = Var(torch.zeros(B * Q, d, device=dev))
+            for L in self.decoder:                                                # transformer.py:372-408
+                qk = tape.add_const(t, qe)
+                t = tape.layernorm(tape.add(t, self._mha(tape, L.self_attn, qk, qk, t, B, Q, Q)), *L.n1, 1e-5)
+                tq = tape.add_const(t, qe)
+                t = tape.layernorm(tape.add(t, self._mha(tape, L.multihead_attn, tq, mem_pe, memory, B, Q, S)), *L.n2, 1e-5)
+                ff = tape.linear(tape.linear(t, L.l1, ACT_RELU), L.l2)
+                t = tape.layernorm(tape.add(t, ff), *L.n3, 1e-5)
+            hs = tape.layernorm(t, *self.dec_norm, 1e-5)
+            logits = tape.linear(hs, self.class_embed)                             # [B*Q, C+1]
+            C1 = logits.cols
+            self.pred_logits = logits.v.view(B, Q, C1)
+            tq_idx = torch.as_tensor(target_index, device=dev).reshape(B).long()
+            rows = torch.arange(B, device=dev) * Q + tq_idx
+            if index is None:                                                      # ExplanationGenerator.py:151-152
+                cls = logits.v[rows, :-1].argmax(-1)
+            else:
+                cls = torch.as_tensor(index, device=dev).reshape(B).long()
+            one_hot = torch.zeros_like(logits.v)
+            one_hot[rows, cls] = 1.0
+            logits.g = one_hot
+            tape.backward()
+            self._shape = (B, S, Q)
+        return {"pred_logits": self.pred_logits}
+
+
+class Generator:
+    """DETR/modules/ExplanationGenerator.py:56-195 (``generate_ours`` and its three handlers)."""
+
+    def __init__(self, model: DetrEngine):
+        if not isinstance(model, DetrEngine):
+            raise MmxError("model must be a mmx_b200.DetrEngine")
+        self.model = model
+        self.model.eval()
+
+    def handle_self_attention_image(self, blocks):                                 # :110-118
+        for blk in blocks:
+            cam = rules.avg_heads_record(blk.self_attn["rec"], self.B)
+            self.R_i_i, _ = rules.self_update(self.R_i_i, cam)
+
+    def handle_co_attn_self_query(self, block):                                    # :120-129
+        cam = rules.avg_heads_record(block.self_attn["rec"], self.B)
+        self.R_q_q, self.R_q_i = rules.self_update(self.R_q_q, cam, self.R_q_i)
+
+    def handle_co_attn_query(self, block):                                         # :131-140
+        cam_q_i = rules.avg_heads_record(block.multihead_attn["rec"], self.B)
+        add, _, md = rules.mm_update_batched(self.R_q_q, self.R_i_i, None, cam_q_i,
+                                             apply_normalization=self.normalize_self_attention,
+                                             apply_self_in_rule_10=self.apply_self_in_rule_10, nan_to_zero=True)
+        self._min_diag.append(md)
+        self.R_q_i = rules.add(self.R_q_i, add)
+
+    def generate_ours(self, img, target_index, index=None, use_lrp=True, normalize_self_attention=True,
+                      apply_self_in_rule_10=True):
+        if use_lrp:
+            raise NotImplementedError("use_lrp=True (LRP relprop sweep, DETR/modules/layers.py:770-801) is outside the "
+                                      "hot-path scope; call with use_lrp=False as the notebooks and the ours_no_lrp CLI do")
+        self.use_lrp = use_lrp
+        self.normalize_self_attention = normalize_self_attention
+        self.apply_self_in_rule_10 = apply_self_in_rule_10
+        src, pos = img
+        m = self.model
+        m.forward_backward(src, pos, target_index, index)
+        B, S, Q = m._shape
+        self.B = B
+        dev = m.device
+        self._min_diag: List[torch.Tensor] = []
+        self.R_i_i = torch.eye(S, device=dev).repeat(B, 1, 1)                       # :176-180
+        self.R_q_q = torch.eye(Q, device=dev).repeat(B, 1, 1)
+        self.R_q_i = torch.zeros(B, Q, S, device=dev)
+        self.handle_self_attention_image(m.encoder)
+        for blk in m.decoder:
+            self.handle_co_attn_self_query(blk)
+            self.handle_co_attn_query(blk)
+        if normalize_self_attention and apply_self_in_rule_10 and self._min_diag:
+            assert torch.stack(self._min_diag).min().item() >= 0                     # handle_residual's assert (:50)
+        tq = torch.as_tensor(target_index, device=dev).reshape(B).long()
+        picked = self.R_q_i[torch.arange(B, device=dev), tq]                        # [B, S]
+        if B == 1:                                                                   # reference return shapes (:192-194)
+            self.R_q_i = self.R_q_i                                                  # [1, Q, S] like unsqueeze_(0)
+            return picked.view(1, 1, 1, S) if isinstance(target_index, torch.Tensor) else picked.view(1, 1, S)
+        return picked

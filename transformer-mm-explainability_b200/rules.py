@@ -31,6 +31,18 @@ def avg_heads_batched(cam: torch.Tensor, grad: torch.Tensor, batch: int) -> torc
     return out
 
 
+def avg_heads_record(rec, batch: int) -> torch.Tensor:
+    """Rule 5 straight from an attention record (nn.AttnRecord): reads the zero-padded staged A / dA in place."""
+    A, dA, ld = rec.padded()
+    if dA is None:
+        raise MmxError("no attention gradient recorded (backward did not reach this attention)")
+    B, H, T = A.shape[0], A.shape[1], A.shape[2]
+    assert B == batch
+    out = torch.empty(B, T, rec.S, device=A.device, dtype=torch.float32)
+    check(lib().mmx_avg_heads(ptr(A), ptr(dA), ptr(out), B, H, T, rec.S, ld, rec.S, current_stream()))
+    return out
+
+
 def avg_heads(cam: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
     """Rule 5 (DETR/modules/ExplanationGenerator.py:19-24): all leading dims are heads of ONE sample."""
     return avg_heads_batched(cam, grad, 1)[0]
@@ -128,3 +140,35 @@ def compute_rollout_attention(all_layer_matrices, start_layer=0, normalize=True)
     ws = torch.empty(2, B, S, S, device=mats.device, dtype=torch.float32)
     check(lib().mmx_rollout(ptr(mats), L, B, S, start_layer, 1 if normalize else 0, ptr(out), ptr(ws), current_stream()))
     return out[0] if squeeze else out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a + b for equally shaped fp32 CUDA tensors (the ``R += addition`` of the generators)."""
+    a, b = _prep(a), _prep(b)
+    out = torch.empty_like(a)
+    cols = a.shape[-1]
+    rows = a.numel() // cols
+    import ctypes as C
+    check(lib().mmx_add(ptr(a), cols, ptr(b), cols, C.c_float(1.0), ptr(out), cols, rows, cols, current_stream()))
+    return out
+
+
+def mm_update_batched(R_ss, R_qq, R_qs, cam_sq, apply_normalization=True, apply_self_in_rule_10=True, nan_to_zero=False):
+    """Batched rules 10+11: R_ss [B,T,T], R_qq [B,S,S], R_qs [B,S,T] or None, cam_sq [B,T,S].
+    Returns (R_sq_addition [B,T,S], R_ss_addition [B,T,T] or None, min_diag [2] device tensor for the reference's
+    ``assert diag(R - I) >= 0``)."""
+    Rs, Rq, Ab = _prep(R_ss), _prep(R_qq), _prep(cam_sq)
+    B, T, S = Ab.shape
+    flags = (MM_NORMALIZE if apply_normalization else 0) | (MM_SELF_IN_10 if apply_self_in_rule_10 else 0) | \
+            (MM_NAN_TO_ZERO if nan_to_zero else 0)
+    l = lib()
+    ws = torch.empty(l.mmx_mm_update_workspace(B, T, S) // 4 + 4, device=Rs.device, dtype=torch.float32)
+    sq_add = torch.empty(B, T, S, device=Rs.device, dtype=torch.float32)
+    Rqs = ss_add = None
+    if R_qs is not None:
+        Rqs = _prep(R_qs)
+        ss_add = torch.empty(B, T, T, device=Rs.device, dtype=torch.float32)
+    md = torch.zeros(2, device=Rs.device, dtype=torch.float32)
+    check(l.mmx_mm_update(ptr(Rs), T, ptr(Rq), S, ptr(Rqs), T, ptr(Ab), S, ptr(sq_add), S, ptr(ss_add), T, B, T, S, flags,
+                          ptr(ws), ptr(md), current_stream()))
+    return sq_add, ss_add, md
