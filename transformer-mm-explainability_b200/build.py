@@ -13,7 +13,8 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmmx.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("MMX_PTXAS_V") else "-O3"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("MMX_PTXAS_V") else "-O3"] + \
+    os.environ.get("MMX_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

@@ -29,6 +29,8 @@ bool gemm_tc_shape_ok(const float* A, int lda, const float* Bt, int ldb, float* 
 int gemm_nt_tc(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
                const GemmEpilogue& ep, cudaStream_t st);
 
+void gemm_tc_set_trace(long long* buf);
+
 int gemm_backend() {
   int b = g_backend.load();
   if (b < 0) {
@@ -110,6 +112,10 @@ int mmx_profile_gemm_report(double* total_ms, double* total_flops, int* launches
   return 0;
 }
 
+int mmx_gemm_trace(long long* device_buf) {
+  gemm_tc_set_trace(device_buf);
+  return 0;
+}
 int mmx_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
   MMX_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;

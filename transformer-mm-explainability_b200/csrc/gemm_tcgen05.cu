@@ -134,9 +134,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
+#ifdef MMX_TC_TRACE   // build with -DMMX_TC_TRACE for profiles/gemm_trace.py; off in the product (it costs ~15 %)
+#define MMX_TRACE(role, idx, slot)                                                                  \
+  do {                                                                                               \
+    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 256) p.trace[((role) * 256 + (idx)) * 4 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define MMX_TRACE(role, idx, slot) do { } while (0)
+#endif
+
 struct Params {
   int M, N, K, ldc;
-  int dbg;   // timing experiments only (results invalid): 1 = no MMAs, 2 = no splitter work, 4 = no TMA, 8 = no epilogue stores
+  long long* trace;   // optional device buffer [4 roles][256 events][4]: clock64 timeline of CTA 0 (profiling aid)
+  int dbg;   // experiments only: 1 = no MMAs, 2 = no splitter work, 4 = no TMA, 8 = no epilogue stores (results invalid);
+             // 16 = also write the explicit B hi plane (results identical)
   float* C;
   GemmEpilogue ep;
 };
@@ -181,10 +192,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int pslab = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
         for (int kb = 0; kb < nk; ++kb) {
           mbar_spin(empty_bar(stage), phase ^ 1);
+          MMX_TRACE(0, pslab, 0);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           if (p.dbg & 4) { mbar_arrive(full_bar(stage)); }
           else {
@@ -192,6 +205,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
           tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m0);
           tma_load_2d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0);
           }
+          MMX_TRACE(0, pslab, 1);
+          ++pslab;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -201,13 +216,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
+      int it = 0, mslab = 0;
       const uint32_t d_main = tmem_base + TM_MAIN, d_cross = tmem_base + TM_CROSS;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         mbar_spin(tempty_bar, (uint32_t)(it & 1) ^ 1);           // epilogue drained the accumulators
         tc_fence_after();
         for (int kb = 0; kb < nk; ++kb) {
           mbar_spin(split_bar(stage), phase);                   // A hi/lo in TMEM (implies the TMA landed B too)
+          MMX_TRACE(1, mslab, 0);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint64_t b_hi = make_desc(sa + A_BYTES), b_lo = make_desc(sa + A_BYTES + B_BYTES);
@@ -221,8 +237,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
             umma_tf32_ts(d_cross, a_hi + 8u * k, b_lo + adv, idesc, 1u);
             umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + adv, idesc, first);
           }
+          MMX_TRACE(1, mslab, 1);
           umma_commit(empty_bar(stage));                        // frees the stage (smem + TMEM A slab) when these MMAs retire
           if (kb == nk - 1) umma_commit(tfull_bar);             // accumulators complete -> epilogue
+          MMX_TRACE(1, mslab, 2);
+          ++mslab;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -242,6 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         const uint32_t phase = (uint32_t)((slab / STAGES) & 1);
         if (lane == 0) mbar_spin(full_bar(stage), phase);       // one polling lane per warp, no suspend/wake-up latency
         __syncwarp();
+        if (warp == SPLIT_WARP0 && lane == 0) MMX_TRACE(2, (int)slab, 0);
         if (p.dbg & 2) { __syncwarp(); if (lane == 0) mbar_arrive(split_bar(stage)); continue; }
         // B slab: raw -> hi (in place) + lo plane; elementwise, so the swizzle does not matter
         uint4* braw = reinterpret_cast<uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES);
@@ -259,7 +279,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
             l.y = __float_as_uint(__uint_as_float(x[u].y) - __uint_as_float(h.y));
             l.z = __float_as_uint(__uint_as_float(x[u].z) - __uint_as_float(h.z));
             l.w = __float_as_uint(__uint_as_float(x[u].w) - __uint_as_float(h.w));
-            braw[i0 + u * 128 + gtid] = h;
+            // The tensor core reads only the top 19 bits of an fp32 operand (kind::tf32 truncates; measured: results
+            // are bit-identical with and without writing hi back), so the raw tile already IS the hi plane.
+            if (p.dbg & 16) braw[i0 + u * 128 + gtid] = h;       // dbg 16: write the explicit hi plane anyway (A/B test)
             blo[i0 + u * 128 + gtid] = l;
           }
         }
@@ -278,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const uint32_t h = xv[e] & 0xFFFFE000u;
-              hi[c * 4 + e] = h;
+              hi[c * 4 + e] = xv[e];                              // raw fp32: the MMA truncates it to hi itself
               lo[c * 4 + e] = __float_as_uint(__uint_as_float(xv[e]) - __uint_as_float(h));
             }
           }
@@ -289,6 +311,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(split_bar(stage));
+        if (warp == SPLIT_WARP0 && lane == 0) MMX_TRACE(2, (int)slab, 1);
       }
     }
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
@@ -300,6 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
       if (lane == 0) mbar_spin(tfull_bar, (uint32_t)(it & 1));
       __syncwarp();
+      if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 0);
       tc_fence_after();
       // drain main + cross accumulators into registers (RN add), then hand TMEM back before any global traffic
       uint32_t acc[64];
@@ -315,6 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);                  // next tile's MMAs may start
+      if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 1);
       const int m = m0 + q * 32 + lane;
       if (m < p.M && !(p.dbg & 8)) {
         float* crow = p.C + (long long)m * p.ldc;
@@ -349,6 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
           }
         }
       }
+      if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 2);
     }
   }
   // ---------------------------------------------------------------------- teardown
@@ -361,6 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static long long* g_trace = nullptr;
 static int g_avail = -1;
 
 static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
@@ -390,7 +417,7 @@ static int launch(const float* A, int lda, const float* Bt, int ldb, float* C, i
   }
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("MMX_TC_DBG"); dbg = e ? atoi(e) : 0; }
-  Params p{M, N, K, ldc, dbg, C, ep};
+  Params p{M, N, K, ldc, g_trace, dbg, C, ep};
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tf32x3_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
@@ -416,6 +443,10 @@ int gemm_tc_available() {
   tc::g_avail = 1;
   return 1;
 }
+
+// Profiling aid: the next tensor-core GEMM launches write CTA 0's clock64 timeline into `buf`
+// ([4 roles][256 events][4] int64: producer, MMA issuer, splitter, epilogue); nullptr switches it off.
+void gemm_tc_set_trace(long long* buf) { tc::g_trace = buf; }
 
 // Which problems go to the tensor-core kernel.  Deliberately independent of M, so that a sample computed alone
 // and the same sample inside a batch take the same arithmetic path (bitwise-equal maps, sharded == single GPU).
