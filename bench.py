@@ -247,6 +247,7 @@ def main():
 
     # ---- roofline of the dominant kernel (the transformer GEMMs), CUDA events per launch inside the pipeline
     hbm_peak, tf_burst, tf_sust, peak_src = _peaks()
+    gemm_backend = lib.mmx_set_gemm_backend(int(os.environ.get('MMX_GEMM_BACKEND', '1')))
     lib.mmx_profile_gemm(1)
     prof_steps = 3
     for _ in range(prof_steps):
@@ -255,7 +256,7 @@ def main():
     tms, tfl, nl = C.c_double(), C.c_double(), C.c_int()
     lib.mmx_profile_gemm_report(C.byref(tms), C.byref(tfl), C.byref(nl))
     gemm_tflops = tfl.value / (tms.value * 1e-3) / 1e12 if tms.value > 0 else 0.0
-    roofline = {"kernel": "transformer GEMMs (" + ("tcgen05 3xTF32" if lib.mmx_set_gemm_backend(1) == 1 else "fp32 FFMA") + ")",
+    roofline = {"kernel": "transformer GEMMs (" + {0: "fp32 FFMA", 1: "tcgen05 3xTF32, 1 CTA/tile", 2: "tcgen05 3xTF32, cta_group::2"}[gemm_backend] + ")",
                 "bound": "tensor", "achieved": gemm_tflops, "peak": tf_sust, "unit": "TFLOP/s",
                 "frac": gemm_tflops / tf_sust, "traffic": None, "peak_source": peak_src + " bf16 dense, sustained",
                 "launches_per_step": nl.value // prof_steps, "gemm_ms_per_step": tms.value / prof_steps,

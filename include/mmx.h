@@ -31,8 +31,10 @@ const char* mmx_last_error(void);
 int mmx_version(void);
 /* Number of kernels this library has launched since load (all streams); the bench reports it as gpu_launches. */
 uint64_t mmx_launch_count(void);
-/* Selects the GEMM backend for the transformer linears: 0 = fp32 FFMA (bisecting reference),
- * 1 = tcgen05 3xTF32 (default when available).  Returns the backend in effect. */
+/* Selects the GEMM backend for the transformer linears: 0 = fp32 FFMA (bisecting reference), 1 = tcgen05 3xTF32
+ * one CTA per tile (default when available), 2 = tcgen05 3xTF32 CTA pairs (cta_group::2; correct, but measured
+ * slower in round 1 - see profiles/gemm_ablation_r1.md).  Env MMX_GEMM_BACKEND overrides the default.  Returns the
+ * backend in effect. */
 int mmx_set_gemm_backend(int backend);
 /* Per-launch CUDA-event timing of the transformer GEMMs (the dominant kernel): enable=1 opens a window, enable=0
  * closes it; the report synchronises the device and returns the summed launch durations, the algorithmic FLOPs

@@ -19,10 +19,10 @@ def main():
     l = lib()
     out = []
     global SHAPES
-    backends = (0, 1)
+    backends = (0, 1, 2)
     if "--only" in sys.argv:            # e.g. --only 3200,2304,768  (tcgen05 backend only; for ncu captures)
         SHAPES = [tuple(int(v) for v in sys.argv[sys.argv.index("--only") + 1].split(","))]
-        backends = (1,)
+        backends = (int(sys.argv[sys.argv.index('--backend') + 1]),) if '--backend' in sys.argv else (2,)
     for backend in backends:
         if l.mmx_set_gemm_backend(backend) != backend:
             continue

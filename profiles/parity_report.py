@@ -20,7 +20,7 @@ def main():
     eng = mmx_b200.ClipEngine(mmx_b200.ClipConfig(*cfg.ref_args()), sd, max_batch=B, device="cuda:0")
     dtype = torch.float64 if "--fp64" in sys.argv else torch.float32
     ot, oi, stg = co.clip_interpret(sd, cfg, images, tokens, 0, 0, return_stages=True, dtype=dtype)
-    for backend in (0, 1):
+    for backend in (0, 1, 2):
         if mmx_b200.lib().mmx_set_gemm_backend(backend) != backend:
             continue
         rt, ri = mmx_b200.interpret(images.cuda(), tokens.cuda(), eng, "cuda:0", 0, 0)

@@ -22,7 +22,7 @@ def L():
 ACTS = {0: lambda x: x, 1: lambda x: x * torch.sigmoid(1.702 * x), 2: lambda x: F.gelu(x), 3: lambda x: F.relu(x)}
 
 
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K", [(3200, 2304, 768), (4928, 512, 2048), (64, 512, 768), (37, 96, 64), (1, 8, 4),
                                    (130, 260, 36), (3136, 768, 3072)])
 def test_linear_and_dgrad(L, backend, M, N, K):

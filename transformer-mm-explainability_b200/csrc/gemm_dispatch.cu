@@ -2,6 +2,7 @@
 #include "gemm.cuh"
 #include <mutex>
 #include <vector>
+#include <cstdlib>
 
 namespace mmx {
 
@@ -28,6 +29,9 @@ bool gemm_tc_shape_ok(const float* A, int lda, const float* Bt, int ldb, float* 
                       const GemmEpilogue& ep);
 int gemm_nt_tc(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
                const GemmEpilogue& ep, cudaStream_t st);
+// gemm_tcgen05_2cta.cu
+int gemm_nt_tc2(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+                const GemmEpilogue& ep, cudaStream_t st);
 
 void gemm_tc_set_trace(long long* buf);
 
@@ -35,6 +39,8 @@ int gemm_backend() {
   int b = g_backend.load();
   if (b < 0) {
     b = gemm_tc_available() ? 1 : 0;
+    const char* env = getenv("MMX_GEMM_BACKEND");
+    if (env && b) b = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));
     g_backend.store(b);
   }
   return b;
@@ -42,8 +48,10 @@ int gemm_backend() {
 
 static int gemm_nt_impl(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
                         const GemmEpilogue& ep, cudaStream_t st) {
-  if (gemm_backend() == 1 && gemm_tc_shape_ok(A, lda, Bt, ldb, C, ldc, N, K, ep))
-    return gemm_nt_tc(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
+  const int be = gemm_backend();
+  if (be >= 1 && gemm_tc_shape_ok(A, lda, Bt, ldb, C, ldc, N, K, ep))
+    return be == 2 ? gemm_nt_tc2(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st)
+                   : gemm_nt_tc(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
   return gemm_nt_simt(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
 }
 
@@ -83,8 +91,10 @@ const char* mmx_last_error(void) { return mmx::last_error(); }
 int mmx_version(void) { return MMX_VERSION; }
 uint64_t mmx_launch_count(void) { return g_launches.load(); }
 int mmx_set_gemm_backend(int backend) {
-  if (backend == 1 && !gemm_tc_available()) backend = 0;
-  g_backend.store(backend ? 1 : 0);
+  if (backend < 0) backend = 0;
+  if (backend > 2) backend = 2;
+  if (backend >= 1 && !gemm_tc_available()) backend = 0;
+  g_backend.store(backend);
   return g_backend.load();
 }
 

@@ -1,28 +1,18 @@
-// tcgen05 (5th-gen tensor core) GEMM with fp32-faithful numerics:  C[M,N] = A[M,K] * Bt[N,K]^T  (+ epilogue).
+// tcgen05 3xTF32 GEMM, CTA-pair version (cta_group::2): one 256x128 output tile per pair of SMs.
 //
-// Why 3xTF32: the relevancy maps must match the fp32 reference to 1e-4 after ~100 chained GEMMs (forward +
-// dgrad), which rules out plain TF32/BF16 inputs.  Each fp32 operand x is split exactly into
-//      x = hi + lo,   hi = x with the low 13 mantissa bits cleared (a TF32 value),  lo = x - hi (exact in fp32)
-// and the product is A_hi*B_hi + (A_lo*B_hi + A_hi*B_lo); the dropped lo*lo term and the TF32 rounding of lo are both
-// ~2^-21 relative.  The tensor core adds into its fp32 accumulator with truncation (measured: error grows linearly
-// with the number of accumulating MMAs), so the two small cross products go to their OWN TMEM accumulator (their
-// truncation error is 2^-11 smaller) and are added to the hi*hi accumulator once, in the epilogue, with RN.
+// Why a pair: in the single-CTA kernel (gemm_tcgen05.cu) every K-slab costs 12 tcgen05.mma issues + a commit on ONE
+// thread (~57 clk per issue, measured) for 12 x 64 clk of tensor work, and the B operand is split and fetched from
+// shared memory once per CTA.  With cta_group::2 the leader's 12 issues drive BOTH SMs (12 x 128 clk of work each),
+// and each CTA loads / splits / serves only HALF of the B tile (64 of the 128 N-rows), so the issue cost and the
+// B-related shared-memory traffic per flop are halved.  Everything else (raw fp32 through L2 once, A split in
+// registers into TMEM, separate cross-term accumulator, TMEM drained to registers before the global epilogue) is
+// the same as in the single-CTA kernel; see the header comment there.
 //
-// A 3-pass fp32 GEMM is limited by operand movement, not by the tensor pipe: measured on B200, L2->SM delivers
-// ~24 B/clk/SM with all 148 SMs pulling, and shared memory serves 128 B/clk/SM to TMA writes, LSU traffic and the
-// UMMA operand fetch together.  So both operands cross L2 ONCE as raw fp32 and are split on the SM:
-//   * A (activations): raw tile -> registers -> hi/lo -> TMEM (tcgen05.st); the MMAs take A from TMEM (.ts form),
-//     so A costs one shared-memory read instead of three operand fetches;
-//   * B (weights): raw tile split in shared memory (hi in place, lo beside it), fetched by the MMAs from there.
-//
-// Structure (one CTA per SM, persistent over 128x128 output tiles, 4-stage ring of 128x32 K-slabs):
-//   warp 0      TMA producer: raw fp32 A and B tiles -> shared memory (128-byte swizzle), mbarrier complete_tx
-//   warps 12-19 splitters (two per TMEM lane quarter, each converts half of the slab's K columns): A tile (smem) -> hi/lo -> TMEM columns of this
-//               stage; B tile -> hi/lo planes in smem
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (3 per k-step), tcgen05.commit
-//   warp 2      TMEM allocator (512 columns: 128 main + 128 cross accumulator + 4 stages x 64 columns of A)
-//   warps 4-11  epilogue: tcgen05.ld (main + cross, added with RN) -> registers, TMEM released at once, then
-//               bias / act' / residual / act -> global from registers (overlaps the next tile's main loop)
+// Per CTA (rank r of the pair): A slab rows [128r, 128r+128) of the 256-row tile -> own TMEM; B rows [64r, 64r+64)
+// -> own shared memory (raw = hi plane, lo plane beside it); accumulators (main, cross) for its own 128 rows.
+// Barriers: full[s] (TMA, local) -> splitter -> split_done[s] on the LEADER (8 warp arrivals, remote for rank 1) ->
+// leader issues the MMAs -> tcgen05.commit multicast to empty[s] / tmem_full of BOTH CTAs -> epilogue warps of both
+// CTAs -> tmem_empty on the leader (16 warp arrivals).
 #include "gemm.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -30,18 +20,16 @@
 
 namespace mmx {
 
-namespace tc {
+namespace tc2 {
 
 constexpr int BM = 128, BN = 128, BK = 32;    // BK fp32 = 128 bytes = one swizzle-128B row
-constexpr int SPLIT_WARPS = 8;                 // two warps per TMEM lane quarter, each takes half of the slab's K columns
-constexpr int THREADS = (12 + SPLIT_WARPS) * 32;   // 4 control + 8 epilogue + 8 splitter warps = 640 threads
-// 65536 / 640 = 102 -> ptxas budget 96 regs/thread; the epilogue needs ~128, the other roles far fewer, so the
-// warpgroups rebalance at run time (setmaxnreg): 4*32*64 + 8*32*136 + 8*32*72 = 61440 = 640*96.
-constexpr int REGS_CTRL = 64, REGS_EPI = 136, REGS_SPLIT = 72;
+constexpr int SPLIT_GROUPS = 1;                // groups of 4 splitter warps (group g takes K-slabs g, g+G, ...)
+constexpr int THREADS = (12 + 4 * SPLIT_GROUPS) * 32;   // 4 control + 8 epilogue + splitter warps (<= 512: 128 regs/thread)
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, SPLIT_WARP0 = 12;
 constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 4;           // 16 KB raw A slab
-constexpr int B_BYTES = BN * BK * 4;           // 16 KB per B plane
+constexpr int A_BYTES = BM * BK * 4;           // 16 KB raw A slab (this CTA's 128 rows)
+constexpr int BNH = BN / 2;                    // N-rows of the B tile held by each CTA of the pair
+constexpr int B_BYTES = BNH * BK * 4;          // 8 KB per B plane
 constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t TM_MAIN = 0, TM_CROSS = 128, TM_A = 256;   // TMEM column map; A stage s: hi at TM_A+64s, lo at +32
@@ -99,7 +87,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]   (A from tensor memory: .ts form)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
@@ -107,21 +96,25 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}" : "=r"(pred));
-  return pred != 0;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -161,12 +154,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 struct Params {
   int M, N, K, ldc;
   long long* trace;   // optional device buffer [4 roles][256 events][4]: clock64 timeline of CTA 0 (profiling aid)
-  int dbg;   // timing experiments only (results invalid): 1 = no MMAs, 2 = no splitter work, 4 = no TMA, 8 = no epilogue stores
+  int dbg;   // experiments only: 1 = no MMAs, 2 = no splitter work, 4 = no TMA, 8 = no epilogue stores (results invalid);
+             // 16 = also write the explicit B hi plane (results identical)
   float* C;
   GemmEpilogue ep;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB, Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle-128B tiles need 1024 B alignment
@@ -180,166 +174,164 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const uint32_t rank = cluster_ctarank();                     // 0 = leader (issues the MMAs for the pair)
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int nk = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(split_bar(s), SPLIT_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(split_bar(s), 8); mbar_init(empty_bar(s), 1); }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, EPI_WARPS);
-    // (split_done gets one arrival per splitter warp)
+    mbar_init(tempty_bar, 2 * EPI_WARPS);                      // split_done / tmem_empty are used on the leader only
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
   }
+  cluster_sync();                                              // both CTAs' barriers initialised before any remote arrive
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                  "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    reg_dec<REGS_CTRL>();
-  }
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    // The whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); one elected
-    // lane issues.  Single-lane loops made ptxas wrap every UTMALDG / UTCHMMA in a lane "waterfall" loop.
-    int stage = 0; uint32_t phase = 0;
-    int pslab = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
-      for (int kb = 0; kb < nk; ++kb) {
-        if (lane == 0) mbar_spin(empty_bar(stage), phase ^ 1);
-        __syncwarp();
-        MMX_TRACE(0, pslab, 0);
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        if (elect_one()) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int pslab = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int m0 = (t % tiles_m) * 2 * BM + (int)rank * BM, n0 = (t / tiles_m) * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_spin(empty_bar(stage), phase ^ 1);
+          MMX_TRACE(0, pslab, 0);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
           if (p.dbg & 4) { mbar_arrive(full_bar(stage)); }
           else {
-            mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
-            tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m0);
-            tma_load_2d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0);
+          mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
+          tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0 + (int)rank * BNH);
           }
+          MMX_TRACE(0, pslab, 1);
+          ++pslab;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        MMX_TRACE(0, pslab, 1);
-        ++pslab;
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    int stage = 0; uint32_t phase = 0;
-    int it = 0, mslab = 0;
-    const uint32_t d_main = tmem_base + TM_MAIN, d_cross = tmem_base + TM_CROSS;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      if (lane == 0) mbar_spin(tempty_bar, (uint32_t)(it & 1) ^ 1);   // epilogue drained the accumulators
-      __syncwarp();
-      tc_fence_after();
-      for (int kb = 0; kb < nk; ++kb) {
-        if (lane == 0) mbar_spin(split_bar(stage), phase);        // A hi/lo in TMEM, B lo plane written (implies the TMA landed)
-        __syncwarp();
-        MMX_TRACE(1, mslab, 0);
+    // ------------------------------------------------------------------ MMA issuer (single thread of the leader CTA)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 across the pair
+      int stage = 0; uint32_t phase = 0;
+      int it = 0, mslab = 0;
+      const uint32_t d_main = tmem_base + TM_MAIN, d_cross = tmem_base + TM_CROSS;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        mbar_spin(tempty_bar, (uint32_t)(it & 1) ^ 1);           // epilogue drained the accumulators
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        const uint64_t b_hi = make_desc(sa + A_BYTES), b_lo = make_desc(sa + A_BYTES + B_BYTES);
-        const uint32_t a_hi = tmem_base + TM_A + 64u * stage, a_lo = a_hi + 32u;
-        if (elect_one()) {
-          if (!(p.dbg & 1)) {
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_spin(split_bar(stage), phase);                   // A hi/lo in TMEM (implies the TMA landed B too)
+          MMX_TRACE(1, mslab, 0);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t b_hi = make_desc(sa + A_BYTES), b_lo = make_desc(sa + A_BYTES + B_BYTES);
+          const uint32_t a_hi = tmem_base + TM_A + 64u * stage, a_lo = a_hi + 32u;
+          if (!(p.dbg & 1))
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {                    // UMMA_K = 8 (tf32): +32 B in smem (+2 in the descriptor), +8 TMEM columns
-              const uint64_t adv = (uint64_t)(2 * k);
-              const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-              umma_tf32_ts(d_cross, a_lo + 8u * k, b_hi + adv, idesc, first);
-              umma_tf32_ts(d_cross, a_hi + 8u * k, b_lo + adv, idesc, 1u);
-              umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + adv, idesc, first);
-            }
+          for (int k = 0; k < BK / 8; ++k) {                    // UMMA_K = 8 (tf32): +32 B in smem (+2 in the descriptor), +8 TMEM columns
+            const uint64_t adv = (uint64_t)(2 * k);
+            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_tf32_ts(d_cross, a_lo + 8u * k, b_hi + adv, idesc, first);
+            umma_tf32_ts(d_cross, a_hi + 8u * k, b_lo + adv, idesc, 1u);
+            umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + adv, idesc, first);
           }
           MMX_TRACE(1, mslab, 1);
-          umma_commit(empty_bar(stage));                          // frees the stage (smem + TMEM A slab) when these MMAs retire
-          if (kb == nk - 1) umma_commit(tfull_bar);               // accumulators complete -> epilogue
+          umma_commit(empty_bar(stage));                        // frees the stage (smem + TMEM A slab) when these MMAs retire
+          if (kb == nk - 1) umma_commit(tfull_bar);             // accumulators complete -> epilogue
+          MMX_TRACE(1, mslab, 2);
+          ++mslab;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        MMX_TRACE(1, mslab, 2);
-        ++mslab;
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= SPLIT_WARP0) {
-    reg_dec<REGS_SPLIT>();
     // ------------------------------------------------------------------ splitter: A slab (smem) -> hi/lo -> TMEM
     const int q = warp & 3;                                     // TMEM lane quarter this warp may write
-    const int half = (warp - SPLIT_WARP0) >> 2;                 // which 16 of the slab's 32 K columns this warp converts
-    const int stid = threadIdx.x - SPLIT_WARP0 * 32;            // 0..255
+    const int grp = (warp - SPLIT_WARP0) >> 2;                  // splitter group: handles K-slabs grp, grp+2, grp+4, ...
+    const int gtid = threadIdx.x - (SPLIT_WARP0 + 4 * grp) * 32;  // 0..127 inside the group
     const int row = q * 32 + lane;                              // tile row handled by this thread
     const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
-    int stage = 0; uint32_t phase = 0;
-    int slab = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    long long slab = 0;                                         // global K-slab counter of this CTA
+    for (int t = pair; t < num_tiles; t += num_pairs) {
       for (int kb = 0; kb < nk; ++kb, ++slab) {
+        if ((int)(slab % SPLIT_GROUPS) != grp) continue;
+        const int stage = (int)(slab % STAGES);
+        const uint32_t phase = (uint32_t)((slab / STAGES) & 1);
         if (lane == 0) mbar_spin(full_bar(stage), phase);       // one polling lane per warp, no suspend/wake-up latency
         __syncwarp();
-        if (warp == SPLIT_WARP0 && lane == 0) MMX_TRACE(2, slab, 0);
-        if (!(p.dbg & 2)) {
-          // A slab: half of this thread's row (64 B, swizzled 16-byte chunks) -> hi/lo -> 16 + 16 TMEM columns.
-          // The tensor core reads only the top 19 bits of an fp32 operand (kind::tf32 truncates; measured: results
-          // are bit-identical with and without an explicit hi plane), so the raw values ARE the hi operand.
-          const uint8_t* a_raw = smem_gen + stage * STAGE_BYTES + row_off;
-          const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * stage + 16u * half;
+        if (warp == SPLIT_WARP0 && lane == 0) MMX_TRACE(2, (int)slab, 0);
+        if (p.dbg & 2) { __syncwarp(); if (lane == 0) mbar_arrive(split_bar(stage)); continue; }
+        // B slab: raw -> hi (in place) + lo plane; elementwise, so the swizzle does not matter
+        uint4* braw = reinterpret_cast<uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES);
+        uint4* blo = reinterpret_cast<uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES + B_BYTES);
+#pragma unroll
+        for (int i0 = 0; i0 < B_BYTES / 16; i0 += 128 * 4) {   // 512 x 16 B = this CTA's half of the B tile
+          uint4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = braw[i0 + u * 128 + gtid];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 h, l;
+            h.x = x[u].x & 0xFFFFE000u; h.y = x[u].y & 0xFFFFE000u; h.z = x[u].z & 0xFFFFE000u; h.w = x[u].w & 0xFFFFE000u;
+            l.x = __float_as_uint(__uint_as_float(x[u].x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(x[u].y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(x[u].z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(x[u].w) - __uint_as_float(h.w));
+            // The tensor core reads only the top 19 bits of an fp32 operand (kind::tf32 truncates; measured: results
+            // are bit-identical with and without writing hi back), so the raw tile already IS the hi plane.
+            if (p.dbg & 16) braw[i0 + u * 128 + gtid] = h;       // dbg 16: write the explicit hi plane anyway (A/B test)
+            blo[i0 + u * 128 + gtid] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
+        // A slab: this thread's row (128 B, swizzled chunks) -> hi/lo -> 32 + 32 TMEM columns of the stage
+        const uint8_t* a_raw = smem_gen + stage * STAGE_BYTES + row_off;
+        const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * stage;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint32_t chunk = (uint32_t)(half * 4 + c);    // 16-byte chunk = k 4*chunk .. 4*chunk+3
+            const uint32_t chunk = (uint32_t)(half * 4 + c);    // 16-byte chunk = k 4*chunk .. 4*chunk+3, swizzled by row
             const uint4 x = *reinterpret_cast<const uint4*>(a_raw + ((chunk ^ sw) << 4));
             const uint32_t xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              hi[c * 4 + e] = xv[e];
-              lo[c * 4 + e] = __float_as_uint(__uint_as_float(xv[e]) - __uint_as_float(xv[e] & 0xFFFFE000u));
+              const uint32_t h = xv[e] & 0xFFFFE000u;
+              hi[c * 4 + e] = xv[e];                              // raw fp32: the MMA truncates it to hi itself
+              lo[c * 4 + e] = __float_as_uint(__uint_as_float(xv[e]) - __uint_as_float(h));
             }
           }
-          tmem_st16(t_hi, hi);
-          tmem_st16(t_hi + 32u, lo);
-          // B slab: lo plane beside the raw tile (elementwise, so the swizzle does not matter)
-          const uint4* braw = reinterpret_cast<const uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES);
-          uint4* blo = reinterpret_cast<uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES + B_BYTES);
-          uint4 x[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) x[u] = braw[u * 256 + stid];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 l;
-            l.x = __float_as_uint(__uint_as_float(x[u].x) - __uint_as_float(x[u].x & 0xFFFFE000u));
-            l.y = __float_as_uint(__uint_as_float(x[u].y) - __uint_as_float(x[u].y & 0xFFFFE000u));
-            l.z = __float_as_uint(__uint_as_float(x[u].z) - __uint_as_float(x[u].z & 0xFFFFE000u));
-            l.w = __float_as_uint(__uint_as_float(x[u].w) - __uint_as_float(x[u].w & 0xFFFFE000u));
-            blo[u * 256 + stid] = l;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
+          tmem_st16(t_hi + 16u * half, hi);
+          tmem_st16(t_hi + 32u + 16u * half, lo);
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(split_bar(stage));
-        if (warp == SPLIT_WARP0 && lane == 0) MMX_TRACE(2, slab, 1);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive_cluster(mapa(split_bar(stage), 0));     // the leader's barrier
+        if (warp == SPLIT_WARP0 && lane == 0) MMX_TRACE(2, (int)slab, 1);
       }
     }
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
-    reg_inc<REGS_EPI>();
     // ------------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
     const int q = warp & 3;                                     // TMEM lane quarter this warp may read
     const int ch = (warp - EPI_WARP0) >> 2;                     // column half: 64 of the 128 accumulator columns
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int m0 = (t % tiles_m) * 2 * BM + (int)rank * BM, n0 = (t / tiles_m) * BN;
       if (lane == 0) mbar_spin(tfull_bar, (uint32_t)(it & 1));
       __syncwarp();
       if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 0);
@@ -357,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);                  // next tile's MMAs may start
+      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar, 0));   // next tile's MMAs may start (leader's barrier)
       if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 1);
       const int m = m0 + q * 32 + lane;
       if (m < p.M && !(p.dbg & 8)) {
@@ -398,16 +390,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
   }
   // ---------------------------------------------------------------------- teardown
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();                                              // the peer may still read this CTA's smem / TMEM until here
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static long long* g_trace = nullptr;
-static int g_avail = -1;
 
 static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -428,60 +419,38 @@ static int launch(const float* A, int lda, const float* Bt, int ldb, float* C, i
                   const GemmEpilogue& ep, cudaStream_t st) {
   CUtensorMap mapA, mapB;
   MMX_TRY(make_map(&mapA, A, M, K, lda, BM));
-  MMX_TRY(make_map(&mapB, Bt, N, K, ldb, BN));
+  MMX_TRY(make_map(&mapB, Bt, N, K, ldb, BNH));
   static bool attr_set = false;
   if (!attr_set) {
-    MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("MMX_TC_DBG"); dbg = e ? atoi(e) : 0; }
   Params p{M, N, K, ldc, g_trace, dbg, C, ep};
-  const int tiles = cdiv(M, BM) * cdiv(N, BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tf32x3_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
+  const int tiles = cdiv(M, 2 * BM) * cdiv(N, BN);
+  const int max_pairs = sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  gemm_tf32x3_2cta_kernel<<<2 * pairs, THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);   // __cluster_dims__(2,1,1)
   MMX_LAUNCH_CHECK();
   return 0;
 }
 
-}  // namespace tc
+}  // namespace tc2
 
-int gemm_tc_available() {
-  if (tc::g_avail >= 0) return tc::g_avail;
-  tc::g_avail = 0;
-  int dev = 0;
-  cudaDeviceProp prop;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
-  if (prop.major != 10) return 0;                         // tcgen05 / TMEM: sm_100 family only
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) return 0;
-  tc::g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-  tc::g_avail = 1;
-  return 1;
-}
-
-// Profiling aid: the next tensor-core GEMM launches write CTA 0's clock64 timeline into `buf`
-// ([4 roles][256 events][4] int64: producer, MMA issuer, splitter, epilogue); nullptr switches it off.
-void gemm_tc_set_trace(long long* buf) { tc::g_trace = buf; }
-
-// Which problems go to the tensor-core kernel.  Deliberately independent of M, so that a sample computed alone
-// and the same sample inside a batch take the same arithmetic path (bitwise-equal maps, sharded == single GPU).
-bool gemm_tc_shape_ok(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int N, int K,
-                      const GemmEpilogue& ep) {
-  if (!gemm_tc_available()) return false;
-  if (N < 128 || K < 64 || (K % 4) || (N % 4) || (lda % 4) || (ldb % 4) || (ldc % 4)) return false;
-  if (!aligned16(A) || !aligned16(Bt) || !aligned16(C)) return false;
-  if ((ep.bias && !aligned16(ep.bias)) || (ep.pre && (!aligned16(ep.pre) || ep.ldpre % 4)) ||
-      (ep.residual && (!aligned16(ep.residual) || ep.ldres % 4)) || (ep.C_act && !aligned16(ep.C_act)))
-    return false;
-  return true;
-}
-
-int gemm_nt_tc(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
-               const GemmEpilogue& ep, cudaStream_t st) {
+int gemm_nt_tc2(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+                const GemmEpilogue& ep, cudaStream_t st) {
   if (M == 0 || N == 0) return 0;
-  return tc::launch(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
+  if (tc2::g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+      set_error("cuTensorMapEncodeTiled not available");
+      return 1;
+    }
+    tc2::g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  return tc2::launch(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
 }
 
 }  // namespace mmx
