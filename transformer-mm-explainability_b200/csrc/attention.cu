@@ -14,33 +14,46 @@ constexpr int ATT_THREADS = 128;
 
 template <int HD>
 struct AttnSmem {
-  static constexpr int LDH = HD + 1;
+  static constexpr int LDH = HD + 4;
   static size_t bytes(int S_pad) { return sizeof(float) * ((size_t)TQ * S_pad + (size_t)TQ * LDH + (size_t)TKEY * LDH); }
 };
 
+// Shared-memory operand rows are HD + 4 floats: 16-byte aligned for 128-bit reads, and 8 consecutive rows start in 8
+// different 4-bank groups, so a quarter-warp's LDS.128 is conflict-free.
+//
 // scores[i][j] (i in tile, j in [0,S)) = sum_d X[i][d] * Y[j][d];  X rows already in sX, Y streamed through sY.
 template <int HD>
 __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy, long long ybase, int S,
                                             const float* sX, float* sY, float* sP, int S_pad, float post_scale) {
-  constexpr int LDH = HD + 1;
+  constexpr int LDH = HD + 4;
   const int tid = threadIdx.x, ri = tid >> 4, cj = tid & 15;
   for (int j0 = 0; j0 < S; j0 += TKEY) {
     __syncthreads();
-    for (int e = tid; e < TKEY * HD; e += ATT_THREADS) {
-      const int r = e / HD, d = e % HD;
-      sY[r * LDH + d] = (j0 + r < S) ? Y[ybase + (long long)(j0 + r) * ldy + d] : 0.f;
+    for (int e = tid; e < TKEY * (HD / 4); e += ATT_THREADS) {
+      const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + r < S) v = *reinterpret_cast<const float4*>(Y + ybase + (long long)(j0 + r) * ldy + d);
+      *reinterpret_cast<float4*>(sY + r * LDH + d) = v;
     }
     __syncthreads();
     float acc[4][4] = {};
-#pragma unroll 8
-    for (int d = 0; d < HD; ++d) {
-      float x[4], y[4];
+#pragma unroll 4
+    for (int d = 0; d < HD; d += 4) {
+      float4 x[4], y[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { x[u] = sX[(ri * 4 + u) * LDH + d]; y[u] = sY[(cj + 16 * u) * LDH + d]; }
+      for (int u = 0; u < 4; ++u) {
+        x[u] = *reinterpret_cast<const float4*>(sX + (ri * 4 + u) * LDH + d);
+        y[u] = *reinterpret_cast<const float4*>(sY + (cj + 16 * u) * LDH + d);
+      }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(x[a], y[c], acc[a][c]);
+        for (int c = 0; c < 4; ++c) {
+          acc[a][c] = fmaf(x[a].x, y[c].x, acc[a][c]);
+          acc[a][c] = fmaf(x[a].y, y[c].y, acc[a][c]);
+          acc[a][c] = fmaf(x[a].z, y[c].z, acc[a][c]);
+          acc[a][c] = fmaf(x[a].w, y[c].w, acc[a][c]);
+        }
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -53,34 +66,54 @@ __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy
   __syncthreads();
 }
 
-// out[i][d] = sum_j sP[i][j] * Y[j][d]
+// out[i][d] = sum_j sP[i][j] * Y[j][d];  thread (ri, cj) owns rows ri*4..+3 and the 4 contiguous columns d = 4*cj..
+// (threads with 4*cj >= HD idle for small head dims)
 template <int HD>
 __device__ __forceinline__ void tile_pv(const float* __restrict__ Y, int ldy, long long ybase, int S, const float* sP,
-                                        int S_pad, float* sY, float (&out)[4][HD / 16]) {
-  constexpr int LDH = HD + 1, NU = HD / 16;
+                                        int S_pad, float* sY, float4 (&out)[4]) {
+  constexpr int LDH = HD + 4;
   const int tid = threadIdx.x, ri = tid >> 4, cj = tid & 15;
+  const bool active = cj * 4 < HD;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int u = 0; u < NU; ++u) out[a][u] = 0.f;
+  for (int a = 0; a < 4; ++a) out[a] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int j0 = 0; j0 < S; j0 += TKEY) {
     __syncthreads();
-    for (int e = tid; e < TKEY * HD; e += ATT_THREADS) {
-      const int r = e / HD, d = e % HD;
-      sY[r * LDH + d] = (j0 + r < S) ? Y[ybase + (long long)(j0 + r) * ldy + d] : 0.f;
+    for (int e = tid; e < TKEY * (HD / 4); e += ATT_THREADS) {
+      const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + r < S) v = *reinterpret_cast<const float4*>(Y + ybase + (long long)(j0 + r) * ldy + d);
+      *reinterpret_cast<float4*>(sY + r * LDH + d) = v;
     }
     __syncthreads();
+    if (!active) continue;
     const int jn = min(TKEY, S - j0);
-    for (int j = 0; j < jn; ++j) {
-      float p[4], y[NU];
+    int j = 0;
+    for (; j + 4 <= jn; j += 4) {                       // S_pad % 4 == 0 and j0 % 4 == 0: aligned float4 reads of P
+      float4 p[4], y[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) p[a] = sP[(ri * 4 + a) * S_pad + j0 + j];
+      for (int a = 0; a < 4; ++a) p[a] = *reinterpret_cast<const float4*>(sP + (ri * 4 + a) * S_pad + j0 + j);
 #pragma unroll
-      for (int u = 0; u < NU; ++u) y[u] = sY[j * LDH + cj + 16 * u];
+      for (int u = 0; u < 4; ++u) y[u] = *reinterpret_cast<const float4*>(sY + (j + u) * LDH + cj * 4);
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 4; ++a) {
+        const float pa[4] = {p[a].x, p[a].y, p[a].z, p[a].w};
 #pragma unroll
-        for (int u = 0; u < NU; ++u) out[a][u] = fmaf(p[a], y[u], out[a][u]);
+        for (int u = 0; u < 4; ++u) {
+          out[a].x = fmaf(pa[u], y[u].x, out[a].x);
+          out[a].y = fmaf(pa[u], y[u].y, out[a].y);
+          out[a].z = fmaf(pa[u], y[u].z, out[a].z);
+          out[a].w = fmaf(pa[u], y[u].w, out[a].w);
+        }
+      }
+    }
+    for (; j < jn; ++j) {
+      const float4 y = *reinterpret_cast<const float4*>(sY + j * LDH + cj * 4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float pa = sP[(ri * 4 + a) * S_pad + j0 + j];
+        out[a].x = fmaf(pa, y.x, out[a].x); out[a].y = fmaf(pa, y.y, out[a].y);
+        out[a].z = fmaf(pa, y.z, out[a].z); out[a].w = fmaf(pa, y.w, out[a].w);
+      }
     }
   }
 }
@@ -90,7 +123,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
     const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
     const float* __restrict__ key_bias, float* __restrict__ A, int ldA, float* __restrict__ O, int ldo, int H, int T, int S,
     float scale, int flags) {
-  constexpr int LDH = HD + 1, NU = HD / 16;
+  constexpr int LDH = HD + 4;
   extern __shared__ float smem[];
   const int S_pad = ldA;  // score rows use the same padded width as the staged A rows
   float* sP = smem;
@@ -100,9 +133,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool scale_scores = flags & MMX_ATTN_SCALE_SCORES;
   const float qs = scale_scores ? 1.f : scale;
-  for (int e = tid; e < TQ * HD; e += ATT_THREADS) {
-    const int r = e / HD, d = e % HD;
-    sQ[r * LDH + d] = (i0 + r < T) ? Q[((long long)b * T + i0 + r) * ldq + h * HD + d] * qs : 0.f;
+  for (int e = tid; e < TQ * (HD / 4); e += ATT_THREADS) {
+    const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + r < T) v = *reinterpret_cast<const float4*>(Q + ((long long)b * T + i0 + r) * ldq + h * HD + d);
+    v.x *= qs; v.y *= qs; v.z *= qs; v.w *= qs;
+    *reinterpret_cast<float4*>(sQ + r * LDH + d) = v;
   }
   tile_scores<HD>(K, ldk, (long long)b * S * ldk + h * HD, S, sQ, sKV, sP, S_pad, scale_scores ? scale : 1.f);
   // softmax per row (warp w owns rows w*8 .. w*8+7), stage A
@@ -130,15 +166,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
     }
   }
   __syncthreads();
-  float out[4][NU];
+  float4 out[4];
   tile_pv<HD>(V, ldv, (long long)b * S * ldv + h * HD, S, sP, S_pad, sKV, out);
   const int ri = tid >> 4, cj = tid & 15;
+  if (cj * 4 < HD) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int i = i0 + ri * 4 + a;
-    if (i >= T) continue;
-#pragma unroll
-    for (int u = 0; u < NU; ++u) O[((long long)b * T + i) * ldo + h * HD + cj + 16 * u] = out[a][u];
+    for (int a = 0; a < 4; ++a) {
+      const int i = i0 + ri * 4 + a;
+      if (i < T) *reinterpret_cast<float4*>(O + ((long long)b * T + i) * ldo + h * HD + cj * 4) = out[a];
+    }
   }
 }
 
@@ -148,7 +184,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
     const float* __restrict__ A, float* __restrict__ dA, int ldA, float* __restrict__ delta, float* __restrict__ dQ,
     int lddq, int H, int T, int S, float scale) {
-  constexpr int LDH = HD + 1, NU = HD / 16;
+  constexpr int LDH = HD + 4;
   extern __shared__ float smem[];
   const int S_pad = ldA;
   float* sP = smem;
@@ -156,9 +192,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
   float* sKV = sX + TQ * LDH;
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TQ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int e = tid; e < TQ * HD; e += ATT_THREADS) {
-    const int r = e / HD, d = e % HD;
-    sX[r * LDH + d] = (i0 + r < T) ? dO[((long long)b * T + i0 + r) * lddo + h * HD + d] : 0.f;
+  for (int e = tid; e < TQ * (HD / 4); e += ATT_THREADS) {
+    const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + r < T) v = *reinterpret_cast<const float4*>(dO + ((long long)b * T + i0 + r) * lddo + h * HD + d);
+    *reinterpret_cast<float4*>(sX + r * LDH + d) = v;
   }
   tile_scores<HD>(V, ldv, (long long)b * S * ldv + h * HD, S, sX, sKV, sP, S_pad, 1.f);
   for (int rr = 0; rr < TQ / 4; ++rr) {
@@ -180,15 +218,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
   }
   if (dQ == nullptr) return;
   __syncthreads();
-  float out[4][NU];
+  float4 out[4];
   tile_pv<HD>(K, ldk, (long long)b * S * ldk + h * HD, S, sP, S_pad, sKV, out);
   const int ri = tid >> 4, cj = tid & 15;
+  if (cj * 4 < HD) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int i = i0 + ri * 4 + a;
-    if (i >= T) continue;
-#pragma unroll
-    for (int u = 0; u < NU; ++u) dQ[((long long)b * T + i) * lddq + h * HD + cj + 16 * u] = out[a][u] * scale;
+    for (int a = 0; a < 4; ++a) {
+      const int i = i0 + ri * 4 + a;
+      if (i < T) {
+        const float4 v = make_float4(out[a].x * scale, out[a].y * scale, out[a].z * scale, out[a].w * scale);
+        *reinterpret_cast<float4*>(dQ + ((long long)b * T + i) * lddq + h * HD + cj * 4) = v;
+      }
+    }
   }
 }
 
@@ -200,15 +241,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ Q, int ldq, const float* __restrict__ A,
     const float* __restrict__ dA, int ldA, const float* __restrict__ delta, float* __restrict__ dK, int lddk,
     float* __restrict__ dV, int lddv, int H, int T, int S, float scale) {
-  constexpr int LDH = HD + 1, NU = HD / 16;
+  constexpr int LDH = HD + 4, LDK = KV_KEYS + 4;
   extern __shared__ float smem[];
   float* sdO = smem;
   float* sQ = sdO + KV_ROWS * LDH;
-  float (*sA)[KV_KEYS + 1] = reinterpret_cast<float (*)[KV_KEYS + 1]>(sQ + KV_ROWS * LDH);
-  float (*sS)[KV_KEYS + 1] = sA + KV_ROWS;
+  float* sA = sQ + KV_ROWS * LDH;          // [KV_ROWS][LDK]  A[i][j]
+  float* sS = sA + KV_ROWS * LDK;          // [KV_ROWS][LDK]  dS[i][j]
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * KV_KEYS;
   const int tid = threadIdx.x, rj = tid >> 4, cj = tid & 15;
-  float accV[4][NU] = {}, accK[4][NU] = {};
+  const bool active = cj * 4 < HD;
+  float4 accV[4], accK[4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) accV[x] = accK[x] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long plane = ((long long)b * H + h) * T;
   for (int i0 = 0; i0 < T; i0 += KV_ROWS) {
     __syncthreads();
@@ -220,41 +264,45 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
         a = A[off];
         ds = a * (dA[off] - delta[plane + i0 + r]);
       }
-      sA[r][c] = a;
-      sS[r][c] = ds;
+      sA[r * LDK + c] = a;
+      sS[r * LDK + c] = ds;
     }
-    for (int e = tid; e < KV_ROWS * HD; e += ATT_THREADS) {
-      const int r = e / HD, d = e % HD;
-      const bool ok = i0 + r < T;
-      sdO[r * LDH + d] = ok ? dO[((long long)b * T + i0 + r) * lddo + h * HD + d] : 0.f;
-      sQ[r * LDH + d] = ok ? Q[((long long)b * T + i0 + r) * ldq + h * HD + d] : 0.f;
+    for (int e = tid; e < KV_ROWS * (HD / 4); e += ATT_THREADS) {
+      const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
+      float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), vq = vo;
+      if (i0 + r < T) {
+        vo = *reinterpret_cast<const float4*>(dO + ((long long)b * T + i0 + r) * lddo + h * HD + d);
+        vq = *reinterpret_cast<const float4*>(Q + ((long long)b * T + i0 + r) * ldq + h * HD + d);
+      }
+      *reinterpret_cast<float4*>(sdO + r * LDH + d) = vo;
+      *reinterpret_cast<float4*>(sQ + r * LDH + d) = vq;
     }
     __syncthreads();
+    if (!active) continue;
     const int in = min(KV_ROWS, T - i0);
     for (int i = 0; i < in; ++i) {
-      float a[4], s[4], o[NU], q[NU];
+      const float4 a = *reinterpret_cast<const float4*>(sA + i * LDK + rj * 4);
+      const float4 sv = *reinterpret_cast<const float4*>(sS + i * LDK + rj * 4);
+      const float4 o = *reinterpret_cast<const float4*>(sdO + i * LDH + cj * 4);
+      const float4 q = *reinterpret_cast<const float4*>(sQ + i * LDH + cj * 4);
+      const float av[4] = {a.x, a.y, a.z, a.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u] = sA[i][rj * 4 + u]; s[u] = sS[i][rj * 4 + u]; }
-#pragma unroll
-      for (int u = 0; u < NU; ++u) { o[u] = sdO[i * LDH + cj + 16 * u]; q[u] = sQ[i * LDH + cj + 16 * u]; }
-#pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-          accV[x][u] = fmaf(a[x], o[u], accV[x][u]);
-          accK[x][u] = fmaf(s[x], q[u], accK[x][u]);
-        }
+      for (int x = 0; x < 4; ++x) {
+        accV[x].x = fmaf(av[x], o.x, accV[x].x); accV[x].y = fmaf(av[x], o.y, accV[x].y);
+        accV[x].z = fmaf(av[x], o.z, accV[x].z); accV[x].w = fmaf(av[x], o.w, accV[x].w);
+        accK[x].x = fmaf(ss[x], q.x, accK[x].x); accK[x].y = fmaf(ss[x], q.y, accK[x].y);
+        accK[x].z = fmaf(ss[x], q.z, accK[x].z); accK[x].w = fmaf(ss[x], q.w, accK[x].w);
+      }
     }
   }
+  if (!active) return;
 #pragma unroll
   for (int x = 0; x < 4; ++x) {
     const int j = j0 + rj * 4 + x;
     if (j >= S) continue;
-#pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      dV[((long long)b * S + j) * lddv + h * HD + cj + 16 * u] = accV[x][u];
-      dK[((long long)b * S + j) * lddk + h * HD + cj + 16 * u] = accK[x][u] * scale;
-    }
+    *reinterpret_cast<float4*>(dV + ((long long)b * S + j) * lddv + h * HD + cj * 4) = accV[x];
+    const float4 kk = make_float4(accK[x].x * scale, accK[x].y * scale, accK[x].z * scale, accK[x].w * scale);
+    *reinterpret_cast<float4*>(dK + ((long long)b * S + j) * lddk + h * HD + cj * 4) = kk;
   }
 }
 
@@ -284,7 +332,7 @@ static int launch_bwd(const float* dO, int lddo, const float* Q, int ldq, const 
                                                               scale);
   MMX_LAUNCH_CHECK();
   if (dQ == nullptr) return 0;
-  const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 1) + 2 * KV_ROWS * (KV_KEYS + 1));
+  const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 4) + 2 * KV_ROWS * (KV_KEYS + 4));
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   dim3 grid2(cdiv(S, KV_KEYS), H, B);
   attention_bwd_kv_kernel<HD><<<grid2, ATT_THREADS, smem2, st>>>(dO, lddo, Q, ldq, A, dA, ldA, delta, dK, lddk, dV, lddv, H,
@@ -295,7 +343,9 @@ static int launch_bwd(const float* dO, int lddo, const float* Q, int ldq, const 
 
 int attention_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const float* key_bias, float* A,
                   int ldA, float* O, int ldo, int B, int H, int T, int S, int hd, float scale, int flags, cudaStream_t st) {
-  MMX_REQUIRE(ldA >= S, "ldA < S");
+  MMX_REQUIRE(ldA >= S && ldA % 4 == 0, "ldA must be >= S and a multiple of 4");
+  MMX_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && aligned16(Q) && aligned16(K) && aligned16(V) &&
+                  aligned16(O) && aligned16(A), "attention operands must be 16-byte aligned with leading dims % 4 == 0");
   if (B == 0 || T == 0) return 0;
   switch (hd) {
     case 16: return launch_fwd<16>(Q, ldq, K, ldk, V, ldv, key_bias, A, ldA, O, ldo, B, H, T, S, scale, flags, st);
@@ -309,7 +359,11 @@ int attention_fwd(const float* Q, int ldq, const float* K, int ldk, const float*
 int attention_bwd(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                   const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, float* dK, int lddk, float* dV,
                   int lddv, int B, int H, int T, int S, int hd, float scale, int flags, cudaStream_t st) {
-  MMX_REQUIRE(ldA >= S, "ldA < S");
+  MMX_REQUIRE(ldA >= S && ldA % 4 == 0, "ldA must be >= S and a multiple of 4");
+  MMX_REQUIRE(lddo % 4 == 0 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && aligned16(dO) && aligned16(Q) && aligned16(K) &&
+                  aligned16(V) && aligned16(A) && aligned16(dA) && (dQ == nullptr || (lddq % 4 == 0 && lddk % 4 == 0 &&
+                  lddv % 4 == 0 && aligned16(dQ) && aligned16(dK) && aligned16(dV))),
+              "attention operands must be 16-byte aligned with leading dims % 4 == 0");
   MMX_REQUIRE((dQ == nullptr) == (dK == nullptr) && (dQ == nullptr) == (dV == nullptr), "dQ/dK/dV: all or none");
   MMX_REQUIRE(dQ == nullptr || delta != nullptr, "delta scratch required");
   (void)flags;  // the mask is already folded into A (masked entries are exactly 0, so dS vanishes there)
