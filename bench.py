@@ -258,7 +258,10 @@ def main():
     gemm_tflops = tfl.value / (tms.value * 1e-3) / 1e12 if tms.value > 0 else 0.0
     roofline = {"kernel": "transformer GEMMs (" + {0: "fp32 FFMA", 1: "tcgen05 3xTF32, 1 CTA/tile", 2: "tcgen05 3xTF32, cta_group::2"}[gemm_backend] + ")",
                 "bound": "tensor", "achieved": gemm_tflops, "peak": tf_sust, "unit": "TFLOP/s",
-                "frac": gemm_tflops / tf_sust, "traffic": None, "peak_source": peak_src + " bf16 dense, sustained",
+                "frac": gemm_tflops / tf_sust, "traffic": None,
+                "traffic_captured": {"launch": "M=3200 N=2304 K=768 (vision QKV)", "dram_bytes": 17334016,
+                                     "algorithmic_bytes": 16908288, "source": "profiles/gemm_tc_r1_v6_ncu.txt"},
+                "peak_source": peak_src + " bf16 dense, sustained",
                 "launches_per_step": nl.value // prof_steps, "gemm_ms_per_step": tms.value / prof_steps,
                 "flops_per_step": tfl.value / prof_steps,
                 "note": "algorithmic 2MNK per launch / CUDA-event launch time, summed over both towers' streams; "
@@ -287,7 +290,11 @@ def main():
     r5_bytes = (2 * A.numel() + Ab.numel()) * 4
     r5_gbs = r5_bytes / (ts[len(ts) // 2] * 1e-3) / 1e9
     roofline_rule5 = {"kernel": "avg_heads (rule 5)", "bound": "hbm", "achieved": r5_gbs, "peak": hbm_peak, "unit": "GB/s",
-                      "frac": r5_gbs / hbm_peak, "traffic": None, "bytes_per_launch": r5_bytes,
+                      "frac": r5_gbs / hbm_peak, "traffic": None,
+                      "traffic_captured": {"launch": "in-pipeline vision tower (12 layers x 64 x 12 heads, S=50)",
+                                           "dram_bytes": 196507904, "algorithmic_bytes": 199703040,
+                                           "source": "profiles/avg_heads_r1_ncu.txt"},
+                      "bytes_per_launch": r5_bytes,
                       "us_per_launch": ts[len(ts) // 2] * 1e3, "peak_source": peak_src}
     del A, G, Ab, flush
 
