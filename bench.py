@@ -315,7 +315,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": n_total, "start_layer": START_LAYER,
                        "start_layer_text": START_LAYER, "image": cfg.image_resolution, "context": cfg.context_length,
-                       "weights": "random-init (seed 0)", "parallelism": f"sample-sharded x{world}, 1 all-gather of maps",
+                       "weights": "random-init (seed 0)", "prompt_lengths": "U{1..75} tokens + SOT/EOT (dead rows after the EOT are skipped, results identical)", "parallelism": f"sample-sharded x{world}, 1 all-gather of maps",
                        "l2": "no flush: per-step working set (1.2 GB weights + >2 GB staged activations) >> 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -8,17 +8,21 @@
 #include <vector>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace mmx {
 
 // kernels from the other translation units
-int layernorm_fwd(const float*, int, const int*, const float*, const float*, float*, int, float*, float*, int, int, float, cudaStream_t);
+int layernorm_fwd(const float*, int, const int*, const float*, const float*, float*, int, float*, float*, int, int, float, cudaStream_t,
+                  const int* rows_dev);
 int layernorm_bwd(const float*, int, const float*, int, const int*, const float*, const float*, const float*, const float*, int,
-                  float*, int, int, int, cudaStream_t);
+                  float*, int, int, int, cudaStream_t, const int* rows_dev);
 int attention_fwd(const float*, int, const float*, int, const float*, int, const float*, float*, int, float*, int, int, int, int,
-                  int, int, float, int, cudaStream_t);
+                  int, int, float, int, cudaStream_t, const int* offs, const int* lens);
 int attention_bwd(const float*, int, const float*, int, const float*, int, const float*, int, const float*, float*, int, float*,
-                  float*, int, float*, int, float*, int, int, int, int, int, int, float, int, cudaStream_t);
+                  float*, int, float*, int, float*, int, int, int, int, int, int, float, int, cudaStream_t, const int* offs,
+                  const int* lens);
+int text_embed_packed(const int*, const float*, const float*, float*, int*, int*, int*, int*, int, int, int, int, cudaStream_t);
 int avg_heads(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int bmm_add(const float*, int, long long, int, const float*, int, long long, const float*, int, long long, float*, int, long long,
             int, int, int, int, int, cudaStream_t);
@@ -84,6 +88,9 @@ struct Tower {
   float* R[2] = {nullptr, nullptr};  // [B,S,ld] ping-pong
   float *h = nullptr, *o = nullptr, *g = nullptr, *dx0 = nullptr, *dx1 = nullptr, *dqkv = nullptr, *delta = nullptr;
   int* rows = nullptr;      // [Bm] pooled row per sample (cls / eot)
+  // ragged text batches: packed rows, sample b owns rows offs[b] .. offs[b] + lens[b] - 1; *total = sum(lens)
+  bool ragged = false;
+  int *offs = nullptr, *lens = nullptr, *total = nullptr;
   float *pool_ln = nullptr, *pool_mean = nullptr, *pool_rstd = nullptr, *dpool = nullptr;  // [Bm,D], [Bm]
   float *lnf_g = nullptr, *lnf_b = nullptr;  // ln_post / ln_final
   Mat proj, projT;                           // [D,E] (as stored: the dgrad operand), [E,D] (forward operand)
@@ -188,6 +195,9 @@ int alloc_tower(mmx_clip* h, Tower& T, const std::string& prefix, int Bm, int E)
   MMX_TRY(dallocT(h, &T.dqkv, M * 3 * D));
   MMX_TRY(dallocT(h, &T.delta, (size_t)Bm * T.H * T.S));
   MMX_TRY(dallocT(h, &T.rows, (size_t)Bm));
+  MMX_TRY(dallocT(h, &T.offs, (size_t)Bm));
+  MMX_TRY(dallocT(h, &T.lens, (size_t)Bm));
+  MMX_TRY(dallocT(h, &T.total, (size_t)1));
   MMX_TRY(dallocT(h, &T.pool_ln, (size_t)Bm * D));
   MMX_TRY(dallocT(h, &T.pool_mean, (size_t)Bm));
   MMX_TRY(dallocT(h, &T.pool_rstd, (size_t)Bm));
@@ -208,6 +218,9 @@ int tower_forward(Tower& T, int B) {
   const size_t MD = (size_t)M * D;
   const size_t plane = (size_t)B * T.H * T.S * T.ld;
   const float scale = 1.f / sqrtf((float)T.hd);     // CLIP/clip/auxilary.py:72
+  const int* md = T.ragged ? T.total : nullptr;      // device row count; M = B*S is then only the upper bound
+  const int* offs = T.ragged ? T.offs : nullptr;
+  const int* lens = T.ragged ? T.lens : nullptr;
   for (int l = 0; l < T.L; ++l) {
     const LayerW& w = T.w[l];
     float* x_in = T.x + l * MD;
@@ -216,17 +229,17 @@ int tower_forward(Tower& T, int B) {
     float* qkv = T.qkv + l * MD * 3;
     float* f = T.f + l * MD * 4;
     float* stt = T.stats + (size_t)l * 4 * M;
-    MMX_TRY(layernorm_fwd(x_in, D, nullptr, w.ln1_g, w.ln1_b, T.h, D, stt, stt + M, M, D, 1e-5f, st));
-    GemmEpilogue e1; e1.bias = w.bqkv;
+    MMX_TRY(layernorm_fwd(x_in, D, nullptr, w.ln1_g, w.ln1_b, T.h, D, stt, stt + M, M, D, 1e-5f, st, md));
+    GemmEpilogue e1; e1.bias = w.bqkv; e1.m_dev = md;
     MMX_TRY(mm(T.h, D, w.Wqkv, qkv, 3 * D, M, e1, st));
     MMX_TRY(attention_fwd(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, nullptr, T.A + l * plane, T.ld, T.o, D, B, T.H, T.S,
-                          T.S, T.hd, scale, T.causal ? MMX_ATTN_CAUSAL : 0, st));
-    GemmEpilogue e2; e2.bias = w.bo; e2.residual = x_in; e2.ldres = D;
+                          T.S, T.hd, scale, T.causal ? MMX_ATTN_CAUSAL : 0, st, offs, lens));
+    GemmEpilogue e2; e2.bias = w.bo; e2.residual = x_in; e2.ldres = D; e2.m_dev = md;
     MMX_TRY(mm(T.o, D, w.Wo, x_mid, D, M, e2, st));
-    MMX_TRY(layernorm_fwd(x_mid, D, nullptr, w.ln2_g, w.ln2_b, T.h, D, stt + 2 * M, stt + 3 * M, M, D, 1e-5f, st));
-    GemmEpilogue e3; e3.bias = w.bfc; e3.C_act = T.g; e3.act = T.act;
+    MMX_TRY(layernorm_fwd(x_mid, D, nullptr, w.ln2_g, w.ln2_b, T.h, D, stt + 2 * M, stt + 3 * M, M, D, 1e-5f, st, md));
+    GemmEpilogue e3; e3.bias = w.bfc; e3.C_act = T.g; e3.act = T.act; e3.m_dev = md;
     MMX_TRY(mm(T.h, D, w.Wfc, f, 4 * D, M, e3, st));
-    GemmEpilogue e4; e4.bias = w.bproj; e4.residual = x_mid; e4.ldres = D;
+    GemmEpilogue e4; e4.bias = w.bproj; e4.residual = x_mid; e4.ldres = D; e4.m_dev = md;
     MMX_TRY(mm(T.g, 4 * D, w.Wproj, x_out, D, M, e4, st));
   }
   return 0;
@@ -236,7 +249,7 @@ int tower_forward(Tower& T, int B) {
 int tower_pool(Tower& T, int B, int E) {
   const size_t MD = (size_t)T.M(B) * T.D;
   const float* xL = T.x + (size_t)T.L * MD;
-  MMX_TRY(layernorm_fwd(xL, T.D, T.rows, T.lnf_g, T.lnf_b, T.pool_ln, T.D, T.pool_mean, T.pool_rstd, B, T.D, 1e-5f, T.st));
+  MMX_TRY(layernorm_fwd(xL, T.D, T.rows, T.lnf_g, T.lnf_b, T.pool_ln, T.D, T.pool_mean, T.pool_rstd, B, T.D, 1e-5f, T.st, nullptr));
   GemmEpilogue e;
   MMX_TRY(mm(T.pool_ln, T.D, T.projT, T.feat, E, B, e, T.st));
   return 0;
@@ -255,7 +268,10 @@ int tower_backward(Tower& T, int B, int E, int stop) {
   float* dx_mid = T.dx1;
   MMX_CHECK_CUDA(cudaMemsetAsync(dx_out, 0, MD * sizeof(float), st));
   MMX_TRY(layernorm_bwd(T.dpool, D, T.x + (size_t)T.L * MD, D, T.rows, T.lnf_g, T.pool_mean, T.pool_rstd, nullptr, 0, dx_out, D,
-                        B, D, st));
+                        B, D, st, nullptr));
+  const int* md = T.ragged ? T.total : nullptr;
+  const int* offs = T.ragged ? T.offs : nullptr;
+  const int* lens = T.ragged ? T.lens : nullptr;
   for (int l = T.L - 1; l >= stop; --l) {
     const LayerW& w = T.w[l];
     const float* x_in = T.x + l * MD;
@@ -263,19 +279,19 @@ int tower_backward(Tower& T, int B, int E, int stop) {
     const float* qkv = T.qkv + l * MD * 3;
     const float* f = T.f + l * MD * 4;
     const float* stt = T.stats + (size_t)l * 4 * M;
-    GemmEpilogue e1; e1.pre = f; e1.ldpre = 4 * D; e1.act = T.act;
+    GemmEpilogue e1; e1.pre = f; e1.ldpre = 4 * D; e1.act = T.act; e1.m_dev = md;
     MMX_TRY(mm(dx_out, D, w.WprojT, T.g, 4 * D, M, e1, st));                        // df = (dx W_proj) . act'(f)
-    GemmEpilogue e2;
+    GemmEpilogue e2; e2.m_dev = md;
     MMX_TRY(mm(T.g, 4 * D, w.WfcT, T.h, D, M, e2, st));                             // dh2 = df W_fc
-    MMX_TRY(layernorm_bwd(T.h, D, x_mid, D, nullptr, w.ln2_g, stt + 2 * M, stt + 3 * M, dx_out, D, dx_mid, D, M, D, st));
+    MMX_TRY(layernorm_bwd(T.h, D, x_mid, D, nullptr, w.ln2_g, stt + 2 * M, stt + 3 * M, dx_out, D, dx_mid, D, M, D, st, md));
     MMX_TRY(mm(dx_mid, D, w.WoT, T.o, D, M, e2, st));                               // d(attn out) = dx_mid W_o
     const bool last = (l == stop);
     MMX_TRY(attention_bwd(T.o, D, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, T.A + l * plane, T.dA + l * plane, T.ld,
                           T.delta, last ? nullptr : T.dqkv, 3 * D, last ? nullptr : T.dqkv + D, 3 * D,
-                          last ? nullptr : T.dqkv + 2 * D, 3 * D, B, T.H, T.S, T.S, T.hd, scale, 0, st));
+                          last ? nullptr : T.dqkv + 2 * D, 3 * D, B, T.H, T.S, T.S, T.hd, scale, 0, st, offs, lens));
     if (last) break;
     MMX_TRY(mm(T.dqkv, 3 * D, w.WqkvT, T.h, D, M, e2, st));                          // dh1 = dqkv W_qkv
-    MMX_TRY(layernorm_bwd(T.h, D, x_in, D, nullptr, w.ln1_g, stt, stt + M, dx_mid, D, dx_out, D, M, D, st));
+    MMX_TRY(layernorm_bwd(T.h, D, x_in, D, nullptr, w.ln1_g, stt, stt + M, dx_mid, D, dx_out, D, M, D, st, md));
   }
   return 0;
 }
@@ -321,7 +337,11 @@ int run_chunk(mmx_clip* h, const float* images, int n_images, const int32_t* tok
   }
   // ---- text tower
   {
-    MMX_TRY(text_embed(tokens, h->tok_emb, h->pos_t, Tx.x, Tx.rows, B, Tx.S, Tx.D, c.vocab_size, Tx.st));
+    if (Tx.ragged)
+      MMX_TRY(text_embed_packed(tokens, h->tok_emb, h->pos_t, Tx.x, Tx.offs, Tx.lens, Tx.rows, Tx.total, B, Tx.S, Tx.D,
+                                c.vocab_size, Tx.st));
+    else
+      MMX_TRY(text_embed(tokens, h->tok_emb, h->pos_t, Tx.x, Tx.rows, B, Tx.S, Tx.D, c.vocab_size, Tx.st));
     MMX_TRY(tower_forward(Tx, B));
     MMX_TRY(tower_pool(Tx, B, E));
   }
@@ -380,6 +400,12 @@ int mmx_clip_create(const mmx_clip_config* cfg, int max_batch, mmx_clip** out) {
   V.L = cfg->vision_layers; V.D = cfg->vision_width; V.H = cfg->vision_width / 64; V.S = h->G * h->G + 1; V.causal = 0;
   T.L = cfg->transformer_layers; T.D = cfg->transformer_width; T.H = cfg->transformer_heads; T.S = cfg->context_length;
   T.causal = 1;
+  {
+    // tokens after the EOT are dead under the causal mask (see norm_embed.cu: text_lens_kernel); MMX_RAGGED_TEXT=0
+    // restores the reference's dense [B,77] computation (same results)
+    const char* e = getenv("MMX_RAGGED_TEXT");
+    T.ragged = !(e && atoi(e) == 0);
+  }
   const int hdv = V.D / V.H, hdt = T.D / T.H;
   int rc = 0;
   auto fail = [&](int r) { mmx_clip_destroy(h); return r; };

@@ -12,6 +12,7 @@ struct GemmEpilogue {
   int ldres = 0;
   float* C_act = nullptr;           // [M,N] (row stride ldc): also store act(C)
   int act = MMX_ACT_NONE;
+  const int* m_dev = nullptr;       // optional device-resident row count (<= M): M becomes an upper bound (ragged batches)
 };
 
 // C[M,N] = A[M,K] * Bt[N,K]^T, both operands K-major.

@@ -56,7 +56,7 @@ static int gemm_nt_impl(const float* A, int lda, const float* Bt, int ldb, float
 }
 
 // Optional per-launch CUDA-event timing of the GEMMs (the dominant kernel) for bench.py's roofline line.
-struct ProfRec { cudaEvent_t s, e; double flops; };
+struct ProfRec { cudaEvent_t s, e; double flops; const int* m_dev; int M; };
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;       // records of the current profiling window
 static std::vector<cudaEvent_t> g_pool;   // reusable events
@@ -75,6 +75,8 @@ int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc
     }
   }
   r.flops = 2.0 * (double)M * (double)N * (double)K;
+  r.m_dev = ep.m_dev;
+  r.M = M;
   MMX_CHECK_CUDA(cudaEventRecord(r.s, st));
   MMX_TRY(gemm_nt_impl(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st));
   MMX_CHECK_CUDA(cudaEventRecord(r.e, st));
@@ -114,7 +116,13 @@ int mmx_profile_gemm_report(double* total_ms, double* total_flops, int* launches
   for (ProfRec& r : g_prof) {
     float t = 0.f;
     MMX_CHECK_CUDA(cudaEventElapsedTime(&t, r.s, r.e));
-    ms += t; fl += r.flops;
+    double f = r.flops;
+    if (r.m_dev && r.M > 0) {           // ragged batch: count the rows actually processed, not the upper bound
+      int m = r.M;
+      MMX_CHECK_CUDA(cudaMemcpy(&m, r.m_dev, sizeof(int), cudaMemcpyDeviceToHost));
+      f *= (double)(m < r.M ? m : r.M) / (double)r.M;
+    }
+    ms += t; fl += f;
   }
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;

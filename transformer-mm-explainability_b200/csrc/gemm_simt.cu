@@ -15,7 +15,9 @@ __global__ void __launch_bounds__(256) gemm_nt_simt_kernel(const float* __restri
   __shared__ __align__(16) float As[2][TK][TM + 4];
   __shared__ __align__(16) float Bs[2][TK][TN + 4];
   const int tid = threadIdx.x;
+  if (ep.m_dev) M = min(M, __ldg(ep.m_dev));
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  if (m0 >= M) return;
   const int tx = tid & 15, ty = tid >> 4;
   // loader mapping: each thread moves two float4 of A and two of Bt per k-tile
   const int lrow = tid >> 2, lk = (tid & 3) * 4;

@@ -174,6 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_tf3
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
   const uint32_t rank = cluster_ctarank();                     // 0 = leader (issues the MMAs for the pair)
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = (p.N + BN - 1) / BN;

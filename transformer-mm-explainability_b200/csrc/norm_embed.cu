@@ -9,8 +9,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const int* __restrict__ row_map,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ y, int ldy, float* __restrict__ mean,
-                                                            float* __restrict__ rstd, int rows, int D, float eps) {
+                                                            float* __restrict__ rstd, int rows, int D, float eps,
+                                                            const int* __restrict__ rows_dev) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (rows_dev) rows = min(rows, __ldg(rows_dev));
   if (r >= rows) return;
   const float* xr = x + (long long)(row_map ? row_map[r] : r) * ldx;
   float s = 0.f;
@@ -34,8 +36,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd,
                                                             const float* __restrict__ resid, int ldres,
-                                                            float* __restrict__ dx, int lddx, int rows, int D) {
+                                                            float* __restrict__ dx, int lddx, int rows, int D,
+                                                            const int* __restrict__ rows_dev) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (rows_dev) rows = min(rows, __ldg(rows_dev));
   if (r >= rows) return;
   const long long xrow = row_map ? row_map[r] : r;
   const float* xr = x + xrow * ldx;
@@ -60,18 +64,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 }
 
 int layernorm_fwd(const float* x, int ldx, const int* row_map, const float* gamma, const float* beta, float* y, int ldy,
-                  float* mean, float* rstd, int rows, int D, float eps, cudaStream_t st) {
+                  float* mean, float* rstd, int rows, int D, float eps, cudaStream_t st, const int* rows_dev) {
   if (rows == 0) return 0;
-  layernorm_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, D, eps);
+  layernorm_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, D, eps, rows_dev);
   MMX_LAUNCH_CHECK();
   return 0;
 }
 int layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const int* row_map, const float* gamma,
                   const float* mean, const float* rstd, const float* resid, int ldres, float* dx, int lddx, int rows, int D,
-                  cudaStream_t st) {
+                  cudaStream_t st, const int* rows_dev) {
   if (rows == 0) return 0;
   layernorm_bwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(dy, lddy, x, ldx, row_map, gamma, mean, rstd, resid, ldres, dx, lddx,
-                                                      rows, D);
+                                                      rows, D, rows_dev);
   MMX_LAUNCH_CHECK();
   return 0;
 }
@@ -153,6 +157,51 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const int* __restrict__
     }
     if (lane == 0) eot_row[b] = b * S + bi;
   }
+}
+
+// Ragged text batches.  Under the causal mask a token never sees later tokens and only the EOT feature is pooled
+// (CLIP/clip/model.py:334-340,360), so rows after the EOT cannot influence the logits; the reference still computes
+// them (their A rows get zero gradient, their R rows stay identity).  lens[b] = eot_b + 1 rows per sample are kept,
+// packed back to back: offs = exclusive scan, total = sum, eot_row[b] = offs[b] + lens[b] - 1.
+__global__ void __launch_bounds__(256) text_lens_kernel(const int* __restrict__ tokens, int* __restrict__ lens, int B, int S) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  int best = -2147483647 - 1, bi = 0;
+  for (int j = lane; j < S; j += 32) {
+    const int t = tokens[b * S + j];
+    if (t > best) { best = t; bi = j; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) lens[b] = bi + 1;
+}
+__global__ void text_scan_kernel(const int* __restrict__ lens, int* __restrict__ offs, int* __restrict__ eot_row,
+                                 int* __restrict__ total, int B) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;     // B is a batch size (<= a few thousand): a serial scan is free
+  int acc = 0;
+  for (int b = 0; b < B; ++b) {
+    offs[b] = acc;
+    acc += lens[b];
+    eot_row[b] = acc - 1;
+  }
+  *total = acc;
+}
+__global__ void __launch_bounds__(256) text_embed_packed_kernel(const int* __restrict__ tokens, const float* __restrict__ emb,
+                                                                const float* __restrict__ pos, float* __restrict__ x,
+                                                                const int* __restrict__ offs, const int* __restrict__ lens,
+                                                                int B, int S, int D, int vocab) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= B * S) return;
+  const int b = r / S, sidx = r % S;
+  if (sidx >= lens[b]) return;
+  int tok = tokens[r];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+  const float* er = emb + (long long)tok * D;
+  const float* pr = pos + (long long)sidx * D;
+  float* xr = x + (long long)(offs[b] + sidx) * D;
+  for (int i = lane; i < D; i += 32) xr[i] = er[i] + pr[i];
 }
 
 __global__ void cls_rows_kernel(int* __restrict__ rows, int B, int S) {
@@ -271,6 +320,16 @@ int text_embed(const int* tokens, const float* emb, const float* pos, float* x, 
   MMX_LAUNCH_CHECK();
   return 0;
 }
+int text_embed_packed(const int* tokens, const float* emb, const float* pos, float* x, int* offs, int* lens, int* eot_row,
+                      int* total, int B, int S, int D, int vocab, cudaStream_t st) {
+  text_lens_kernel<<<cdiv(B, 8), 256, 0, st>>>(tokens, lens, B, S);
+  MMX_LAUNCH_CHECK();
+  text_scan_kernel<<<1, 32, 0, st>>>(lens, offs, eot_row, total, B);
+  MMX_LAUNCH_CHECK();
+  text_embed_packed_kernel<<<cdiv(B * S, 8), 256, 0, st>>>(tokens, emb, pos, x, offs, lens, B, S, D, vocab);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
 int cls_rows(int* rows, int B, int S, cudaStream_t st) {
   cls_rows_kernel<<<cdiv(B, 128), 128, 0, st>>>(rows, B, S);
   MMX_LAUNCH_CHECK();
@@ -342,12 +401,12 @@ int mmx_im2col_patches(const float* images, float* patches, int n_images, int re
 }
 int mmx_layernorm_fwd(const float* x, int ldx, const int* row_map, const float* gamma, const float* beta, float* y, int ldy,
                       float* mean, float* rstd, int rows, int D, float eps, void* stream) {
-  return layernorm_fwd(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, D, eps, (cudaStream_t)stream);
+  return layernorm_fwd(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, D, eps, (cudaStream_t)stream, nullptr);
 }
 int mmx_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const int* row_map, const float* gamma,
                       const float* mean, const float* rstd, const float* residual_grad, int ldres, float* dx, int lddx,
                       int rows, int D, void* stream) {
   return layernorm_bwd(dy, lddy, x, ldx, row_map, gamma, mean, rstd, residual_grad, ldres, dx, lddx, rows, D,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, nullptr);
 }
 }
