@@ -1,6 +1,7 @@
 // Row-wise kernels around the GEMMs: LayerNorm forward/backward (one warp per row), CLIP token assembly
 // (patch im2col, class/positional embedding, token embedding) and the logit head with its analytic backward.
 #include "mmx_common.cuh"
+#include <initializer_list>
 
 namespace mmx {
 
@@ -63,9 +64,113 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
+// Register-cached variants: one warp per row, the row (D <= 1024, D % 128 == 0) is read ONCE as 128-bit loads and kept
+// in registers across the mean / variance / output passes (2 reads + 1 write of HBM traffic total per LN forward).
+template <int NV>   // NV = D / 128 float4 per lane
+__global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const float* __restrict__ x, int ldx,
+                                                                const int* __restrict__ row_map,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ y, int ldy, float* __restrict__ mean,
+                                                                float* __restrict__ rstd, int rows, float eps,
+                                                                const int* __restrict__ rows_dev) {
+  constexpr int D = NV * 128;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (rows_dev) rows = min(rows, __ldg(rows_dev));
+  if (r >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)(row_map ? row_map[r] : r) * ldx);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { v[i] = xr[lane + 32 * i]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  const float mu = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+    q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)D + eps);
+  float4* yr = reinterpret_cast<float4*>(y + (long long)r * ldy);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = g4[lane + 32 * i], b = b4[lane + 32 * i];
+    float4 o;
+    o.x = (v[i].x - mu) * rs * g.x + b.x; o.y = (v[i].y - mu) * rs * g.y + b.y;
+    o.z = (v[i].z - mu) * rs * g.z + b.z; o.w = (v[i].w - mu) * rs * g.w + b.w;
+    yr[lane + 32 * i] = o;
+  }
+  if (lane == 0) {
+    if (mean) mean[r] = mu;
+    if (rstd) rstd[r] = rs;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __restrict__ dy, int lddy,
+                                                                const float* __restrict__ x, int ldx,
+                                                                const int* __restrict__ row_map,
+                                                                const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd,
+                                                                const float* __restrict__ resid, int ldres,
+                                                                float* __restrict__ dx, int lddx, int rows,
+                                                                const int* __restrict__ rows_dev) {
+  constexpr int D = NV * 128;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (rows_dev) rows = min(rows, __ldg(rows_dev));
+  if (r >= rows) return;
+  const long long xrow = row_map ? row_map[r] : r;
+  const float4* xr = reinterpret_cast<const float4*>(x + xrow * ldx);
+  const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)r * lddy);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float mu = mean[r], rs = rstd[r];
+  float4 gd[NV], xh[NV];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = g4[lane + 32 * i], d = dyr[lane + 32 * i], xv = xr[lane + 32 * i];
+    gd[i] = make_float4(g.x * d.x, g.y * d.y, g.z * d.z, g.w * d.w);
+    xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+    s1 += (gd[i].x + gd[i].y) + (gd[i].z + gd[i].w);
+    s2 = fmaf(gd[i].x, xh[i].x, s2); s2 = fmaf(gd[i].y, xh[i].y, s2);
+    s2 = fmaf(gd[i].z, xh[i].z, s2); s2 = fmaf(gd[i].w, xh[i].w, s2);
+  }
+  s1 = warp_sum(s1) / (float)D;
+  s2 = warp_sum(s2) / (float)D;
+  float4* dxr = reinterpret_cast<float4*>(dx + xrow * lddx);
+  const float4* rr = resid ? reinterpret_cast<const float4*>(resid + xrow * ldres) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float4 o;
+    o.x = rs * (gd[i].x - s1 - xh[i].x * s2); o.y = rs * (gd[i].y - s1 - xh[i].y * s2);
+    o.z = rs * (gd[i].z - s1 - xh[i].z * s2); o.w = rs * (gd[i].w - s1 - xh[i].w * s2);
+    if (rr) { const float4 q = rr[lane + 32 * i]; o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+    dxr[lane + 32 * i] = o;
+  }
+}
+
+static bool ln_vec_ok(int D, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds) {
+  if (D % 128 != 0 || D > 1024) return false;
+  for (const void* p : ptrs) if (p != nullptr && !aligned16(p)) return false;
+  for (int ld : lds) if (ld % 4 != 0) return false;
+  return true;
+}
+
 int layernorm_fwd(const float* x, int ldx, const int* row_map, const float* gamma, const float* beta, float* y, int ldy,
                   float* mean, float* rstd, int rows, int D, float eps, cudaStream_t st, const int* rows_dev) {
   if (rows == 0) return 0;
+  if (ln_vec_ok(D, {x, gamma, beta, y}, {ldx, ldy})) {
+    const int g = cdiv(rows, 8);
+#define MMX_LN_F(NV) layernorm_fwd_vec_kernel<NV><<<g, 256, 0, st>>>(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, eps, rows_dev)
+    switch (D / 128) {
+      case 1: MMX_LN_F(1); break; case 2: MMX_LN_F(2); break; case 3: MMX_LN_F(3); break; case 4: MMX_LN_F(4); break;
+      case 5: MMX_LN_F(5); break; case 6: MMX_LN_F(6); break; case 7: MMX_LN_F(7); break; default: MMX_LN_F(8); break;
+    }
+#undef MMX_LN_F
+    MMX_LAUNCH_CHECK();
+    return 0;
+  }
   layernorm_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, D, eps, rows_dev);
   MMX_LAUNCH_CHECK();
   return 0;
@@ -74,6 +179,17 @@ int layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const int*
                   const float* mean, const float* rstd, const float* resid, int ldres, float* dx, int lddx, int rows, int D,
                   cudaStream_t st, const int* rows_dev) {
   if (rows == 0) return 0;
+  if (ln_vec_ok(D, {dy, x, gamma, resid, dx}, {lddy, ldx, lddx, resid ? ldres : 0})) {
+    const int g = cdiv(rows, 8);
+#define MMX_LN_B(NV) layernorm_bwd_vec_kernel<NV><<<g, 256, 0, st>>>(dy, lddy, x, ldx, row_map, gamma, mean, rstd, resid, ldres, dx, lddx, rows, rows_dev)
+    switch (D / 128) {
+      case 1: MMX_LN_B(1); break; case 2: MMX_LN_B(2); break; case 3: MMX_LN_B(3); break; case 4: MMX_LN_B(4); break;
+      case 5: MMX_LN_B(5); break; case 6: MMX_LN_B(6); break; case 7: MMX_LN_B(7); break; default: MMX_LN_B(8); break;
+    }
+#undef MMX_LN_B
+    MMX_LAUNCH_CHECK();
+    return 0;
+  }
   layernorm_bwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(dy, lddy, x, ldx, row_map, gamma, mean, rstd, resid, ldres, dx, lddx,
                                                       rows, D, rows_dev);
   MMX_LAUNCH_CHECK();
