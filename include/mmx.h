@@ -61,7 +61,10 @@ int mmx_avg_heads(const float* A, const float* dA, float* Abar, int B, int H, in
 /* Rules 6+7:  R_ss_out = R_ss + Abar*R_ss ;  R_sq_out = R_sq + Abar*R_sq  (both from the PRE-update state).
  * Replaces apply_self_attention_rules + the caller's "+=" (DETR/modules/ExplanationGenerator.py:27-30,118,
  * 127-129) and "R = R + torch.bmm(cam, R)" (CLIP_explainability.ipynb:182,205).
- * Abar [B,S,S] (ld_a), R_ss [B,S,S] (ld_ss), R_sq [B,S,Q] (ld_sq) or NULL.  Outputs may not alias inputs. */
+ * Abar [B,S,S] (ld_a), R_ss [B,S,S] (ld_ss), R_sq [B,S,Q] (ld_sq) or NULL.  Outputs may not alias inputs.
+ * For S >= 128 (and Q >= 128) with row strides that are multiples of 4 covering round_up(cols, 4) zero-padded columns,
+ * the product runs on the tensor cores (tcgen05 3xTF32, "+R" fused as the epilogue residual); smaller or unaligned
+ * problems use the fp32 FFMA kernel. */
 int mmx_self_update(const float* Abar, int ld_a, const float* R_ss, float* R_ss_out, int ld_ss,
                     const float* R_sq, float* R_sq_out, int ld_sq, int B, int S, int Q, void* stream);
 

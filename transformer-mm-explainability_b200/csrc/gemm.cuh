@@ -25,6 +25,12 @@ int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc
             const GemmEpilogue& ep, cudaStream_t st);
 
 int gemm_tc_available();
+
+// Tensor-core product for the relevancy updates (no bias / activation): C = residual + A * Bt^T with N possibly not a
+// multiple of 4 as long as every row stride covers round_up(N, 4) columns (the pad columns receive zeros).  Returns
+// taken = false when the shapes / alignment / backend do not qualify.
+int gemm_nt_tc_rule(const float* A, int lda, const float* Bt, int ldb, const float* residual, int ldres, float* C, int ldc,
+                    int M, int N, int K, cudaStream_t st, bool* taken);
 int gemm_backend();
 
 }  // namespace mmx

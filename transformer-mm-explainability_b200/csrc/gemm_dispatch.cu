@@ -55,6 +55,21 @@ static int gemm_nt_impl(const float* A, int lda, const float* Bt, int ldb, float
   return gemm_nt_simt(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
 }
 
+int gemm_nt_tc_rule(const float* A, int lda, const float* Bt, int ldb, const float* residual, int ldres, float* C, int ldc,
+                    int M, int N, int K, cudaStream_t st, bool* taken) {
+  *taken = false;
+  const int Np = round_up(N, 4);
+  if (gemm_backend() < 1 || !gemm_tc_available()) return 0;
+  if (M < 128 || N < 128 || K < 64 || (lda % 4) || (ldb % 4) || (ldc % 4) || ldc < Np) return 0;
+  if (residual && ((ldres % 4) || ldres < Np || !aligned16(residual))) return 0;
+  if (!aligned16(A) || !aligned16(Bt) || !aligned16(C)) return 0;
+  GemmEpilogue ep;
+  ep.residual = residual; ep.ldres = ldres;
+  *taken = true;
+  // N is passed rounded up: rows N..Np-1 of Bt do not exist for TMA (zero-filled), the pad columns of C get 0 + residual pad
+  return gemm_nt_tc(A, lda, Bt, ldb, C, ldc, M, Np, K, ep, st);
+}
+
 // Optional per-launch CUDA-event timing of the GEMMs (the dominant kernel) for bench.py's roofline line.
 struct ProfRec { cudaEvent_t s, e; double flops; const int* m_dev; int M; };
 static std::mutex g_prof_mu;

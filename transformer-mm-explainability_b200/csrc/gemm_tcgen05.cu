@@ -17,7 +17,7 @@
 //
 // Structure (one CTA per SM, persistent over 128x128 output tiles, 4-stage ring of 128x32 K-slabs):
 //   warp 0      TMA producer: raw fp32 A and B tiles -> shared memory (128-byte swizzle), mbarrier complete_tx
-//   warps 12-19 splitters (two per TMEM lane quarter, each converts half of the slab's K columns): A tile (smem) -> hi/lo -> TMEM columns of this
+//   warps 12-15 splitters (one per TMEM lane quarter; build with -DMMX_TC_SPLIT_WARPS=8 for two per quarter): A tile (smem) -> hi/lo -> TMEM columns of this
 //               stage; B tile -> hi/lo planes in smem
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (3 per k-step), tcgen05.commit
 //   warp 2      TMEM allocator (512 columns: 128 main + 128 cross accumulator + 4 stages x 64 columns of A)
@@ -33,10 +33,16 @@ namespace mmx {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;    // BK fp32 = 128 bytes = one swizzle-128B row
-constexpr int SPLIT_WARPS = 8;                 // two warps per TMEM lane quarter, each takes half of the slab's K columns
-constexpr int THREADS = (12 + SPLIT_WARPS) * 32;   // 4 control + 8 epilogue + 8 splitter warps = 640 threads
-// 65536 / 640 = 102 -> ptxas budget 96 regs/thread; the epilogue needs ~128, the other roles far fewer, so the
-// warpgroups rebalance at run time (setmaxnreg): 4*32*64 + 8*32*136 + 8*32*72 = 61440 = 640*96.
+// Splitter warps: 4 (one per TMEM lane quarter, 512 threads, 128 regs/thread for everyone) or 8 (two per quarter, each
+// converting half of the slab's K columns; 640 threads, which needs setmaxnreg rebalancing because the epilogue uses
+// ~128 registers: 4*32*64 + 8*32*136 + 8*32*72 = 61440 = 640*96).  Measured 75.7 vs ~77 us on the QKV shape; the
+// 4-warp build is the default because it has no blocking register hand-off.
+#ifndef MMX_TC_SPLIT_WARPS
+#define MMX_TC_SPLIT_WARPS 4
+#endif
+constexpr int SPLIT_WARPS = MMX_TC_SPLIT_WARPS;
+constexpr bool REBALANCE = SPLIT_WARPS == 8;
+constexpr int THREADS = (12 + SPLIT_WARPS) * 32;
 constexpr int REGS_CTRL = 64, REGS_EPI = 136, REGS_SPLIT = 72;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, SPLIT_WARP0 = 12;
 constexpr int STAGES = 4;
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (REBALANCE && warp < 4) {
     reg_dec<REGS_CTRL>();
   }
   if (warp == 0) {
@@ -274,11 +280,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       }
     }
   } else if (warp >= SPLIT_WARP0) {
-    reg_dec<REGS_SPLIT>();
+    if (REBALANCE) reg_dec<REGS_SPLIT>();
     // ------------------------------------------------------------------ splitter: A slab (smem) -> hi/lo -> TMEM
     const int q = warp & 3;                                     // TMEM lane quarter this warp may write
-    const int half = (warp - SPLIT_WARP0) >> 2;                 // which 16 of the slab's 32 K columns this warp converts
-    const int stid = threadIdx.x - SPLIT_WARP0 * 32;            // 0..255
+    constexpr int HSTEP = SPLIT_WARPS / 4;                       // warps per lane quarter (1 or 2)
+    const int half0 = (warp - SPLIT_WARP0) >> 2;                // first 16-column half of the slab this warp converts
+    const int stid = threadIdx.x - SPLIT_WARP0 * 32;            // 0 .. SPLIT_WARPS*32-1
     const int row = q * 32 + lane;                              // tile row handled by this thread
     const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
     int stage = 0; uint32_t phase = 0;
@@ -289,39 +296,46 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         __syncwarp();
         if (warp == SPLIT_WARP0 && lane == 0) MMX_TRACE(2, slab, 0);
         if (!(p.dbg & 2)) {
-          // A slab: half of this thread's row (64 B, swizzled 16-byte chunks) -> hi/lo -> 16 + 16 TMEM columns.
+          // A slab: this thread's row (128 B, swizzled 16-byte chunks) -> hi/lo -> TMEM columns of the stage.
           // The tensor core reads only the top 19 bits of an fp32 operand (kind::tf32 truncates; measured: results
           // are bit-identical with and without an explicit hi plane), so the raw values ARE the hi operand.
           const uint8_t* a_raw = smem_gen + stage * STAGE_BYTES + row_off;
-          const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * stage + 16u * half;
-          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t chunk = (uint32_t)(half * 4 + c);    // 16-byte chunk = k 4*chunk .. 4*chunk+3
-            const uint4 x = *reinterpret_cast<const uint4*>(a_raw + ((chunk ^ sw) << 4));
-            const uint32_t xv[4] = {x.x, x.y, x.z, x.w};
+          for (int half = half0; half < 2; half += HSTEP) {
+            const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * stage + 16u * half;
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              hi[c * 4 + e] = xv[e];
-              lo[c * 4 + e] = __float_as_uint(__uint_as_float(xv[e]) - __uint_as_float(xv[e] & 0xFFFFE000u));
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t chunk = (uint32_t)(half * 4 + c);  // 16-byte chunk = k 4*chunk .. 4*chunk+3
+              const uint4 x = *reinterpret_cast<const uint4*>(a_raw + ((chunk ^ sw) << 4));
+              const uint32_t xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hi[c * 4 + e] = xv[e];
+                lo[c * 4 + e] = __float_as_uint(__uint_as_float(xv[e]) - __uint_as_float(xv[e] & 0xFFFFE000u));
+              }
             }
+            tmem_st16(t_hi, hi);
+            tmem_st16(t_hi + 32u, lo);
           }
-          tmem_st16(t_hi, hi);
-          tmem_st16(t_hi + 32u, lo);
           // B slab: lo plane beside the raw tile (elementwise, so the swizzle does not matter)
           const uint4* braw = reinterpret_cast<const uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES);
           uint4* blo = reinterpret_cast<uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES + B_BYTES);
-          uint4 x[4];
+          constexpr int NT = SPLIT_WARPS * 32, PER = (B_BYTES / 16) / NT;   // 16-byte elements per thread (8 or 4)
 #pragma unroll
-          for (int u = 0; u < 4; ++u) x[u] = braw[u * 256 + stid];
+          for (int u0 = 0; u0 < PER; u0 += 4) {
+            uint4 x[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 l;
-            l.x = __float_as_uint(__uint_as_float(x[u].x) - __uint_as_float(x[u].x & 0xFFFFE000u));
-            l.y = __float_as_uint(__uint_as_float(x[u].y) - __uint_as_float(x[u].y & 0xFFFFE000u));
-            l.z = __float_as_uint(__uint_as_float(x[u].z) - __uint_as_float(x[u].z & 0xFFFFE000u));
-            l.w = __float_as_uint(__uint_as_float(x[u].w) - __uint_as_float(x[u].w & 0xFFFFE000u));
-            blo[u * 256 + stid] = l;
+            for (int u = 0; u < 4; ++u) x[u] = braw[(u0 + u) * NT + stid];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 l;
+              l.x = __float_as_uint(__uint_as_float(x[u].x) - __uint_as_float(x[u].x & 0xFFFFE000u));
+              l.y = __float_as_uint(__uint_as_float(x[u].y) - __uint_as_float(x[u].y & 0xFFFFE000u));
+              l.z = __float_as_uint(__uint_as_float(x[u].z) - __uint_as_float(x[u].z & 0xFFFFE000u));
+              l.w = __float_as_uint(__uint_as_float(x[u].w) - __uint_as_float(x[u].w & 0xFFFFE000u));
+              blo[(u0 + u) * NT + stid] = l;
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       }
     }
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
-    reg_inc<REGS_EPI>();
+    if (REBALANCE) reg_inc<REGS_EPI>();
     // ------------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
     const int q = warp & 3;                                     // TMEM lane quarter this warp may read
     const int ch = (warp - EPI_WARP0) >> 2;                     // column half: 64 of the 128 accumulator columns
@@ -471,7 +485,7 @@ void gemm_tc_set_trace(long long* buf) { tc::g_trace = buf; }
 bool gemm_tc_shape_ok(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int N, int K,
                       const GemmEpilogue& ep) {
   if (!gemm_tc_available()) return false;
-  if (N < 128 || K < 64 || (K % 4) || (N % 4) || (lda % 4) || (ldb % 4) || (ldc % 4)) return false;
+  if (N < 128 || K < 64 || (N % 4) || (lda % 4) || (ldb % 4) || (ldc % 4)) return false;   // K itself is free: TMA zero-fills the tail
   if (!aligned16(A) || !aligned16(Bt) || !aligned16(C)) return false;
   if ((ep.bias && !aligned16(ep.bias)) || (ep.pre && (!aligned16(ep.pre) || ep.ldpre % 4)) ||
       (ep.residual && (!aligned16(ep.residual) || ep.ldres % 4)) || (ep.C_act && !aligned16(ep.C_act)))

@@ -1,6 +1,7 @@
 // Relevancy rule kernels: rule 5 (Hadamard / clamp / head-mean), rules 6/7/10/11 (batched R updates),
 // eq. 8-9 (row normalisation) and the rollout baseline.  See include/mmx.h for the reference lines replaced.
 #include "mmx_common.cuh"
+#include "gemm.cuh"
 #include <math_constants.h>
 
 namespace mmx {
@@ -213,6 +214,64 @@ int bmm_add(const float* A, int lda, long long sA, int transA, const float* Bm, 
   return 0;
 }
 
+// out[b][n][k] = in[b][k][n] for n < N, k < K, zero in the pads (out is [batch][Np][Kp] dense): the K-major "B"
+// operand of the tensor-core product  R + Abar * R  (the GEMM kernel takes both operands K-major).
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ in, int ld_in, long long s_in,
+                                                            float* __restrict__ out, int K, int N, int Kp, int Np) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  in += b * s_in;
+  out += (long long)b * Np * Kp;
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + tx;
+    t[i][tx] = (k < K && n < N) ? in[(long long)k * ld_in + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + tx;
+    if (n < Np && k < Kp) out[(long long)n * Kp + k] = t[tx][i];
+  }
+}
+
+// Rules 6/7 on the tensor cores:  C[b] = R[b] + Abar[b] * R[b]   for S >= 128 (DETR 625-850, ViT-B/16 197, ViT-L 577).
+// Per sample: transpose R into a K-major scratch, then one tcgen05 3xTF32 GEMM with the "+R" fused as the residual
+// epilogue.  Small S (CLIP 50/77, LXMERT 20/36) stays on the FFMA kernel: a 128x128 tensor tile would be mostly padding.
+static int self_update_tc(const float* Abar, int ld_a, const float* R, float* R_out, int ld, int B, int S, int Q,
+                          cudaStream_t st, bool* taken) {
+  *taken = false;
+  if (gemm_backend() < 1 || S < 128 || Q < 128 || (ld_a % 4) || (ld % 4) || ld < round_up(Q, 4) || !aligned16(Abar) ||
+      !aligned16(R) || !aligned16(R_out))
+    return 0;
+  static bool pool_set = false;
+  if (!pool_set) {                       // keep stream-ordered scratch cached across synchronisation points
+    cudaMemPool_t pool;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    pool_set = true;
+  }
+  const int Kp = round_up(S, 4), Np = round_up(Q, 4);
+  float* Rt = nullptr;
+  MMX_CHECK_CUDA(cudaMallocAsync((void**)&Rt, (size_t)B * Np * Kp * sizeof(float), st));
+  dim3 grid(cdiv(Np, 32), cdiv(Kp, 32), B);
+  transpose_pad_kernel<<<grid, 256, 0, st>>>(R, ld, (long long)S * ld, Rt, S, Q, Kp, Np);
+  count_launch();
+  int rc = 0;
+  for (int b = 0; b < B && rc == 0; ++b) {
+    bool ok = false;
+    rc = gemm_nt_tc_rule(Abar + (size_t)b * S * ld_a, ld_a, Rt + (size_t)b * Np * Kp, Kp, R + (size_t)b * S * ld, ld,
+                         R_out + (size_t)b * S * ld, ld, S, Q, S, st, &ok);
+    if (rc == 0 && !ok) { rc = 3; set_error("tensor-core rule GEMM rejected a shape it was offered"); }
+  }
+  cudaFreeAsync(Rt, st);
+  *taken = rc == 0;
+  return rc;
+}
+
 int avg_heads(const float* A, const float* dA, float* Abar, int B, int H, int T, int S, int ld_in, int ld_out,
               cudaStream_t st) {
   MMX_REQUIRE(B >= 0 && H > 0 && T >= 0 && S >= 0 && ld_in >= S && ld_out >= S, "bad dims");
@@ -267,11 +326,18 @@ int mmx_self_update(const float* Abar, int ld_a, const float* R_ss, float* R_ss_
                     float* R_sq_out, int ld_sq, int B, int S, int Q, void* stream) {
   MMX_REQUIRE(R_ss != R_ss_out && (R_sq == nullptr || R_sq != R_sq_out), "outputs may not alias inputs");
   cudaStream_t st = (cudaStream_t)stream;
-  MMX_TRY(bmm_add(Abar, ld_a, (long long)S * ld_a, 0, R_ss, ld_ss, (long long)S * ld_ss, R_ss, ld_ss,
-                  (long long)S * ld_ss, R_ss_out, ld_ss, (long long)S * ld_ss, B, S, S, S, 0, st));
-  if (R_sq != nullptr && Q > 0)
-    MMX_TRY(bmm_add(Abar, ld_a, (long long)S * ld_a, 0, R_sq, ld_sq, (long long)S * ld_sq, R_sq, ld_sq,
-                    (long long)S * ld_sq, R_sq_out, ld_sq, (long long)S * ld_sq, B, S, Q, S, 0, st));
+  bool tc = false;
+  MMX_TRY(self_update_tc(Abar, ld_a, R_ss, R_ss_out, ld_ss, B, S, S, st, &tc));
+  if (!tc)
+    MMX_TRY(bmm_add(Abar, ld_a, (long long)S * ld_a, 0, R_ss, ld_ss, (long long)S * ld_ss, R_ss, ld_ss,
+                    (long long)S * ld_ss, R_ss_out, ld_ss, (long long)S * ld_ss, B, S, S, S, 0, st));
+  if (R_sq != nullptr && Q > 0) {
+    tc = false;
+    MMX_TRY(self_update_tc(Abar, ld_a, R_sq, R_sq_out, ld_sq, B, S, Q, st, &tc));
+    if (!tc)
+      MMX_TRY(bmm_add(Abar, ld_a, (long long)S * ld_a, 0, R_sq, ld_sq, (long long)S * ld_sq, R_sq, ld_sq,
+                      (long long)S * ld_sq, R_sq_out, ld_sq, (long long)S * ld_sq, B, S, Q, S, 0, st));
+  }
   return 0;
 }
 

@@ -32,15 +32,33 @@ def avg_heads_batched(cam: torch.Tensor, grad: torch.Tensor, batch: int) -> torc
 
 
 def avg_heads_record(rec, batch: int) -> torch.Tensor:
-    """Rule 5 straight from an attention record (nn.AttnRecord): reads the zero-padded staged A / dA in place."""
+    """Rule 5 straight from an attention record (nn.AttnRecord): reads the zero-padded staged A / dA in place with the
+    128-bit kernel and returns a [B,T,S] VIEW of a zero-padded [B,T,ld] buffer (row stride ld = round_up(S,4)), the
+    layout the tensor-core R update wants."""
     A, dA, ld = rec.padded()
     if dA is None:
         raise MmxError("no attention gradient recorded (backward did not reach this attention)")
     B, H, T = A.shape[0], A.shape[1], A.shape[2]
     assert B == batch
-    out = torch.empty(B, T, rec.S, device=A.device, dtype=torch.float32)
-    check(lib().mmx_avg_heads(ptr(A), ptr(dA), ptr(out), B, H, T, rec.S, ld, rec.S, current_stream()))
-    return out
+    out = torch.empty(B, T, ld, device=A.device, dtype=torch.float32)
+    # the pad columns of A and dA are zero, so the plane is treated as dense [T, ld]
+    check(lib().mmx_avg_heads(ptr(A), ptr(dA), ptr(out), B, H, T, ld, ld, ld, current_stream()))
+    return out[..., :rec.S]
+
+
+def _padded3(t: torch.Tensor):
+    """[B,R,C] fp32 CUDA tensor -> (tensor whose rows are 16-byte aligned with zero pads, ld).  Views produced by this
+    module (row stride = round_up(C,4), dense planes) pass through without a copy."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise MmxError("mmx_b200 rule functions need CUDA tensors (no CPU fallback)")
+    B, R, Cc = t.shape
+    ldp = (Cc + 3) // 4 * 4
+    if (t.dtype == torch.float32 and t.stride(2) == 1 and t.stride(1) == ldp and (B == 1 or t.stride(0) == R * ldp)
+            and t.data_ptr() % 16 == 0):
+        return t, ldp
+    buf = torch.zeros(B, R, ldp, device=t.device, dtype=torch.float32)
+    buf[..., :Cc] = t
+    return buf[..., :Cc], ldp
 
 
 def avg_heads(cam: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
@@ -52,17 +70,17 @@ def self_update(R_ss: torch.Tensor, cam_ss: torch.Tensor, R_sq: torch.Tensor | N
     """Fused rules 6+7 including the caller's ``+=``: returns (R_ss + cam*R_ss, R_sq + cam*R_sq).  Accepts [S,S] or
     batched [B,S,S]."""
     squeeze = R_ss.dim() == 2
-    R = _prep(R_ss if not squeeze else R_ss.unsqueeze(0))
-    Ab = _prep(cam_ss if not squeeze else cam_ss.unsqueeze(0))
+    R, ld = _padded3(R_ss if not squeeze else R_ss.unsqueeze(0))
+    Ab, lda = _padded3(cam_ss if not squeeze else cam_ss.unsqueeze(0))
     B, S = R.shape[0], R.shape[-1]
-    out = torch.empty_like(R)
+    out = torch.zeros(B, S, ld, device=R.device, dtype=torch.float32)[..., :S]     # zero pads, 16-byte aligned rows
     Rq = outq = None
-    Q = 0
+    Q, ldq = 0, 4
     if R_sq is not None:
-        Rq = _prep(R_sq if not squeeze else R_sq.unsqueeze(0))
+        Rq, ldq = _padded3(R_sq if not squeeze else R_sq.unsqueeze(0))
         Q = Rq.shape[-1]
-        outq = torch.empty_like(Rq)
-    check(lib().mmx_self_update(ptr(Ab), S, ptr(R), ptr(out), S, ptr(Rq), ptr(outq), max(Q, 1), B, S, Q, current_stream()))
+        outq = torch.zeros(B, S, ldq, device=R.device, dtype=torch.float32)[..., :Q]
+    check(lib().mmx_self_update(ptr(Ab), lda, ptr(R), ptr(out), ld, ptr(Rq), ptr(outq), ldq, B, S, Q, current_stream()))
     if squeeze:
         return out[0], (outq[0] if outq is not None else None)
     return out, outq
