@@ -222,8 +222,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
       for (int kb = 0; kb < nk; ++kb) {
-        if (lane == 0) mbar_spin(empty_bar(stage), phase ^ 1);
-        __syncwarp();
+        mbar_wait(empty_bar(stage), phase ^ 1);
         MMX_TRACE(0, pslab, 0);
         const uint32_t sa = smem_base + stage * STAGE_BYTES;
         if (elect_one()) {
@@ -247,12 +246,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     int it = 0, mslab = 0;
     const uint32_t d_main = tmem_base + TM_MAIN, d_cross = tmem_base + TM_CROSS;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      if (lane == 0) mbar_spin(tempty_bar, (uint32_t)(it & 1) ^ 1);   // epilogue drained the accumulators
-      __syncwarp();
+      mbar_wait(tempty_bar, (uint32_t)(it & 1) ^ 1);               // epilogue drained the accumulators
       tc_fence_after();
       for (int kb = 0; kb < nk; ++kb) {
-        if (lane == 0) mbar_spin(split_bar(stage), phase);        // A hi/lo in TMEM, B lo plane written (implies the TMA landed)
-        __syncwarp();
+        mbar_wait(split_bar(stage), phase);                       // A hi/lo in TMEM, B lo plane written (implies the TMA landed)
         MMX_TRACE(1, mslab, 0);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -292,8 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     int slab = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < nk; ++kb, ++slab) {
-        if (lane == 0) mbar_spin(full_bar(stage), phase);       // one polling lane per warp, no suspend/wake-up latency
-        __syncwarp();
+        mbar_wait(full_bar(stage), phase);
         if (warp == SPLIT_WARP0 && lane == 0) MMX_TRACE(2, slab, 0);
         if (!(p.dbg & 2)) {
           // A slab: this thread's row (128 B, swizzled 16-byte chunks) -> hi/lo -> TMEM columns of the stage.
@@ -355,8 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
-      if (lane == 0) mbar_spin(tfull_bar, (uint32_t)(it & 1));
-      __syncwarp();
+      mbar_wait(tfull_bar, (uint32_t)(it & 1));
       if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 0);
       tc_fence_after();
       // drain main + cross accumulators into registers (RN add), then hand TMEM back before any global traffic
