@@ -58,6 +58,12 @@ int mmx_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 int mmx_avg_heads(const float* A, const float* dA, float* Abar, int B, int H, int T, int S,
                   int ld_in, int ld_out, void* stream);
 
+/* attn-GradCAM baseline:  out[b,t,s] = relu( (1/H) sum_h A[b,h,t,s] * mean_{t',s'} dA[b,h,t',s'] ).
+ * Replaces gradcam() (DETR/modules/ExplanationGenerator.py:275-280; lxmert/lxmert/src/ExplanationGenerator.py:542-547).
+ * gbar: device scratch of B*H floats. */
+int mmx_attn_gradcam(const float* A, const float* dA, float* out, float* gbar, int B, int H, int T, int S, int ld_in,
+                     int ld_out, void* stream);
+
 /* Rules 6+7:  R_ss_out = R_ss + Abar*R_ss ;  R_sq_out = R_sq + Abar*R_sq  (both from the PRE-update state).
  * Replaces apply_self_attention_rules + the caller's "+=" (DETR/modules/ExplanationGenerator.py:27-30,118,
  * 127-129) and "R = R + torch.bmm(cam, R)" (CLIP_explainability.ipynb:182,205).

@@ -112,6 +112,8 @@ def golden_detr():
         for s10 in (True, False):
             r = ref_detr.generate_ours(cfg, sd, src, pos, tq, normalize_self_attention=norm, apply_self_in_rule_10=s10)
             out[f"R.n{int(norm)}s{int(s10)}"] = r.numpy()
+    for method in ("raw_attn", "rollout", "attn_gradcam"):          # baselines behind the same API
+        out["base." + method] = ref_detr.generate_baseline(cfg, sd, src, pos, tq, method).numpy()
     np.savez_compressed(os.path.join(OUT, "detr_tiny.npz"), **out)
     print("wrote detr_tiny", out["R.n1s1"].shape)
 
@@ -129,6 +131,9 @@ def golden_lxmert():
             rtt, rti = ref_lxmert.generate_ours(cfg, sd, ids, feats, boxes, normalize_self_attention=norm,
                                                 apply_self_in_rule_10=s10)
             out[f"Rtt.n{int(norm)}s{int(s10)}"], out[f"Rti.n{int(norm)}s{int(s10)}"] = rtt.numpy(), rti.numpy()
+    for method in ("raw_attn", "rollout", "attn_gradcam"):
+        rtt, rti = ref_lxmert.generate_baseline(cfg, sd, ids, feats, boxes, method)
+        out[f"base.{method}.Rtt"], out[f"base.{method}.Rti"] = rtt.numpy(), rti.numpy()
     np.savez_compressed(os.path.join(OUT, "lxmert_tiny.npz"), **out)
     print("wrote lxmert_tiny", out["Rtt.n1s1"].shape, out["Rti.n1s1"].shape)
 

@@ -51,3 +51,16 @@ def generate_ours(cfg, sd, src, pos, tq, **kw):
             r = gen.generate_ours((src[b:b + 1], pos[b:b + 1]), torch.tensor([int(tq[b])]), use_lrp=False, **kw)
             outs.append(r.reshape(-1).detach())
     return torch.stack(outs)
+
+
+def generate_baseline(cfg, sd, src, pos, tq, method):
+    """method in {"raw_attn", "rollout", "attn_gradcam"}: the reference Generator's baseline of that name, per sample."""
+    m, Generator = build(cfg, sd)
+    gen = Generator(m)
+    outs = []
+    with rs.cuda_is_identity():
+        for b in range(src.shape[0]):
+            fn = getattr(gen, "generate_" + method)
+            r = fn((src[b:b + 1], pos[b:b + 1]), torch.tensor([int(tq[b])]))
+            outs.append(r.reshape(-1).detach())
+    return torch.stack(outs)

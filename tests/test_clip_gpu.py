@@ -156,3 +156,16 @@ def test_ragged_text_edge_lengths(mmx):
         ot, oi = co.clip_interpret(sd, cfg, images, tokens, sl, sl)
         assert text_rel_err(rt, ot) < TOL and rel_err(ri, oi) < TOL
         assert torch.equal(rt[2].cpu()[1:], torch.eye(ctx)[1:])      # a one-token prompt: only row 0 can change
+
+
+def test_vit_l14_336_vs_oracle(mmx):
+    """BASELINE.json config 5 model (CLIP ViT-L/14@336: 24 vision blocks, 577 tokens, 16 heads; 12 text blocks of
+    width 768) on 2 pairs, all layers, against the oracle; also exercises micro-batching (max_batch = 1)."""
+    cfg = co.VIT_L14_336
+    sd = co.init_state_dict(cfg, seed=0)
+    images, tokens = co.synthetic_inputs(cfg, 2, seed=4)
+    ot, oi = co.clip_interpret(sd, cfg, images, tokens, 0, 0)
+    eng = _engine(mmx, cfg, sd, 1)
+    rt, ri = mmx.interpret(images.cuda(), tokens.cuda(), eng, "cuda:0", 0, 0)
+    assert ri.shape == (2, 576) and rt.shape == (2, 77, 77)
+    assert text_rel_err(rt, ot) < TOL and rel_err(ri, oi) < TOL

@@ -89,3 +89,30 @@ def test_lxmert_base_shape_vs_oracle():
     assert rel_err(eng.question_answering_score, logits) < TOL
     assert rel_err(rtt, ott) < TOL and rel_err(rti, oti) < TOL
     assert (rtt[:, 0, 0] == 0).all()
+
+
+@pytest.mark.parametrize("method", ["raw_attn", "rollout", "attn_gradcam"])
+def test_detr_baselines_golden(golden_dir, method):
+    """Baseline methods behind the same API vs the reference Generator's own outputs."""
+    import mmx_b200
+    g = np.load(os.path.join(golden_dir, "detr_tiny.npz"))
+    eng = mmx_b200.DetrEngine(_sd(g), nhead=do.DETR_TINY.nhead, device="cuda:0")
+    gen = mmx_b200.Generator(eng)
+    src, pos, tq = (torch.from_numpy(g[k]) for k in ("src", "pos", "tq"))
+    out = getattr(gen, "generate_" + method)((src.cuda(), pos.cuda()), tq)
+    assert rel_err(out, g["base." + method]) < TOL
+    with pytest.raises(NotImplementedError):
+        gen.generate_partial_lrp((src.cuda(), pos.cuda()), tq)
+
+
+@pytest.mark.parametrize("method", ["raw_attn", "rollout", "attn_gradcam"])
+def test_lxmert_baselines_golden(golden_dir, method):
+    import mmx_b200
+    g = np.load(os.path.join(golden_dir, "lxmert_tiny.npz"))
+    eng = mmx_b200.LxmertEngine(_sd(g), num_heads=lo.LXMERT_TINY.heads, device="cuda:0")
+    gen = mmx_b200.GeneratorBaselines(eng)
+    ids, feats, boxes = (torch.from_numpy(g[k]) for k in ("ids", "feats", "boxes"))
+    rtt, rti = getattr(gen, "generate_" + method)((ids.cuda(), feats.cuda(), boxes.cuda()))
+    assert rel_err(rtt, g[f"base.{method}.Rtt"]) < TOL and rel_err(rti, g[f"base.{method}.Rti"]) < TOL
+    with pytest.raises(NotImplementedError):
+        gen.generate_transformer_attr((ids.cuda(), feats.cuda(), boxes.cuda()))

@@ -16,7 +16,7 @@ from .rules import (avg_heads, avg_heads_batched, apply_self_attention_rules, ap
 from .clip import ClipConfig, ClipEngine, interpret, VIT_B32, VIT_L14_336  # noqa: F401
 from .vit import ViTEngine, generate_relevance  # noqa: F401
 from .detr import DetrEngine, Generator  # noqa: F401
-from .lxmert import LxmertEngine, GeneratorOurs  # noqa: F401
+from .lxmert import LxmertEngine, GeneratorOurs, GeneratorBaselines  # noqa: F401
 
 __all__ = ["MmxError", "lib", "interpret", "ClipEngine", "ClipConfig", "avg_heads", "avg_heads_batched",
            "apply_self_attention_rules", "apply_mm_attention_rules", "apply_mm_attention_rules_lxmert",

@@ -32,6 +32,7 @@ _SIGS = {
     "mmx_gemm_trace": (C.c_int, [C.c_void_p]),
     "mmx_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mmx_avg_heads": (C.c_int, [c_float_p, c_float_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "mmx_attn_gradcam": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
     "mmx_self_update": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_handle_residual": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p]),

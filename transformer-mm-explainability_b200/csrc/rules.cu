@@ -52,6 +52,41 @@ __global__ void __launch_bounds__(256) avg_heads_vec4_kernel(const float* __rest
   }
 }
 
+// attn-GradCAM baseline (DETR/modules/ExplanationGenerator.py:275-280): gbar[b,h] = mean_{t,s} dA[b,h,t,s], then
+// out[b,t,s] = relu((1/H) sum_h A[b,h,t,s] * gbar[b,h]).
+__global__ void __launch_bounds__(256) plane_mean_kernel(const float* __restrict__ G, float* __restrict__ gbar, int T, int S,
+                                                         int ld) {
+  __shared__ float red[8];
+  const float* g = G + (long long)blockIdx.x * T * ld;
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < T * S; e += blockDim.x) acc += g[(long long)(e / S) * ld + e % S];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    gbar[blockIdx.x] = t / (float)((long long)T * S);
+  }
+}
+__global__ void __launch_bounds__(256) gradcam_kernel(const float* __restrict__ A, const float* __restrict__ gbar,
+                                                      float* __restrict__ out, int B, int H, int T, int S, int ld_in,
+                                                      int ld_out) {
+  const long long items = (long long)B * T * S;
+  const long long plane = (long long)T * ld_in;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(it % S);
+    const long long r = it / S;
+    const int t = (int)(r % T);
+    const long long b = r / T;
+    const long long off = (b * H) * plane + (long long)t * ld_in + s;
+    float acc = 0.f;
+    for (int h = 0; h < H; ++h) acc = fmaf(A[off + h * plane], gbar[b * H + h], acc);
+    out[(b * T + t) * ld_out + s] = fmaxf(acc / (float)H, 0.f);
+  }
+}
+
 // generic strided / unaligned form (32-bit coalesced loads)
 __global__ void __launch_bounds__(256) avg_heads_scalar_kernel(const float* __restrict__ A, const float* __restrict__ G,
                                                                float* __restrict__ out, int B, int H, int T, int S,
@@ -313,6 +348,18 @@ extern "C" {
 int mmx_avg_heads(const float* A, const float* dA, float* Abar, int B, int H, int T, int S, int ld_in, int ld_out,
                   void* stream) {
   return avg_heads(A, dA, Abar, B, H, T, S, ld_in, ld_out, (cudaStream_t)stream);
+}
+
+int mmx_attn_gradcam(const float* A, const float* dA, float* out, float* gbar, int B, int H, int T, int S, int ld_in,
+                     int ld_out, void* stream) {
+  MMX_REQUIRE(B >= 0 && H > 0 && ld_in >= S && ld_out >= S && gbar != nullptr, "bad arguments");
+  if (B == 0 || T == 0 || S == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  plane_mean_kernel<<<B * H, 256, 0, st>>>(dA, gbar, T, S, ld_in);
+  MMX_LAUNCH_CHECK();
+  gradcam_kernel<<<grid_for((long long)B * T * S), 256, 0, st>>>(A, gbar, out, B, H, T, S, ld_in, ld_out);
+  MMX_LAUNCH_CHECK();
+  return 0;
 }
 
 int mmx_bmm_add(const float* A, int lda, long long strideA, int transA, const float* Bm, int ldb, long long strideB,

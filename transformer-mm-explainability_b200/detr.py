@@ -84,8 +84,9 @@ class DetrEngine:
         o = tape.attention(q, k, v, B, H, T, S, float(self.d_model // H) ** -0.5, 0, None, m["rec"])
         return tape.linear(o, m["o"])
 
-    def forward_backward(self, src: torch.Tensor, pos: torch.Tensor, target_index, index=None):
-        """Forward staging every A, one-hot on pred_logits[b, target_b, class_b], backward staging every dA."""
+    def forward_backward(self, src: torch.Tensor, pos: torch.Tensor, target_index, index=None, backward: bool = True):
+        """Forward staging every A, one-hot on pred_logits[b, target_b, class_b], backward staging every dA
+        (``backward=False``: forward only, for the raw-attention / rollout baselines)."""
         dev = self.device
         with torch.cuda.device(dev):
             B, d, h, w = src.shape
@@ -113,6 +114,9 @@ class DetrEngine:
             logits = tape.linear(hs, self.class_embed)                             # [B*Q, C+1]
             C1 = logits.cols
             self.pred_logits = logits.v.view(B, Q, C1)
+            self._shape = (B, S, Q)
+            if not backward:
+                return {"pred_logits": self.pred_logits}
             tq_idx = torch.as_tensor(target_index, device=dev).reshape(B).long()
             rows = torch.arange(B, device=dev) * Q + tq_idx
             if index is None:                                                      # ExplanationGenerator.py:151-152
@@ -177,9 +181,56 @@ class Generator:
             self.handle_co_attn_query(blk)
         if normalize_self_attention and apply_self_in_rule_10 and self._min_diag:
             assert torch.stack(self._min_diag).min().item() >= 0                     # handle_residual's assert (:50)
+        return self._pick(target_index)
+
+    def _pick(self, target_index):
+        """``aggregated[:, target_index, :].unsqueeze_(0)`` (:192-194): [1,1,1,S] for a tensor index, [1,1,S] for an int;
+        [B,S] for a batch."""
+        B, S, Q = self.model._shape
+        dev = self.model.device
         tq = torch.as_tensor(target_index, device=dev).reshape(B).long()
-        picked = self.R_q_i[torch.arange(B, device=dev), tq]                        # [B, S]
-        if B == 1:                                                                   # reference return shapes (:192-194)
-            self.R_q_i = self.R_q_i                                                  # [1, Q, S] like unsqueeze_(0)
+        picked = self.R_q_i[torch.arange(B, device=dev), tq].contiguous()
+        if B == 1:
             return picked.view(1, 1, 1, S) if isinstance(target_index, torch.Tensor) else picked.view(1, 1, S)
         return picked
+
+    # ---- baselines sharing the API (SURVEY.md §8f-2); the LRP ones need relprop and are not implemented
+    def generate_raw_attn(self, img, target_index):
+        """Head-mean of the last decoder layer's cross-attention (DETR/modules/ExplanationGenerator.py:224-236)."""
+        src, pos = img
+        m = self.model
+        m.forward_backward(src, pos, target_index, backward=False)
+        self.B = m._shape[0]
+        self.R_q_i = rules.head_mean_record(m.decoder[-1].multihead_attn["rec"], self.B)
+        return self._pick(target_index)
+
+    def generate_rollout(self, img, target_index):
+        """Attention rollout (DETR/modules/ExplanationGenerator.py:238-273): rollout of the encoder and decoder
+        self-attentions, combined through the last cross-attention as R_qq^T (A_qi R_ii)."""
+        src, pos = img
+        m = self.model
+        m.forward_backward(src, pos, target_index, backward=False)
+        self.B = B = m._shape[0]
+        cams_image = [rules.head_mean_record(blk.self_attn["rec"], B) for blk in m.encoder]
+        cams_queries = [rules.head_mean_record(blk.self_attn["rec"], B) for blk in m.decoder]
+        self.R_i_i = rules.compute_rollout_attention(cams_image)
+        self.R_q_q = rules.compute_rollout_attention(cams_queries)
+        cam_q_i = rules.head_mean_record(m.decoder[-1].multihead_attn["rec"], B)
+        self.R_q_i, _, _ = rules.mm_update_batched(self.R_q_q, self.R_i_i, None, cam_q_i, apply_normalization=False,
+                                                   apply_self_in_rule_10=True)
+        return self._pick(target_index)
+
+    def generate_attn_gradcam(self, img, target_index, index=None):
+        """attn-GradCAM of the last cross-attention (DETR/modules/ExplanationGenerator.py:275-305)."""
+        src, pos = img
+        m = self.model
+        m.forward_backward(src, pos, target_index, index)
+        self.B = m._shape[0]
+        self.R_q_i = rules.gradcam_record(m.decoder[-1].multihead_attn["rec"], self.B)
+        return self._pick(target_index)
+
+    def generate_partial_lrp(self, img, target_index, index=None):
+        raise NotImplementedError("partial LRP needs the relprop sweep (DETR/modules/layers.py:770-801): outside the hot-path scope")
+
+    def generate_transformer_att(self, img, target_index, index=None):
+        raise NotImplementedError("transformer attribution needs the relprop sweep: outside the hot-path scope")

@@ -106,7 +106,7 @@ class LxmertEngine:
         return tape.layernorm(tape.add(tape.linear(tape.linear(x, f.fc1, ACT_GELU), f.fc2), x), *f.ln, EPS)
 
     def forward_backward(self, input_ids, visual_feats, visual_pos, index=None, attention_mask=None,
-                         visual_attention_mask=None):
+                         visual_attention_mask=None, backward: bool = True):
         """Forward staging every A (29 attention maps for the base model), one-hot on the answer logit, backward
         staging every dA.  input_ids [B,T] int, visual_feats [B,I,F], visual_pos [B,I,4]."""
         dev, l = self.device, lib()
@@ -149,6 +149,9 @@ class LxmertEngine:
             h = tape.layernorm(tape.linear(pooled, self.head0, ACT_GELU), *self.head_ln, EPS)
             logits = tape.linear(h, self.head3)
             self.question_answering_score = logits.v
+            self._shape = (B, T, I)
+            if not backward:
+                return self.question_answering_score
             idx = logits.v.argmax(-1) if index is None else torch.as_tensor(index, device=dev).reshape(B).long()
             one_hot = torch.zeros_like(logits.v)
             one_hot[torch.arange(B, device=dev), idx] = 1.0                     # ExplanationGenerator.py:152-160
@@ -222,3 +225,64 @@ class GeneratorOurs:
         if B == 1:
             self.R_t_t, self.R_t_i, self.R_i_i, self.R_i_t = self.R_t_t[0], self.R_t_i[0], self.R_i_i[0], self.R_i_t[0]
         return self.R_t_t, self.R_t_i
+
+
+class GeneratorBaselines:
+    """lxmert/lxmert/src/ExplanationGenerator.py:368-666: raw attention, attn-GradCAM and rollout (the LRP based
+    ``generate_transformer_attr`` / ``generate_partial_lrp`` need relprop and raise)."""
+
+    def __init__(self, model_usage: LxmertEngine, save_visualization=False):
+        if not isinstance(model_usage, LxmertEngine):
+            raise MmxError("model_usage must be a mmx_b200.LxmertEngine")
+        self.model_usage = model_usage
+        self.save_visualization = save_visualization
+
+    def _finish(self):
+        self.R_t_t[:, 0, 0] = 0                                                    # "disregard the [CLS] token itself"
+        if self.R_t_t.shape[0] == 1:
+            self.R_t_t, self.R_t_i = self.R_t_t[0], self.R_t_i[0]
+        return self.R_t_t, self.R_t_i
+
+    def generate_raw_attn(self, input, method_name="raw_attention"):               # EG:508-540
+        m = self.model_usage
+        m.forward_backward(*input, backward=False)
+        B = m._shape[0]
+        blk = m.x_layers[-1]
+        self.R_t_i = rules.head_mean_record(blk.cross.recs[0], B).contiguous()
+        self.R_t_t = rules.head_mean_record(blk.lang_self.recs[0], B).contiguous()
+        return self._finish()
+
+    def generate_attn_gradcam(self, input, index=None, method_name="gradcam"):     # EG:549-593
+        m = self.model_usage
+        m.forward_backward(*input, index=index)
+        B = m._shape[0]
+        blk = m.x_layers[-1]
+        self.R_t_i = rules.gradcam_record(blk.cross.recs[0], B)
+        self.R_t_t = rules.gradcam_record(blk.lang_self.recs[0], B)
+        return self._finish()
+
+    def generate_rollout(self, input, method_name="rollout"):                      # EG:595-666
+        m = self.model_usage
+        m.forward_backward(*input, backward=False)
+        B = m._shape[0]
+        hm = lambda rec: rules.head_mean_record(rec, B)
+        cams_text = [hm(b.att.recs[0]) for b in m.layer]
+        cams_image = [hm(b.att.recs[0]) for b in m.r_layers]
+        for b in m.x_layers[:-1]:
+            cams_text.append(hm(b.lang_self.recs[0]))
+            cams_image.append(hm(b.visn_self.recs[0]))
+        last = m.x_layers[-1]
+        cam_t_i = hm(last.cross.recs[0])
+        R_t_t = rules.compute_rollout_attention(cams_text)
+        self.R_i_i = rules.compute_rollout_attention(cams_image)
+        self.R_t_i, _, _ = rules.mm_update_batched(R_t_t, self.R_i_i, None, cam_t_i, apply_normalization=False,
+                                                   apply_self_in_rule_10=True)
+        cams_text.append(hm(last.lang_self.recs[0]))
+        self.R_t_t = rules.compute_rollout_attention(cams_text)
+        return self._finish()
+
+    def generate_transformer_attr(self, input, index=None, method_name="transformer_attr"):
+        raise NotImplementedError("transformer attribution needs the relprop sweep (lxmert_lrp.py:422-461): outside the hot-path scope")
+
+    def generate_partial_lrp(self, input, index=None, method_name="partial_lrp"):
+        raise NotImplementedError("partial LRP needs the relprop sweep: outside the hot-path scope")

@@ -190,3 +190,28 @@ def mm_update_batched(R_ss, R_qq, R_qs, cam_sq, apply_normalization=True, apply_
     check(l.mmx_mm_update(ptr(Rs), T, ptr(Rq), S, ptr(Rqs), T, ptr(Ab), S, ptr(sq_add), S, ptr(ss_add), T, B, T, S, flags,
                           ptr(ws), ptr(md), current_stream()))
     return sq_add, ss_add, md
+
+
+def head_mean_record(rec, batch: int) -> torch.Tensor:
+    """mean over heads of the staged A (raw-attention / rollout baselines: ``cam.mean(dim=0)``,
+    DETR/modules/ExplanationGenerator.py:229-230,247-249).  A >= 0, so it is rule 5 with a gradient of ones."""
+    A, _, ld = rec.padded()
+    B, H, T = A.shape[0], A.shape[1], A.shape[2]
+    assert B == batch
+    ones = torch.ones_like(A)
+    out = torch.empty(B, T, ld, device=A.device, dtype=torch.float32)
+    check(lib().mmx_avg_heads(ptr(A), ptr(ones), ptr(out), B, H, T, ld, ld, ld, current_stream()))
+    return out[..., :rec.S]
+
+
+def gradcam_record(rec, batch: int) -> torch.Tensor:
+    """attn-GradCAM of one attention module (``gradcam``, DETR/modules/ExplanationGenerator.py:275-280)."""
+    A, dA, ld = rec.padded()
+    if dA is None:
+        raise MmxError("no attention gradient recorded (backward did not reach this attention)")
+    B, H, T = A.shape[0], A.shape[1], A.shape[2]
+    assert B == batch
+    out = torch.empty(B, T, rec.S, device=A.device, dtype=torch.float32)
+    gbar = torch.empty(B * H, device=A.device, dtype=torch.float32)
+    check(lib().mmx_attn_gradcam(ptr(A), ptr(dA), ptr(out), ptr(gbar), B, H, T, rec.S, ld, rec.S, current_stream()))
+    return out
