@@ -259,8 +259,8 @@ def main():
     roofline = {"kernel": "transformer GEMMs (" + {0: "fp32 FFMA", 1: "tcgen05 3xTF32, 1 CTA/tile", 2: "tcgen05 3xTF32, cta_group::2"}[gemm_backend] + ")",
                 "bound": "tensor", "achieved": gemm_tflops, "peak": tf_sust, "unit": "TFLOP/s",
                 "frac": gemm_tflops / tf_sust, "traffic": None,
-                "traffic_captured": {"launch": "M=3200 N=2304 K=768 (vision QKV)", "dram_bytes": 17334016,
-                                     "algorithmic_bytes": 16908288, "source": "profiles/gemm_tc_r1_v6_ncu.txt"},
+                "traffic_captured": {"launch": "M=3200 N=2304 K=768 (vision QKV)", "dram_bytes": 17351168,
+                                     "algorithmic_bytes": 16908288, "source": "profiles/gemm_tc_r1_final_ncu.txt"},
                 "peak_source": peak_src + " bf16 dense, sustained",
                 "launches_per_step": nl.value // prof_steps, "gemm_ms_per_step": tms.value / prof_steps,
                 "flops_per_step": tfl.value / prof_steps,
