@@ -1,0 +1,46 @@
+"""Small end-to-end exercise of every kernel family for `compute-sanitizer --tool memcheck` (run on the GPU box):
+   compute-sanitizer --tool memcheck --error-exitcode 3 python profiles/sanitize_run.py"""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mmx_b200
+from mmx_b200._lib import lib, check, ptr, current_stream
+from oracle import clip_oracle as co, detr_oracle as do, lxmert_oracle as lo, vit_oracle as vo
+
+l = lib()
+# CLIP (fp32 FFMA GEMMs at this size), both start modes, ragged text
+cfg = co.SMALL
+sd = co.init_state_dict(cfg, seed=3)
+images, tokens = co.synthetic_inputs(cfg, 4, seed=5)
+eng = mmx_b200.ClipEngine(mmx_b200.ClipConfig(*cfg.ref_args()), sd, max_batch=3, device="cuda:0")   # micro-batched 3+1
+for sl in (-1, 0):
+    mmx_b200.interpret(images.cuda(), tokens.cuda(), eng, "cuda:0", sl, sl)
+# tcgen05 GEMM with ragged edges in M, N, K + every epilogue input
+M, N, K = 300, 260, 200
+A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda"); b = torch.randn(N, device="cuda")
+res = torch.randn(M, N, device="cuda"); C = torch.empty(M, N, device="cuda"); Ca = torch.empty(M, N, device="cuda")
+for backend in (1, 2):
+    if l.mmx_set_gemm_backend(backend) == backend:
+        check(l.mmx_linear(ptr(A), K, ptr(W), K, ptr(b), ptr(res), N, ptr(C), N, ptr(Ca), 2, M, N, K, current_stream()))
+l.mmx_set_gemm_backend(1)
+# tensor-core rule update (S >= 128) and the FFMA one
+for S in (197, 50):
+    R = torch.eye(S, device="cuda").repeat(2, 1, 1); Ab = torch.rand(2, S, S, device="cuda") * 0.01
+    mmx_b200.self_update(R, Ab)
+# DETR / LXMERT / ViT generators on tiny configs
+dcfg = do.DETR_TINY
+src, pos, tq = do.synthetic_inputs(dcfg, 2, 3, 4, seed=1)
+g = mmx_b200.Generator(mmx_b200.DetrEngine(do.init_state_dict(dcfg, 5), nhead=dcfg.nhead, device="cuda:0"))
+g.generate_ours((src.cuda(), pos.cuda()), tq, use_lrp=False); g.generate_rollout((src.cuda(), pos.cuda()), tq)
+g.generate_attn_gradcam((src.cuda(), pos.cuda()), tq)
+lcfg = lo.LXMERT_TINY
+ids, feats, boxes = lo.synthetic_inputs(lcfg, 2, 6, 5, seed=2)
+le = mmx_b200.LxmertEngine(lo.init_state_dict(lcfg, 3), num_heads=lcfg.heads, device="cuda:0")
+mmx_b200.GeneratorOurs(le).generate_ours((ids.cuda(), feats.cuda(), boxes.cuda()), use_lrp=False)
+mmx_b200.GeneratorBaselines(le).generate_rollout((ids.cuda(), feats.cuda(), boxes.cuda()))
+vcfg = vo.VIT_TINY
+ve = mmx_b200.ViTEngine(vo.init_state_dict(vcfg, 3), heads=vcfg.heads, device="cuda:0")
+mmx_b200.generate_relevance(ve, torch.randn(2, 3, vcfg.image, vcfg.image).cuda())
+torch.cuda.synchronize()
+print("sanitize_run: all kernels executed")

@@ -3,6 +3,7 @@
 #include "mmx_common.cuh"
 #include "gemm.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace mmx {
 
@@ -316,7 +317,23 @@ int avg_heads(const float* A, const float* dA, float* Abar, int B, int H, int T,
   if (ld_in == S && ld_out == S && (P % 4) == 0 && aligned16(A) && aligned16(dA) && aligned16(Abar)) {
     const int PV = (int)(P / 4);
     const long long items = (long long)B * PV;
-    avg_heads_vec4_kernel<4><<<grid_for(items), 256, 0, st>>>(A, dA, Abar, items, PV, H, inv_h);
+    // heads in flight per thread (2 x UNROLL 128-bit loads) and CTAs per SM: tuned on B200 (profiles/rule5_sweep_r1.md)
+    static int unroll = -1, per_sm = -1;
+    if (unroll < 0) {
+      const char* e = getenv("MMX_AVG_UNROLL");
+      unroll = e ? atoi(e) : 8;
+      e = getenv("MMX_AVG_CTAS_PER_SM");
+      per_sm = e ? atoi(e) : 16;
+    }
+    long long g = (items + 255) / 256, cap = (long long)sm_count() * per_sm;
+    const int grid = (int)(g > cap ? cap : g);
+    switch (unroll) {
+      case 2: avg_heads_vec4_kernel<2><<<grid, 256, 0, st>>>(A, dA, Abar, items, PV, H, inv_h); break;
+      case 6: avg_heads_vec4_kernel<6><<<grid, 256, 0, st>>>(A, dA, Abar, items, PV, H, inv_h); break;
+      case 8: avg_heads_vec4_kernel<8><<<grid, 256, 0, st>>>(A, dA, Abar, items, PV, H, inv_h); break;
+      case 12: avg_heads_vec4_kernel<12><<<grid, 256, 0, st>>>(A, dA, Abar, items, PV, H, inv_h); break;
+      default: avg_heads_vec4_kernel<4><<<grid, 256, 0, st>>>(A, dA, Abar, items, PV, H, inv_h); break;
+    }
   } else {
     avg_heads_scalar_kernel<<<grid_for((long long)B * T * S), 256, 0, st>>>(A, dA, Abar, B, H, T, S, ld_in, ld_out, inv_h);
   }
