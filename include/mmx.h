@@ -36,6 +36,10 @@ uint64_t mmx_launch_count(void);
  * slower in round 1 - see profiles/gemm_ablation_r1.md).  Env MMX_GEMM_BACKEND overrides the default.  Returns the
  * backend in effect. */
 int mmx_set_gemm_backend(int backend);
+/* Tile width of the tcgen05 backend: 0 = automatic (the width in {128, 144, 160} whose tile count best fills whole
+ * waves of SMs), or one of 128 / 144 / 160 to force it (profiling and the bit-equality test: the width never changes a
+ * result bit).  Env MMX_TC_BN sets the initial value.  Returns the value in effect. */
+int mmx_set_gemm_tile_n(int bn);
 /* Per-launch CUDA-event timing of the transformer GEMMs (the dominant kernel): enable=1 opens a window, enable=0
  * closes it; the report synchronises the device and returns the summed launch durations, the algorithmic FLOPs
  * (2*M*N*K per launch) and the launch count of the window.  Used by bench.py for the roofline line. */

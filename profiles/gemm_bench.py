@@ -12,21 +12,23 @@ import mmx_b200  # noqa: E402
 from mmx_b200._lib import lib, check, ptr, current_stream  # noqa: E402
 
 SHAPES = [(3200, 2304, 768), (3200, 768, 768), (3200, 3072, 768), (3200, 768, 3072),
-          (4928, 1536, 512), (4928, 512, 512), (4928, 2048, 512), (4928, 512, 2048), (3136, 768, 3072)]
+          (4928, 1536, 512), (4928, 512, 512), (4928, 2048, 512), (4928, 512, 2048), (3136, 768, 3072), (3200, 768, 2304)]
 
 
 def main():
     l = lib()
     out = []
     global SHAPES
-    backends = (0, 1, 2)
+    backends = (1,) if "--tiles" in sys.argv else (0, 1, 2)
     if "--only" in sys.argv:            # e.g. --only 3200,2304,768  (tcgen05 backend only; for ncu captures)
         SHAPES = [tuple(int(v) for v in sys.argv[sys.argv.index("--only") + 1].split(","))]
         backends = (int(sys.argv[sys.argv.index('--backend') + 1]),) if '--backend' in sys.argv else (2,)
     for backend in backends:
         if l.mmx_set_gemm_backend(backend) != backend:
             continue
-        for M, N, K in SHAPES:
+        widths = (128, 144, 160, 0) if (backend == 1 and "--tiles" in sys.argv) else (0,)    # 0 = automatic tile width
+        for (M, N, K), bn in [(sh, w) for sh in SHAPES for w in widths]:
+            l.mmx_set_gemm_tile_n(bn)
             g = torch.Generator(device="cuda").manual_seed(1)
             A = torch.randn(M, K, device="cuda", generator=g)
             W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
@@ -45,9 +47,10 @@ def main():
             ms = e0.elapsed_time(e1) / reps
             ref = (A[:256].double() @ W.double().t() + bias.double())
             err = ((Cm[:256].double() - ref).abs().max() / ref.abs().max()).item()
-            out.append(dict(backend=backend, M=M, N=N, K=K, us=ms * 1e3, tflops=2.0 * M * N * K / (ms * 1e-3) / 1e12, rel_err=err))
+            out.append(dict(backend=backend, tile_n=bn, M=M, N=N, K=K, us=ms * 1e3, tflops=2.0 * M * N * K / (ms * 1e-3) / 1e12, rel_err=err))
             print(out[-1], flush=True)
     l.mmx_set_gemm_backend(1)
+    l.mmx_set_gemm_tile_n(0)
     print(json.dumps(out))
 
 

@@ -67,6 +67,36 @@ def test_linear_and_dgrad(L, backend, M, N, K):
         lib.mmx_set_gemm_backend(1)
 
 
+@pytest.mark.parametrize("M,N,K", [(3200, 768, 768), (3200, 2304, 768), (300, 260, 200), (129, 1000, 3072), (1, 132, 68)])
+def test_tile_width_never_changes_a_bit(L, M, N, K):
+    """The tcgen05 kernel picks its tile width (128 / 144 / 160 columns) from the tile count; each output element
+    still sums its K products in the same order, so all three widths must agree bit for bit (batch invariance and
+    sharded == single-GPU rest on this) and match fp64 to the 3xTF32 tolerance."""
+    lib, check, ptr, st = L["lib"], L["check"], L["ptr"], L["st"]
+    if lib.mmx_set_gemm_backend(1) != 1:
+        pytest.skip("tcgen05 backend not available")
+    try:
+        gen = torch.Generator().manual_seed(7 * M + N + K)
+        A = torch.randn(M, K, generator=gen)
+        W = torch.randn(N, K, generator=gen) / math.sqrt(K)
+        bias, res = torch.randn(N, generator=gen), torch.randn(M, N, generator=gen)
+        Ad, Wd, bd, rd = A.cuda(), W.cuda(), bias.cuda(), res.cuda()
+        outs = {}
+        for bn in (128, 144, 160, 0):
+            assert lib.mmx_set_gemm_tile_n(bn) == bn
+            Cd = torch.full((M, N), float("nan"), device="cuda")
+            Ca = torch.full((M, N), float("nan"), device="cuda")
+            check(lib.mmx_linear(ptr(Ad), K, ptr(Wd), K, ptr(bd), ptr(rd), N, ptr(Cd), N, ptr(Ca), 2, M, N, K, st()))
+            outs[bn] = (Cd.cpu(), Ca.cpu())
+        ref = A.double() @ W.double().t() + bias.double() + res.double()
+        assert rel_err(outs[128][0], ref) < 2e-5
+        for bn in (144, 160, 0):
+            assert torch.equal(outs[bn][0], outs[128][0]), bn
+            assert torch.equal(outs[bn][1], outs[128][1]), bn
+    finally:
+        lib.mmx_set_gemm_tile_n(0)
+
+
 @pytest.mark.parametrize("rows,D", [(3200, 768), (77, 512), (5, 32), (3, 1024), (9, 100)])
 def test_layernorm_fwd_bwd(L, rows, D):
     lib, check, ptr, st = L["lib"], L["check"], L["ptr"], L["st"]
@@ -145,17 +175,23 @@ def test_attention_fwd_bwd(L, B, H, T, S, hd, causal, bias, ss):
                                 B, H, T, S, hd, C.c_float(scale), flags, st()))
     q64, k64, v64 = (t.double().requires_grad_(True) for t in (q, k, v))
     Ar, Or = _attn_ref(q64, k64, v64, H, scale, causal, kb.double() if bias else None, ss)
-    assert rel_err(A[..., :S], Ar.detach()) < 2e-6
+    # the products run as 3xTF32 tensor-core passes (same budget as the linear GEMMs), softmax in fp32
+    errs = {"A": rel_err(A[..., :S], Ar.detach())}
+    assert errs["A"] < 5e-6
     assert (A[..., S:] == 0).all()                       # padded columns are zero-filled (rule 5 relies on it)
-    assert rel_err(O, Or.detach()) < 2e-6
+    errs["O"] = rel_err(O, Or.detach())
+    assert errs["O"] < 5e-6
     Or.backward(dO.double())
     dA = torch.full((B, H, T, ldA), 7.0, device="cuda"); delta = torch.empty(B, H, T, device="cuda")
     dq, dk, dv = (torch.empty_like(t) for t in (qd, kd, vd))
     check(lib.mmx_attention_bwd(ptr(dOd), Dm, ptr(qd), Dm, ptr(kd), Dm, ptr(vd), Dm, ptr(A), ptr(dA), ldA, ptr(delta),
                                 ptr(dq), Dm, ptr(dk), Dm, ptr(dv), Dm, B, H, T, S, hd, C.c_float(scale), flags, st()))
-    assert rel_err(dA[..., :S], Ar.grad) < 2e-6          # the tensor the reference's backward hook captures
+    errs["dA"] = rel_err(dA[..., :S], Ar.grad)         # the tensor the reference's backward hook captures
+    assert errs["dA"] < 5e-6
     assert (dA[..., S:] == 0).all()
-    assert rel_err(dq, q64.grad) < 5e-6 and rel_err(dk, k64.grad) < 5e-6 and rel_err(dv, v64.grad) < 5e-6
+    errs.update(dq=rel_err(dq, q64.grad), dk=rel_err(dk, k64.grad), dv=rel_err(dv, v64.grad))
+    print("attention errors", (B, H, T, S, hd), {k_: f"{v_:.1e}" for k_, v_ in errs.items()})
+    assert max(errs["dq"], errs["dk"], errs["dv"]) < 1e-5
     # stop-after-dA form (last relevant block)
     dA2 = torch.empty_like(dA)
     check(lib.mmx_attention_bwd(ptr(dOd), Dm, ptr(qd), Dm, ptr(kd), Dm, ptr(vd), Dm, ptr(A), ptr(dA2), ldA, None,

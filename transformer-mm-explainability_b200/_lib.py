@@ -27,6 +27,7 @@ _SIGS = {
     "mmx_version": (C.c_int, []),
     "mmx_launch_count": (C.c_uint64, []),
     "mmx_set_gemm_backend": (C.c_int, [C.c_int]),
+    "mmx_set_gemm_tile_n": (C.c_int, [C.c_int]),
     "mmx_profile_gemm": (C.c_int, [C.c_int]),
     "mmx_profile_gemm_report": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "mmx_gemm_trace": (C.c_int, [C.c_void_p]),

@@ -1,6 +1,6 @@
 // Attention forward that stages A = softmax(QK^T) to HBM, and the attention backward that stages dA = dO V^T
 // (the two tensors the reference captures with forward / backward hooks) and continues to dQ, dK, dV.
-// fp32 FFMA; one CTA = one (batch, head, 32-query tile); score rows live in shared memory so any S <= ~1500
+// 3xTF32 mma.sync products with fp32 softmax; one CTA = one (batch, head, 32-query tile); score rows live in shared memory so any S <= ~1500
 // (DETR 850, ViT-L/14@336 577) is handled without a second pass.  Deterministic (no atomics): dK/dV come from a
 // second kernel that walks the query tiles for one key tile.
 #include "mmx_common.cuh"
@@ -15,113 +15,180 @@ struct Ragged {
   const int* lens = nullptr;
 };
 
-constexpr int TQ = 32;    // query rows per CTA
+constexpr int TQ = 32;    // query rows per CTA (two m16 row blocks)
 constexpr int TKEY = 64;  // keys per shared-memory tile
 constexpr int ATT_THREADS = 128;
 
+// The three small matrix products per head (scores, P.V and their backward twins) run on the tensor cores as
+// mma.sync.m16n8k8 TF32 with the same fp32-faithful 3-pass split as the linear GEMMs (gemm_tcgen05.cu): x = hi + lo,
+// hi*hi into one accumulator, lo*hi + hi*lo into a second one that is added once at the end.  tcgen05 / TMEM is the
+// wrong tool here: a head is 50x50x64 (or 77x77x64), far below one 128-row UMMA tile, and the kernels are bound by
+// instruction issue and the staged A / dA traffic, not by math.  The FFMA version of these loops issued 3x the
+// instructions and 5x the shared-memory wavefronts (profiles/attn_r1.md).
+//
+// Fragment layout of m16n8k8 (g = lane / 4, t = lane % 4):
+//   A (16x8, row)  a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
+//   B ( 8x8, col)  b0 (k=t, n=g)  b1 (k=t+4, n=g)
+//   C (16x8)       c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+// Shared-memory strides are chosen so that each fragment load hits 32 different banks: operands indexed
+// [row or n = g][k = t] use a stride = 4 (mod 8) floats, operands indexed [k = t][n = g] a stride = 8 (mod 16).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+struct FragA { uint32_t hi[4], lo[4]; };
+struct FragB { uint32_t hi[2], lo[2]; };
+// A fragment of a [row][k] operand (stride ld): p points at (row0 + g, k0 + t)
+__device__ __forceinline__ FragA frag_a_rowmajor(const float* p, int ld) {
+  FragA f;
+  split_tf32(p[0], f.hi[0], f.lo[0]);
+  split_tf32(p[8 * ld], f.hi[1], f.lo[1]);
+  split_tf32(p[4], f.hi[2], f.lo[2]);
+  split_tf32(p[8 * ld + 4], f.hi[3], f.lo[3]);
+  return f;
+}
+// A fragment of a TRANSPOSED operand stored [k][row] (stride ld): p points at (k0 + t, row0 + g)
+__device__ __forceinline__ FragA frag_a_kmajor(const float* p, int ld) {
+  FragA f;
+  split_tf32(p[0], f.hi[0], f.lo[0]);
+  split_tf32(p[8], f.hi[1], f.lo[1]);
+  split_tf32(p[4 * ld], f.hi[2], f.lo[2]);
+  split_tf32(p[4 * ld + 8], f.hi[3], f.lo[3]);
+  return f;
+}
+// B fragment of an operand stored [n][k] (stride ld): p points at (n0 + g, k0 + t)
+__device__ __forceinline__ FragB frag_b_nmajor(const float* p) {
+  FragB f;
+  split_tf32(p[0], f.hi[0], f.lo[0]);
+  split_tf32(p[4], f.hi[1], f.lo[1]);
+  return f;
+}
+// B fragment of an operand stored [k][n] (stride ld): p points at (k0 + t, n0 + g)
+__device__ __forceinline__ FragB frag_b_kmajor(const float* p, int ld) {
+  FragB f;
+  split_tf32(p[0], f.hi[0], f.lo[0]);
+  split_tf32(p[4 * ld], f.hi[1], f.lo[1]);
+  return f;
+}
+__device__ __forceinline__ void mma3(float (&main)[4], float (&cross)[4], const FragA& a, const FragB& b) {
+  mma_tf32(cross, a.lo, b.hi);
+  mma_tf32(cross, a.hi, b.lo);
+  mma_tf32(main, a.hi, b.hi);
+}
+
+__host__ __device__ inline int score_ld(int S) { return round_up(S, 8) + 4; }   // smem stride of a score row: = 4 (mod 8)
+
 template <int HD>
 struct AttnSmem {
-  static constexpr int LDH = HD + 4;
-  static size_t bytes(int S_pad) { return sizeof(float) * ((size_t)TQ * S_pad + (size_t)TQ * LDH + (size_t)TKEY * LDH); }
+  static constexpr int LDX = HD + 4;   // [row / key][d] operands (Q, dO tiles; K, V as the scores' B operand)
+  static constexpr int LDV = HD + 8;   // [key][d] operand of the P.V product
+  static size_t bytes(int S) { return sizeof(float) * ((size_t)TQ * score_ld(S) + (size_t)TQ * LDX + (size_t)TKEY * LDV); }
 };
 
-// Shared-memory operand rows are HD + 4 floats: 16-byte aligned for 128-bit reads, and 8 consecutive rows start in 8
-// different 4-bank groups, so a quarter-warp's LDS.128 is conflict-free.
-//
-// scores[i][j] (i in tile, j in [0,S)) = sum_d X[i][d] * Y[j][d];  X rows already in sX, Y streamed through sY.
+// rows j0 .. j0+TKEY-1 of Y (zero beyond S) -> sY with row stride ld
+template <int HD>
+__device__ __forceinline__ void load_key_tile(const float* __restrict__ Y, int ldy, long long ybase, int j0, int S, float* sY,
+                                              int ld) {
+  for (int e = threadIdx.x; e < TKEY * (HD / 4); e += ATT_THREADS) {
+    const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j0 + r < S) v = *reinterpret_cast<const float4*>(Y + ybase + (long long)(j0 + r) * ldy + d);
+    *reinterpret_cast<float4*>(sY + r * ld + d) = v;
+  }
+}
+
+// scores[i][j] (i in the 32-row tile, j in [0,S)) = post_scale * sum_d X[i][d] * Y[j][d];  X rows already in sX, Y
+// streamed through sY.  Warp w owns row block w&1 and the 32-key half w>>1 of each key tile.
 template <int HD>
 __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy, long long ybase, int S,
-                                            const float* sX, float* sY, float* sP, int S_pad, float post_scale) {
-  constexpr int LDH = HD + 4;
-  const int tid = threadIdx.x, ri = tid >> 4, cj = tid & 15;
+                                            const float* sX, float* sY, float* sP, int ldP, float post_scale) {
+  constexpr int LDX = AttnSmem<HD>::LDX;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp & 1) * 16, kh = (warp >> 1) * 32;
   for (int j0 = 0; j0 < S; j0 += TKEY) {
     __syncthreads();
-    for (int e = tid; e < TKEY * (HD / 4); e += ATT_THREADS) {
-      const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + r < S) v = *reinterpret_cast<const float4*>(Y + ybase + (long long)(j0 + r) * ldy + d);
-      *reinterpret_cast<float4*>(sY + r * LDH + d) = v;
-    }
+    load_key_tile<HD>(Y, ldy, ybase, j0, S, sY, LDX);
     __syncthreads();
-    float acc[4][4] = {};
-#pragma unroll 4
-    for (int d = 0; d < HD; d += 4) {
-      float4 x[4], y[4];
+    float acc[4][4] = {}, crs[4][4] = {};
+    const int ntiles = (S - j0 - kh + 7) >> 3;          // live 8-key blocks of this warp's half (may be <= 0)
+#pragma unroll 2
+    for (int k0 = 0; k0 < HD; k0 += 8) {
+      const FragA a = frag_a_rowmajor(sX + (m0 + g) * LDX + k0 + t, LDX);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        x[u] = *reinterpret_cast<const float4*>(sX + (ri * 4 + u) * LDH + d);
-        y[u] = *reinterpret_cast<const float4*>(sY + (cj + 16 * u) * LDH + d);
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          acc[a][c] = fmaf(x[a].x, y[c].x, acc[a][c]);
-          acc[a][c] = fmaf(x[a].y, y[c].y, acc[a][c]);
-          acc[a][c] = fmaf(x[a].z, y[c].z, acc[a][c]);
-          acc[a][c] = fmaf(x[a].w, y[c].w, acc[a][c]);
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt < ntiles) {
+          const FragB b = frag_b_nmajor(sY + (kh + nt * 8 + g) * LDX + k0 + t);
+          mma3(acc[nt], crs[nt], a, b);
         }
+      }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = j0 + cj + 16 * c;
-        if (j < S_pad) sP[(ri * 4 + a) * S_pad + j] = acc[a][c] * post_scale;
+    for (int nt = 0; nt < 4; ++nt) {
+      const int j = j0 + kh + nt * 8 + 2 * t;           // even; ldP is even
+      if (j < ldP) {
+        float* p0 = sP + (m0 + g) * ldP + j;
+        *reinterpret_cast<float2*>(p0) = make_float2((acc[nt][0] + crs[nt][0]) * post_scale, (acc[nt][1] + crs[nt][1]) * post_scale);
+        *reinterpret_cast<float2*>(p0 + 8 * ldP) =
+            make_float2((acc[nt][2] + crs[nt][2]) * post_scale, (acc[nt][3] + crs[nt][3]) * post_scale);
       }
+    }
   }
   __syncthreads();
 }
 
-// out[i][d] = sum_j sP[i][j] * Y[j][d];  thread (ri, cj) owns rows ri*4..+3 and the 4 contiguous columns d = 4*cj..
-// (threads with 4*cj >= HD idle for small head dims)
+// out[i][d] = sum_j sP[i][j] * Y[j][d].  Warp w owns row block w&1 and the d half w>>1; its HD/16 accumulator
+// fragments hold rows m0+g, m0+g+8 and columns d0 + 8*nt + 2t, +1.
 template <int HD>
 __device__ __forceinline__ void tile_pv(const float* __restrict__ Y, int ldy, long long ybase, int S, const float* sP,
-                                        int S_pad, float* sY, float4 (&out)[4]) {
-  constexpr int LDH = HD + 4;
-  const int tid = threadIdx.x, ri = tid >> 4, cj = tid & 15;
-  const bool active = cj * 4 < HD;
+                                        int ldP, float* sY, float (&out)[HD / 16][4]) {
+  constexpr int LDV = AttnSmem<HD>::LDV, NT = HD / 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp & 1) * 16, d0 = (warp >> 1) * (HD / 2);
+  float crs[NT][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) out[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[nt][c] = crs[nt][c] = 0.f;
   for (int j0 = 0; j0 < S; j0 += TKEY) {
     __syncthreads();
-    for (int e = tid; e < TKEY * (HD / 4); e += ATT_THREADS) {
-      const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + r < S) v = *reinterpret_cast<const float4*>(Y + ybase + (long long)(j0 + r) * ldy + d);
-      *reinterpret_cast<float4*>(sY + r * LDH + d) = v;
-    }
+    load_key_tile<HD>(Y, ldy, ybase, j0, S, sY, LDV);
     __syncthreads();
-    if (!active) continue;
-    const int jn = min(TKEY, S - j0);
-    int j = 0;
-    for (; j + 4 <= jn; j += 4) {                       // S_pad % 4 == 0 and j0 % 4 == 0: aligned float4 reads of P
-      float4 p[4], y[4];
+    const int jn = min(TKEY, S - j0);                   // keys jn .. round_up(jn, 8) are zero rows of sY, finite columns of sP
+#pragma unroll 2
+    for (int kk = 0; kk < jn; kk += 8) {
+      const FragA a = frag_a_rowmajor(sP + (m0 + g) * ldP + j0 + kk + t, ldP);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) p[a] = *reinterpret_cast<const float4*>(sP + (ri * 4 + a) * S_pad + j0 + j);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) y[u] = *reinterpret_cast<const float4*>(sY + (j + u) * LDH + cj * 4);
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float pa[4] = {p[a].x, p[a].y, p[a].z, p[a].w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          out[a].x = fmaf(pa[u], y[u].x, out[a].x);
-          out[a].y = fmaf(pa[u], y[u].y, out[a].y);
-          out[a].z = fmaf(pa[u], y[u].z, out[a].z);
-          out[a].w = fmaf(pa[u], y[u].w, out[a].w);
-        }
+      for (int nt = 0; nt < NT; ++nt) {
+        const FragB b = frag_b_kmajor(sY + (kk + t) * LDV + d0 + nt * 8 + g, LDV);
+        mma3(out[nt], crs[nt], a, b);
       }
     }
-    for (; j < jn; ++j) {
-      const float4 y = *reinterpret_cast<const float4*>(sY + j * LDH + cj * 4);
+  }
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float pa = sP[(ri * 4 + a) * S_pad + j0 + j];
-        out[a].x = fmaf(pa, y.x, out[a].x); out[a].y = fmaf(pa, y.y, out[a].y);
-        out[a].z = fmaf(pa, y.z, out[a].z); out[a].w = fmaf(pa, y.w, out[a].w);
-      }
-    }
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[nt][c] += crs[nt][c];
+}
+
+// stores the P.V fragments of tile_pv: rows i0 + m0 + g (+8), columns h*HD + d0 + 8*nt + 2t
+template <int HD>
+__device__ __forceinline__ void store_pv(float* __restrict__ O, int ldo, long long row0, int i0, int T, int h,
+                                         const float (&out)[HD / 16][4], float mul) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp & 1) * 16, d0 = (warp >> 1) * (HD / 2);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int i = i0 + m0 + g + 8 * half;
+    if (i >= T) continue;
+    float* orow = O + (row0 + i) * ldo + h * HD + d0 + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < HD / 16; ++nt)
+      *reinterpret_cast<float2*>(orow + nt * 8) = make_float2(out[nt][2 * half] * mul, out[nt][2 * half + 1] * mul);
   }
 }
 
@@ -130,9 +197,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
     const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
     const float* __restrict__ key_bias, float* __restrict__ A, int ldA, float* __restrict__ O, int ldo, int H, int T, int S,
     float scale, int flags, Ragged rg) {
-  constexpr int LDH = HD + 4;
+  constexpr int LDH = AttnSmem<HD>::LDX;
   extern __shared__ float smem[];
-  const int S_pad = ldA;  // score rows use the same padded width as the staged A rows
+  const int S_pad = score_ld(S);  // shared-memory stride of a score row (from the dense S, also for ragged samples)
   float* sP = smem;
   float* sQ = sP + (size_t)TQ * S_pad;
   float* sKV = sQ + TQ * LDH;
@@ -186,16 +253,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
     }
   }
   __syncthreads();
-  float4 out[4];
+  float out[HD / 16][4];
   tile_pv<HD>(V, ldv, krow0 * ldv + h * HD, S, sP, S_pad, sKV, out);
-  const int ri = tid >> 4, cj = tid & 15;
-  if (cj * 4 < HD) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int i = i0 + ri * 4 + a;
-      if (i < T) *reinterpret_cast<float4*>(O + (qrow0 + i) * ldo + h * HD + cj * 4) = out[a];
-    }
-  }
+  store_pv<HD>(O, ldo, qrow0, i0, T, h, out, 1.f);
 }
 
 // backward, query side: dA (staged), delta, dQ
@@ -204,9 +264,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
     const float* __restrict__ A, float* __restrict__ dA, int ldA, float* __restrict__ delta, float* __restrict__ dQ,
     int lddq, int H, int T, int S, float scale, Ragged rg) {
-  constexpr int LDH = HD + 4;
+  constexpr int LDH = AttnSmem<HD>::LDX;
   extern __shared__ float smem[];
-  const int S_pad = ldA;
+  const int S_pad = score_ld(S);
   float* sP = smem;
   float* sX = sP + (size_t)TQ * S_pad;
   float* sKV = sX + TQ * LDH;
@@ -251,19 +311,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
   }
   if (dQ == nullptr) return;
   __syncthreads();
-  float4 out[4];
+  float out[HD / 16][4];
   tile_pv<HD>(K, ldk, krow0 * ldk + h * HD, S, sP, S_pad, sKV, out);
-  const int ri = tid >> 4, cj = tid & 15;
-  if (cj * 4 < HD) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int i = i0 + ri * 4 + a;
-      if (i < T) {
-        const float4 v = make_float4(out[a].x * scale, out[a].y * scale, out[a].z * scale, out[a].w * scale);
-        *reinterpret_cast<float4*>(dQ + (qrow0 + i) * lddq + h * HD + cj * 4) = v;
-      }
-    }
-  }
+  store_pv<HD>(dQ, lddq, qrow0, i0, T, h, out, scale);
 }
 
 // backward, key side: one CTA = 32 keys of one (b,h); walks all query rows in tiles of 64.
@@ -274,22 +324,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ Q, int ldq, const float* __restrict__ A,
     const float* __restrict__ dA, int ldA, const float* __restrict__ delta, float* __restrict__ dK, int lddk,
     float* __restrict__ dV, int lddv, int H, int T, int S, float scale, Ragged rg) {
-  constexpr int LDH = HD + 4, LDK = KV_KEYS + 4;
+  constexpr int LDH = HD + 8, LDK = KV_KEYS + 8, NT = HD / 16;   // both are [k][n]-indexed operands: stride = 8 (mod 16)
   extern __shared__ float smem[];
   float* sdO = smem;
   float* sQ = sdO + KV_ROWS * LDH;
   float* sA = sQ + KV_ROWS * LDH;          // [KV_ROWS][LDK]  A[i][j]
   float* sS = sA + KV_ROWS * LDK;          // [KV_ROWS][LDK]  dS[i][j]
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * KV_KEYS;
-  const int tid = threadIdx.x, rj = tid >> 4, cj = tid & 15;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp & 1) * 16, d0 = (warp >> 1) * (HD / 2);   // this warp's 16 keys and d half
   const int Tm = T;
   long long qrow0 = (long long)b * T, krow0 = (long long)b * S;
   if (rg.lens) { T = S = rg.lens[b]; qrow0 = krow0 = rg.offs[b]; }
   if (j0 >= S) return;
-  const bool active = cj * 4 < HD;
-  float4 accV[4], accK[4];
-#pragma unroll
-  for (int x = 0; x < 4; ++x) accV[x] = accK[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float accV[NT][4] = {}, crsV[NT][4] = {}, accK[NT][4] = {}, crsK[NT][4] = {};
   const long long plane = ((long long)b * H + h) * Tm;
   for (int i0 = 0; i0 < T; i0 += KV_ROWS) {
     __syncthreads();
@@ -315,31 +363,33 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
       *reinterpret_cast<float4*>(sQ + r * LDH + d) = vq;
     }
     __syncthreads();
-    if (!active) continue;
-    const int in = min(KV_ROWS, T - i0);
-    for (int i = 0; i < in; ++i) {
-      const float4 a = *reinterpret_cast<const float4*>(sA + i * LDK + rj * 4);
-      const float4 sv = *reinterpret_cast<const float4*>(sS + i * LDK + rj * 4);
-      const float4 o = *reinterpret_cast<const float4*>(sdO + i * LDH + cj * 4);
-      const float4 q = *reinterpret_cast<const float4*>(sQ + i * LDH + cj * 4);
-      const float av[4] = {a.x, a.y, a.z, a.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
+    const int in = min(KV_ROWS, T - i0);                // rows in .. round_up(in, 8) are zero-filled
+#pragma unroll 2
+    for (int kk = 0; kk < in; kk += 8) {
+      const FragA aA = frag_a_kmajor(sA + (kk + t) * LDK + m0 + g, LDK);
+      const FragA aS = frag_a_kmajor(sS + (kk + t) * LDK + m0 + g, LDK);
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        accV[x].x = fmaf(av[x], o.x, accV[x].x); accV[x].y = fmaf(av[x], o.y, accV[x].y);
-        accV[x].z = fmaf(av[x], o.z, accV[x].z); accV[x].w = fmaf(av[x], o.w, accV[x].w);
-        accK[x].x = fmaf(ss[x], q.x, accK[x].x); accK[x].y = fmaf(ss[x], q.y, accK[x].y);
-        accK[x].z = fmaf(ss[x], q.z, accK[x].z); accK[x].w = fmaf(ss[x], q.w, accK[x].w);
+      for (int nt = 0; nt < NT; ++nt) {
+        const FragB bo = frag_b_kmajor(sdO + (kk + t) * LDH + d0 + nt * 8 + g, LDH);
+        mma3(accV[nt], crsV[nt], aA, bo);
+        const FragB bq = frag_b_kmajor(sQ + (kk + t) * LDH + d0 + nt * 8 + g, LDH);
+        mma3(accK[nt], crsK[nt], aS, bq);
       }
     }
   }
-  if (!active) return;
 #pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int j = j0 + rj * 4 + x;
+  for (int half = 0; half < 2; ++half) {
+    const int j = j0 + m0 + g + 8 * half;
     if (j >= S) continue;
-    *reinterpret_cast<float4*>(dV + (krow0 + j) * lddv + h * HD + cj * 4) = accV[x];
-    const float4 kk = make_float4(accK[x].x * scale, accK[x].y * scale, accK[x].z * scale, accK[x].w * scale);
-    *reinterpret_cast<float4*>(dK + (krow0 + j) * lddk + h * HD + cj * 4) = kk;
+    float* vrow = dV + (krow0 + j) * lddv + h * HD + d0 + 2 * t;
+    float* krow = dK + (krow0 + j) * lddk + h * HD + d0 + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      *reinterpret_cast<float2*>(vrow + nt * 8) =
+          make_float2(accV[nt][2 * half] + crsV[nt][2 * half], accV[nt][2 * half + 1] + crsV[nt][2 * half + 1]);
+      *reinterpret_cast<float2*>(krow + nt * 8) = make_float2((accK[nt][2 * half] + crsK[nt][2 * half]) * scale,
+                                                              (accK[nt][2 * half + 1] + crsK[nt][2 * half + 1]) * scale);
+    }
   }
 }
 
@@ -347,7 +397,7 @@ template <int HD>
 static int launch_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const float* key_bias,
                       float* A, int ldA, float* O, int ldo, int B, int H, int T, int S, float scale, int flags,
                       Ragged rg, cudaStream_t st) {
-  const size_t smem = AttnSmem<HD>::bytes(ldA);
+  const size_t smem = AttnSmem<HD>::bytes(S);
   MMX_REQUIRE(smem <= 227 * 1024, "sequence too long for the single-pass attention kernel");
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, TQ), H, B);
@@ -361,7 +411,7 @@ template <int HD>
 static int launch_bwd(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                       const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, float* dK, int lddk, float* dV,
                       int lddv, int B, int H, int T, int S, float scale, Ragged rg, cudaStream_t st) {
-  const size_t smem = AttnSmem<HD>::bytes(ldA);
+  const size_t smem = AttnSmem<HD>::bytes(S);
   MMX_REQUIRE(smem <= 227 * 1024, "sequence too long for the single-pass attention kernel");
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, TQ), H, B);
@@ -369,7 +419,7 @@ static int launch_bwd(const float* dO, int lddo, const float* Q, int ldq, const 
                                                               scale, rg);
   MMX_LAUNCH_CHECK();
   if (dQ == nullptr) return 0;
-  const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 4) + 2 * KV_ROWS * (KV_KEYS + 4));
+  const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 8) + 2 * KV_ROWS * (KV_KEYS + 8));
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   dim3 grid2(cdiv(S, KV_KEYS), H, B);
   attention_bwd_kv_kernel<HD><<<grid2, ATT_THREADS, smem2, st>>>(dO, lddo, Q, ldq, A, dA, ldA, delta, dK, lddk, dV, lddv, H,

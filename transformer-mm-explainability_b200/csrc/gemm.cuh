@@ -25,6 +25,7 @@ int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc
             const GemmEpilogue& ep, cudaStream_t st);
 
 int gemm_tc_available();
+int gemm_tc_tile_n(int bn);   // forced tcgen05 tile width: bn < 0 reads it, 0 = automatic, 128/144/160 force
 
 // Tensor-core product for the relevancy updates (no bias / activation): C = residual + A * Bt^T with N possibly not a
 // multiple of 4 as long as every row stride covers round_up(N, 4) columns (the pad columns receive zeros).  Returns

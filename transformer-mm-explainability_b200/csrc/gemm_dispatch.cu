@@ -115,6 +115,8 @@ int mmx_set_gemm_backend(int backend) {
   return g_backend.load();
 }
 
+int mmx_set_gemm_tile_n(int bn) { return gemm_tc_tile_n(bn == 0 || bn == 128 || bn == 144 || bn == 160 ? bn : -1); }
+
 int mmx_profile_gemm(int enable) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (enable) {

@@ -15,7 +15,13 @@
 //     so A costs one shared-memory read instead of three operand fetches;
 //   * B (weights): raw tile split in shared memory (hi in place, lo beside it), fetched by the MMAs from there.
 //
-// Structure (one CTA per SM, persistent over 128x128 output tiles, 4-stage ring of 128x32 K-slabs):
+// Tile shape: 128 x BN with BN in {128, 144, 160}, chosen per launch so that the tile count fills whole waves of the
+// 148 SMs (the batch-64 vision tower has 25 row tiles: 128-wide tiles give 150 / 450 / 600 tiles = 2 / 4 / 5 waves for
+// 1.01 / 3.04 / 4.05 waves of work).  Every output element sums its K products in the same order whatever BN is, so
+// the choice never changes a result bit.  TMEM holds 2*BN accumulator columns + 64 columns of A per stage, which is
+// why the wide tiles run a 3-stage ring.
+//
+// Structure (one CTA per SM, persistent over 128xBN output tiles, 3/4-stage ring of 128x32 K-slabs):
 //   warp 0      TMA producer: raw fp32 A and B tiles -> shared memory (128-byte swizzle), mbarrier complete_tx
 //   warps 12-15 splitters (one per TMEM lane quarter; build with -DMMX_TC_SPLIT_WARPS=8 for two per quarter): A tile (smem) -> hi/lo -> TMEM columns of this
 //               stage; B tile -> hi/lo planes in smem
@@ -32,7 +38,7 @@ namespace mmx {
 
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 32;    // BK fp32 = 128 bytes = one swizzle-128B row
+constexpr int BM = 128, BK = 32;              // BK fp32 = 128 bytes = one swizzle-128B row; BN is a template parameter
 // Splitter warps: 4 (one per TMEM lane quarter, 512 threads, 128 regs/thread for everyone) or 8 (two per quarter, each
 // converting half of the slab's K columns; 640 threads, which needs setmaxnreg rebalancing because the epilogue uses
 // ~128 registers: 4*32*64 + 8*32*136 + 8*32*72 = 61440 = 640*96).  Measured 75.7 vs ~77 us on the QKV shape; the
@@ -45,12 +51,18 @@ constexpr bool REBALANCE = SPLIT_WARPS == 8;
 constexpr int THREADS = (12 + SPLIT_WARPS) * 32;
 constexpr int REGS_CTRL = 64, REGS_EPI = 136, REGS_SPLIT = 72;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, SPLIT_WARP0 = 12;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;           // 16 KB raw A slab
-constexpr int B_BYTES = BN * BK * 4;           // 16 KB per B plane
-constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t TM_MAIN = 0, TM_CROSS = 128, TM_A = 256;   // TMEM column map; A stage s: hi at TM_A+64s, lo at +32
+template <int BN, int STAGES> struct Cfg {
+  static_assert(BN % 16 == 0 && BN >= 128 && BN <= 160, "UMMA N for M=128: multiple of 16; TMEM budget caps it at 160");
+  static constexpr int B_BYTES = BN * BK * 4;          // per B plane (raw / lo): 16-20 KB, a multiple of 1024
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // TMEM column map: main accumulator, cross accumulator, then the A ring (stage s: hi at TM_A+64s, lo at +32)
+  static constexpr uint32_t TM_MAIN = 0, TM_CROSS = (BN + 31) / 32 * 32, TM_A = 2 * TM_CROSS;
+  static_assert(TM_A + 64 * STAGES <= 512, "TMEM has 512 columns");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory per CTA");
+  static constexpr int CW = BN / 2;                     // accumulator columns per epilogue warp (64 / 72 / 80)
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -130,6 +142,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// issue only (no wait): 16 / 8 consecutive columns of this warp's 32 lanes
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -154,8 +180,12 @@ struct Params {
   GemmEpilogue ep;
 };
 
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB, Params p) {
+  using cfg = Cfg<BN, STAGES>;
+  constexpr int B_BYTES = cfg::B_BYTES, STAGE_BYTES = cfg::STAGE_BYTES, CW = cfg::CW;
+  constexpr uint32_t TM_MAIN = cfg::TM_MAIN, TM_CROSS = cfg::TM_CROSS, TM_A = cfg::TM_A;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle-128B tiles need 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -299,14 +329,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
           // B slab: lo plane beside the raw tile (elementwise, so the swizzle does not matter)
           const uint4* braw = reinterpret_cast<const uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES);
           uint4* blo = reinterpret_cast<uint4*>(smem_gen + stage * STAGE_BYTES + A_BYTES + B_BYTES);
-          constexpr int NT = SPLIT_WARPS * 32, PER = (B_BYTES / 16) / NT;   // 16-byte elements per thread (8 or 4)
+          constexpr int NT = SPLIT_WARPS * 32, NV = B_BYTES / 16, PER = (NV + NT - 1) / NT;   // 16-byte elements per thread
 #pragma unroll
           for (int u0 = 0; u0 < PER; u0 += 4) {
             uint4 x[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = braw[(u0 + u) * NT + stid];
+            for (int u = 0; u < 4; ++u)
+              if (u0 + u < PER && (NV % NT == 0 || (u0 + u) * NT + stid < NV)) x[u] = braw[(u0 + u) * NT + stid];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+              if (u0 + u >= PER || (NV % NT != 0 && (u0 + u) * NT + stid >= NV)) break;
               uint4 l;
               l.x = __float_as_uint(__uint_as_float(x[u].x) - __uint_as_float(x[u].x & 0xFFFFE000u));
               l.y = __float_as_uint(__uint_as_float(x[u].y) - __uint_as_float(x[u].y & 0xFFFFE000u));
@@ -329,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     if (REBALANCE) reg_inc<REGS_EPI>();
     // ------------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
     const int q = warp & 3;                                     // TMEM lane quarter this warp may read
-    const int ch = (warp - EPI_WARP0) >> 2;                     // column half: 64 of the 128 accumulator columns
+    const int ch = (warp - EPI_WARP0) >> 2;                     // column half: CW of the BN accumulator columns
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
@@ -337,15 +369,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 0);
       tc_fence_after();
       // drain main + cross accumulators into registers (RN add), then hand TMEM back before any global traffic
-      uint32_t acc[64];
+      uint32_t acc[CW];
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CW);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32], x[32];
-        const uint32_t col = (uint32_t)(ch * 64 + c * 32);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TM_MAIN + col, r);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TM_CROSS + col, x);
+      for (int c = 0; c + 16 <= CW; c += 16) {                  // 16-column pieces: main straight into acc, cross added
+        uint32_t x[16];
+        tmem_ld16_nowait(trow + TM_MAIN + c, acc + c);
+        tmem_ld16_nowait(trow + TM_CROSS + c, x);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
+        for (int j = 0; j < 16; ++j) acc[c + j] = __float_as_uint(__uint_as_float(acc[c + j]) + __uint_as_float(x[j]));
+      }
+      if constexpr (CW % 16 == 8) {
+        constexpr int c = CW - 8;
+        uint32_t x[8];
+        tmem_ld8_nowait(trow + TM_MAIN + c, acc + c);
+        tmem_ld8_nowait(trow + TM_CROSS + c, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c + j] = __float_as_uint(__uint_as_float(acc[c + j]) + __uint_as_float(x[j]));
       }
       tc_fence_before();
       __syncwarp();
@@ -357,9 +399,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         const float* prow = p.ep.pre ? p.ep.pre + (long long)m * p.ep.ldpre : nullptr;
         const float* rrow = p.ep.residual ? p.ep.residual + (long long)m * p.ep.ldres : nullptr;
         float* arow = p.ep.C_act ? p.ep.C_act + (long long)m * p.ldc : nullptr;
-        const int nbase = n0 + ch * 64;
+        const int nbase = n0 + ch * CW;
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < CW; j += 4) {
           const int n = nbase + j;
           if (n >= p.N) break;                                  // N % 4 == 0 is required by the host wrapper
           float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
@@ -398,6 +440,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+}  // namespace tc
+// get (bn < 0) / set the forced tile width; 0 = automatic
+int gemm_tc_tile_n(int bn) {
+  static std::atomic<int> forced{-1};
+  if (forced.load() < 0) { const char* e = getenv("MMX_TC_BN"); const int v = e ? atoi(e) : 0; forced.store(v == 128 || v == 144 || v == 160 ? v : 0); }
+  if (bn == 0 || bn == 128 || bn == 144 || bn == 160) forced.store(bn);
+  return forced.load();
+}
+namespace tc {
 static long long* g_trace = nullptr;
 static int g_avail = -1;
 
@@ -416,24 +467,52 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld
   return 0;
 }
 
-static int launch(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
-                  const GemmEpilogue& ep, cudaStream_t st) {
+// Tile width for this launch: the BN whose tile count costs the fewest SM-waves x BN (ties and near-ties go to the
+// narrower tile, which has the deeper ring).  A ragged launch (row count known only on the device) keeps 128.
+// MMX_TC_BN=128|144|160 forces one width (profiling).
+static int pick_bn(int M, int N, bool ragged) {
+  const int forced = gemm_tc_tile_n(-1);
+  if (forced) return forced;
+  if (ragged) return 128;
+  const int sms = sm_count(), tiles_m = cdiv(M, BM);
+  int best = 128;
+  double best_cost = 1e30;
+  for (int bn : {128, 144, 160}) {
+    const double cost = (double)cdiv(tiles_m * cdiv(N, bn), sms) * bn * (bn == 128 ? 1.0 : 1.04);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int BN, int STAGES>
+static int launch_bn(const float* A, int lda, const float* Bt, int ldb, int M, int N, int K, const Params& p, cudaStream_t st) {
+  using cfg = Cfg<BN, STAGES>;
   CUtensorMap mapA, mapB;
   MMX_TRY(make_map(&mapA, A, M, K, lda, BM));
   MMX_TRY(make_map(&mapB, Bt, N, K, ldb, BN));
   static bool attr_set = false;
   if (!attr_set) {
-    MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        cfg::SMEM_BYTES));
     attr_set = true;
   }
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tf32x3_kernel<BN, STAGES><<<grid, THREADS, cfg::SMEM_BYTES, st>>>(mapA, mapB, p);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+                  const GemmEpilogue& ep, cudaStream_t st) {
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("MMX_TC_DBG"); dbg = e ? atoi(e) : 0; }
   Params p{M, N, K, ldc, g_trace, dbg, C, ep};
-  const int tiles = cdiv(M, BM) * cdiv(N, BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tf32x3_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
-  MMX_LAUNCH_CHECK();
-  return 0;
+  switch (pick_bn(M, N, ep.m_dev != nullptr)) {
+    case 144: return launch_bn<144, 3>(A, lda, Bt, ldb, M, N, K, p, st);
+    case 160: return launch_bn<160, 3>(A, lda, Bt, ldb, M, N, K, p, st);
+    default: return launch_bn<128, 4>(A, lda, Bt, ldb, M, N, K, p, st);
+  }
 }
 
 }  // namespace tc
