@@ -1,6 +1,6 @@
 // Attention forward that stages A = softmax(QK^T) to HBM, and the attention backward that stages dA = dO V^T
 // (the two tensors the reference captures with forward / backward hooks) and continues to dQ, dK, dV.
-// 3xTF32 mma.sync products with fp32 softmax; one CTA = one (batch, head, 32-query tile); score rows live in shared memory so any S <= ~1500
+// 3xTF32 mma.sync products with fp32 softmax; one CTA = one (batch, head, 64-query tile), 8 warps; score rows live in shared memory so any S <= ~1500
 // (DETR 850, ViT-L/14@336 577) is handled without a second pass.  Deterministic (no atomics): dK/dV come from a
 // second kernel that walks the query tiles for one key tile.
 #include "mmx_common.cuh"
@@ -15,9 +15,9 @@ struct Ragged {
   const int* lens = nullptr;
 };
 
-constexpr int TQ = 32;    // query rows per CTA (two m16 row blocks)
+constexpr int TQ = 64;    // query rows per CTA (four m16 row blocks): one CTA covers a whole CLIP ViT-B/32 head (50 rows)
 constexpr int TKEY = 64;  // keys per shared-memory tile
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_THREADS = 256, ATT_WARPS = ATT_THREADS / 32;
 
 // The three small matrix products per head (scores, P.V and their backward twins) run on the tensor cores as
 // mma.sync.m16n8k8 TF32 with the same fp32-faithful 3-pass split as the linear GEMMs (gemm_tcgen05.cu): x = hi + lo,
@@ -90,35 +90,57 @@ struct AttnSmem {
   static size_t bytes(int S) { return sizeof(float) * ((size_t)TQ * score_ld(S) + (size_t)TQ * LDX + (size_t)TKEY * LDV); }
 };
 
-// rows j0 .. j0+TKEY-1 of Y (zero beyond S) -> sY with row stride ld
-template <int HD>
-__device__ __forceinline__ void load_key_tile(const float* __restrict__ Y, int ldy, long long ybase, int j0, int S, float* sY,
-                                              int ld) {
-  for (int e = threadIdx.x; e < TKEY * (HD / 4); e += ATT_THREADS) {
+// 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching src
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// rows r0 .. r0+ROWS-1 of Y (zero beyond `limit`) -> sY with row stride ld, asynchronously (commit + wait by the caller)
+template <int HD, int ROWS>
+__device__ __forceinline__ void load_rows_async(const float* __restrict__ Y, int ldy, long long ybase, int r0, int limit,
+                                                float* sY, int ld) {
+  for (int e = threadIdx.x; e < ROWS * (HD / 4); e += ATT_THREADS) {
     const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j0 + r < S) v = *reinterpret_cast<const float4*>(Y + ybase + (long long)(j0 + r) * ldy + d);
-    *reinterpret_cast<float4*>(sY + r * ld + d) = v;
+    const bool ok = r0 + r < limit;
+    cp_async16(sY + r * ld + d, ok ? Y + ybase + (long long)(r0 + r) * ldy + d : Y, ok);
   }
 }
 
-// scores[i][j] (i in the 32-row tile, j in [0,S)) = post_scale * sum_d X[i][d] * Y[j][d];  X rows already in sX, Y
-// streamed through sY.  Warp w owns row block w&1 and the 32-key half w>>1 of each key tile.
+// scores[i][j] (i in the 64-row tile, j in [0,S)) = post_scale * sum_d (pre_scale * X[i][d]) * Y[j][d].  The caller has
+// issued (cp.async, committed) the X tile into sX and the FIRST key tile into sY; later key tiles stream through sY.
+// Warp w owns row block w&3 and the 32-key half w>>2 of each key tile.
 template <int HD>
 __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy, long long ybase, int S,
-                                            const float* sX, float* sY, float* sP, int ldP, float post_scale) {
+                                            const float* sX, float* sY, float* sP, int ldP, float pre_scale, float post_scale,
+                                            int live_rows) {
   constexpr int LDX = AttnSmem<HD>::LDX;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 1) * 16, kh = (warp >> 1) * 32;
+  const int m0 = (warp & 3) * 16, kh = (warp >> 2) * 32;
   for (int j0 = 0; j0 < S; j0 += TKEY) {
-    __syncthreads();
-    load_key_tile<HD>(Y, ldy, ybase, j0, S, sY, LDX);
+    if (j0 > 0) {
+      __syncthreads();
+      load_rows_async<HD, TKEY>(Y, ldy, ybase, j0, S, sY, LDX);
+      cp_async_commit();
+    }
+    cp_async_wait_all();
     __syncthreads();
     float acc[4][4] = {}, crs[4][4] = {};
-    const int ntiles = (S - j0 - kh + 7) >> 3;          // live 8-key blocks of this warp's half (may be <= 0)
+    // live 8-key blocks of this warp's half (may be <= 0); a row block entirely past the sample's rows does no math
+    const int ntiles = m0 < live_rows ? (S - j0 - kh + 7) >> 3 : 0;
 #pragma unroll 2
     for (int k0 = 0; k0 < HD; k0 += 8) {
-      const FragA a = frag_a_rowmajor(sX + (m0 + g) * LDX + k0 + t, LDX);
+      FragA a;
+      {
+        const float* xa = sX + (m0 + g) * LDX + k0 + t;   // the reference scales q before the product (auxilary.py:173)
+        split_tf32(xa[0] * pre_scale, a.hi[0], a.lo[0]);
+        split_tf32(xa[8 * LDX] * pre_scale, a.hi[1], a.lo[1]);
+        split_tf32(xa[4] * pre_scale, a.hi[2], a.lo[2]);
+        split_tf32(xa[8 * LDX + 4] * pre_scale, a.hi[3], a.lo[3]);
+      }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         if (nt < ntiles) {
@@ -141,24 +163,30 @@ __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy
   __syncthreads();
 }
 
-// out[i][d] = sum_j sP[i][j] * Y[j][d].  Warp w owns row block w&1 and the d half w>>1; its HD/16 accumulator
-// fragments hold rows m0+g, m0+g+8 and columns d0 + 8*nt + 2t, +1.
+// out[i][d] = sum_j sP[i][j] * Y[j][d].  Warp w owns row block w&3 and the d half w>>2; its HD/16 accumulator
+// fragments hold rows m0+g, m0+g+8 and columns d0 + 8*nt + 2t, +1.  The caller has issued the first Y tile into sY
+// (stride LDV) with cp.async and passed a __syncthreads after the last write of sP.
 template <int HD>
 __device__ __forceinline__ void tile_pv(const float* __restrict__ Y, int ldy, long long ybase, int S, const float* sP,
-                                        int ldP, float* sY, float (&out)[HD / 16][4]) {
+                                        int ldP, float* sY, float (&out)[HD / 16][4], int live_rows) {
   constexpr int LDV = AttnSmem<HD>::LDV, NT = HD / 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 1) * 16, d0 = (warp >> 1) * (HD / 2);
+  const int m0 = (warp & 3) * 16, d0 = (warp >> 2) * (HD / 2);
   float crs[NT][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[nt][c] = crs[nt][c] = 0.f;
   for (int j0 = 0; j0 < S; j0 += TKEY) {
+    if (j0 > 0) {
+      __syncthreads();
+      load_rows_async<HD, TKEY>(Y, ldy, ybase, j0, S, sY, LDV);
+      cp_async_commit();
+    }
+    cp_async_wait_all();
     __syncthreads();
-    load_key_tile<HD>(Y, ldy, ybase, j0, S, sY, LDV);
-    __syncthreads();
-    const int jn = min(TKEY, S - j0);                   // keys jn .. round_up(jn, 8) are zero rows of sY, finite columns of sP
+    // keys jn .. round_up(jn, 8) are zero rows of sY, finite columns of sP; dead row blocks skip the math
+    const int jn = m0 < live_rows ? min(TKEY, S - j0) : 0;
 #pragma unroll 2
     for (int kk = 0; kk < jn; kk += 8) {
       const FragA a = frag_a_rowmajor(sP + (m0 + g) * ldP + j0 + kk + t, ldP);
@@ -180,7 +208,7 @@ template <int HD>
 __device__ __forceinline__ void store_pv(float* __restrict__ O, int ldo, long long row0, int i0, int T, int h,
                                          const float (&out)[HD / 16][4], float mul) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 1) * 16, d0 = (warp >> 1) * (HD / 2);
+  const int m0 = (warp & 3) * 16, d0 = (warp >> 2) * (HD / 2);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int i = i0 + m0 + g + 8 * half;
@@ -216,18 +244,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
     return;
   }
   const bool scale_scores = flags & MMX_ATTN_SCALE_SCORES;
-  const float qs = scale_scores ? 1.f : scale;
-  for (int e = tid; e < TQ * (HD / 4); e += ATT_THREADS) {
-    const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i0 + r < T) v = *reinterpret_cast<const float4*>(Q + (qrow0 + i0 + r) * ldq + h * HD + d);
-    v.x *= qs; v.y *= qs; v.z *= qs; v.w *= qs;
-    *reinterpret_cast<float4*>(sQ + r * LDH + d) = v;
-  }
-  tile_scores<HD>(K, ldk, krow0 * ldk + h * HD, S, sQ, sKV, sP, S_pad, scale_scores ? scale : 1.f);
+  load_rows_async<HD, TQ>(Q, ldq, qrow0 * ldq + h * HD, i0, T, sQ, LDH);                 // Q tile and the first K tile together
+  load_rows_async<HD, TKEY>(K, ldk, krow0 * ldk + h * HD, 0, S, sKV, LDH);
+  cp_async_commit();
+  tile_scores<HD>(K, ldk, krow0 * ldk + h * HD, S, sQ, sKV, sP, S_pad, scale_scores ? 1.f : scale, scale_scores ? scale : 1.f,
+                  T - i0);
+  load_rows_async<HD, TKEY>(V, ldv, krow0 * ldv + h * HD, 0, S, sKV, AttnSmem<HD>::LDV);     // lands during the softmax
+  cp_async_commit();
   // softmax per row (warp w owns rows w*8 .. w*8+7), stage A
-  for (int rr = 0; rr < TQ / 4; ++rr) {
-    const int r = warp * (TQ / 4) + rr, i = i0 + r;
+  for (int rr = 0; rr < TQ / ATT_WARPS; ++rr) {
+    const int r = warp * (TQ / ATT_WARPS) + rr, i = i0 + r;
     if (i >= T) {
       if (i < Tm) for (int j = lane; j < ldA; j += 32) A[(((long long)b * H + h) * Tm + i) * ldA + j] = 0.f;
       continue;
@@ -254,7 +280,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
   }
   __syncthreads();
   float out[HD / 16][4];
-  tile_pv<HD>(V, ldv, krow0 * ldv + h * HD, S, sP, S_pad, sKV, out);
+  tile_pv<HD>(V, ldv, krow0 * ldv + h * HD, S, sP, S_pad, sKV, out, T - i0);
   store_pv<HD>(O, ldo, qrow0, i0, T, h, out, 1.f);
 }
 
@@ -282,15 +308,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
     }
     return;
   }
-  for (int e = tid; e < TQ * (HD / 4); e += ATT_THREADS) {
-    const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i0 + r < T) v = *reinterpret_cast<const float4*>(dO + (qrow0 + i0 + r) * lddo + h * HD + d);
-    *reinterpret_cast<float4*>(sX + r * LDH + d) = v;
+  load_rows_async<HD, TQ>(dO, lddo, qrow0 * lddo + h * HD, i0, T, sX, LDH);
+  load_rows_async<HD, TKEY>(V, ldv, krow0 * ldv + h * HD, 0, S, sKV, LDH);
+  cp_async_commit();
+  tile_scores<HD>(V, ldv, krow0 * ldv + h * HD, S, sX, sKV, sP, S_pad, 1.f, 1.f, T - i0);
+  if (dQ != nullptr) {                                                                    // lands while dA is staged
+    load_rows_async<HD, TKEY>(K, ldk, krow0 * ldk + h * HD, 0, S, sKV, AttnSmem<HD>::LDV);
+    cp_async_commit();
   }
-  tile_scores<HD>(V, ldv, krow0 * ldv + h * HD, S, sX, sKV, sP, S_pad, 1.f);
-  for (int rr = 0; rr < TQ / 4; ++rr) {
-    const int r = warp * (TQ / 4) + rr, i = i0 + r;
+  for (int rr = 0; rr < TQ / ATT_WARPS; ++rr) {
+    const int r = warp * (TQ / ATT_WARPS) + rr, i = i0 + r;
     if (i >= T) {
       if (i < Tm) for (int j = lane; j < ldA; j += 32) dA[(((long long)b * H + h) * Tm + i) * ldA + j] = 0.f;
       continue;
@@ -312,13 +339,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
   if (dQ == nullptr) return;
   __syncthreads();
   float out[HD / 16][4];
-  tile_pv<HD>(K, ldk, krow0 * ldk + h * HD, S, sP, S_pad, sKV, out);
+  tile_pv<HD>(K, ldk, krow0 * ldk + h * HD, S, sP, S_pad, sKV, out, T - i0);
   store_pv<HD>(dQ, lddq, qrow0, i0, T, h, out, scale);
 }
 
-// backward, key side: one CTA = 32 keys of one (b,h); walks all query rows in tiles of 64.
+// backward, key side: one CTA = 64 keys of one (b,h) (a whole CLIP ViT-B/32 head); walks the query rows in tiles of 64.
 //   dV[j] = sum_i A[i][j] dO[i]      dK[j] = scale * sum_i dS[i][j] Q[i],  dS = A (.) (dA - delta_i)
-constexpr int KV_KEYS = 32, KV_ROWS = 64;
+// Warp w owns the 16-key block w&3 and the d half w>>2 of both products.
+constexpr int KV_KEYS = 64, KV_ROWS = 64;
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ Q, int ldq, const float* __restrict__ A,
@@ -332,7 +360,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
   float* sS = sA + KV_ROWS * LDK;          // [KV_ROWS][LDK]  dS[i][j]
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * KV_KEYS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 1) * 16, d0 = (warp >> 1) * (HD / 2);   // this warp's 16 keys and d half
+  const int m0 = (warp & 3) * 16, d0 = (warp >> 2) * (HD / 2);   // this warp's 16 keys and d half
   const int Tm = T;
   long long qrow0 = (long long)b * T, krow0 = (long long)b * S;
   if (rg.lens) { T = S = rg.lens[b]; qrow0 = krow0 = rg.offs[b]; }
@@ -341,39 +369,39 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
   const long long plane = ((long long)b * H + h) * Tm;
   for (int i0 = 0; i0 < T; i0 += KV_ROWS) {
     __syncthreads();
-    for (int e = tid; e < KV_ROWS * KV_KEYS; e += ATT_THREADS) {
-      const int r = e / KV_KEYS, c = e % KV_KEYS;
-      float a = 0.f, ds = 0.f;
-      if (i0 + r < T && j0 + c < S) {
+    load_rows_async<HD, KV_ROWS>(dO, lddo, qrow0 * lddo + h * HD, i0, T, sdO, LDH);
+    load_rows_async<HD, KV_ROWS>(Q, ldq, qrow0 * ldq + h * HD, i0, T, sQ, LDH);
+    cp_async_commit();
+    // A and dS tiles: 4 keys per 128-bit load.  Staged rows are ldA (% 4 == 0) wide and zero beyond this sample's
+    // keys, so a float4 that starts below ldA is entirely readable and entirely correct.
+    for (int e = tid; e < KV_ROWS * (KV_KEYS / 4); e += ATT_THREADS) {
+      const int r = e / (KV_KEYS / 4), c = (e % (KV_KEYS / 4)) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), ds = a;
+      if (i0 + r < T && j0 + c < ldA) {
         const long long off = (plane + i0 + r) * ldA + j0 + c;
-        a = A[off];
-        ds = a * (dA[off] - delta[plane + i0 + r]);
+        a = *reinterpret_cast<const float4*>(A + off);
+        const float4 ga = *reinterpret_cast<const float4*>(dA + off);
+        const float dl = delta[plane + i0 + r];
+        ds = make_float4(a.x * (ga.x - dl), a.y * (ga.y - dl), a.z * (ga.z - dl), a.w * (ga.w - dl));
       }
-      sA[r * LDK + c] = a;
-      sS[r * LDK + c] = ds;
+      *reinterpret_cast<float4*>(sA + r * LDK + c) = a;
+      *reinterpret_cast<float4*>(sS + r * LDK + c) = ds;
     }
-    for (int e = tid; e < KV_ROWS * (HD / 4); e += ATT_THREADS) {
-      const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
-      float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), vq = vo;
-      if (i0 + r < T) {
-        vo = *reinterpret_cast<const float4*>(dO + (qrow0 + i0 + r) * lddo + h * HD + d);
-        vq = *reinterpret_cast<const float4*>(Q + (qrow0 + i0 + r) * ldq + h * HD + d);
-      }
-      *reinterpret_cast<float4*>(sdO + r * LDH + d) = vo;
-      *reinterpret_cast<float4*>(sQ + r * LDH + d) = vq;
-    }
+    cp_async_wait_all();
     __syncthreads();
     const int in = min(KV_ROWS, T - i0);                // rows in .. round_up(in, 8) are zero-filled
+    if (j0 + m0 < S) {                                  // this warp's 16 keys are live (warp-uniform)
 #pragma unroll 2
-    for (int kk = 0; kk < in; kk += 8) {
-      const FragA aA = frag_a_kmajor(sA + (kk + t) * LDK + m0 + g, LDK);
-      const FragA aS = frag_a_kmajor(sS + (kk + t) * LDK + m0 + g, LDK);
+      for (int kk = 0; kk < in; kk += 8) {
+        const FragA aA = frag_a_kmajor(sA + (kk + t) * LDK + m0 + g, LDK);
+        const FragA aS = frag_a_kmajor(sS + (kk + t) * LDK + m0 + g, LDK);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const FragB bo = frag_b_kmajor(sdO + (kk + t) * LDH + d0 + nt * 8 + g, LDH);
-        mma3(accV[nt], crsV[nt], aA, bo);
-        const FragB bq = frag_b_kmajor(sQ + (kk + t) * LDH + d0 + nt * 8 + g, LDH);
-        mma3(accK[nt], crsK[nt], aS, bq);
+        for (int nt = 0; nt < NT; ++nt) {
+          const FragB bo = frag_b_kmajor(sdO + (kk + t) * LDH + d0 + nt * 8 + g, LDH);
+          mma3(accV[nt], crsV[nt], aA, bo);
+          const FragB bq = frag_b_kmajor(sQ + (kk + t) * LDH + d0 + nt * 8 + g, LDH);
+          mma3(accK[nt], crsK[nt], aS, bq);
+        }
       }
     }
   }
