@@ -106,6 +106,12 @@ int mmx_mm_update(const float* R_ss, int ld_ss, const float* R_qq, int ld_qq, co
 int mmx_rollout(const float* mats, int L, int B, int S, int start_layer, int normalize, float* out,
                 float* workspace, void* stream);
 
+/* Min-max normalisation of B contiguous maps of n floats: Y = (X - min X) / (max X - min X) per map (in place allowed).
+ * Replaces the `(cam - cam.min()) / (cam.max() - cam.min())` step of the attn-GradCAM / partial-LRP baselines
+ * (VisualBERT/mmf/models/transformers/backends/ExplanationGenerator.py:122,203) and of the DETR mask generator
+ * (DETR/mask_generator.py:115-121).  A constant map yields NaN, as in the reference. */
+int mmx_minmax_normalize(const float* X, float* Y, int B, long long n, void* stream);
+
 /* Generic batched C[b] = beta_src[b] + op(A[b]) * B[b]  (fp32, used by the rule entry points above; exported
  * for the host-side generators).  transA: 0 = A is [M,K], 1 = A is stored [K,M].  add may be NULL. */
 int mmx_bmm_add(const float* A, int lda, long long strideA, int transA, const float* Bm, int ldb, long long strideB,

@@ -178,6 +178,35 @@ def generate_ours(sd, cfg: DetrConfig, src, pos, target_index, index=None, norma
     return res
 
 
+def generate_ours_abl(sd, cfg: DetrConfig, src, pos, target_index, index=None, normalize_self_attention=False,
+                      apply_self_in_rule_10=True, dtype=torch.float32):
+    """GeneratorAlbationNoAgg.generate_ours_abl(use_lrp=False) per sample (DETR/modules/ExplanationGenerator.py:306-403):
+    the same sweep as generate_ours with every ``+=`` replaced by ``=``.  Returns R_q_i[target] as [B, S_i]."""
+    sd = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd.items()}
+    src = src.to(dtype).requires_grad_(True)
+    pos = pos.to(dtype)
+    B, H = src.shape[0], cfg.nhead
+    logits, A_e, A_ds, A_dc = detr_forward(sd, cfg, src, pos)
+    tq = torch.as_tensor(target_index).reshape(B)
+    cls = logits[torch.arange(B), tq, :-1].argmax(-1) if index is None else torch.as_tensor(index).reshape(B)
+    grads = torch.autograd.grad(logits[torch.arange(B), tq, cls].sum(), A_e + A_ds + A_dc)
+    ne, nd = len(A_e), len(A_ds)
+    G_e, G_ds, G_dc = grads[:ne], grads[ne:ne + nd], grads[ne + nd:]
+    S, Q = A_e[0].shape[-1], A_ds[0].shape[-1]
+    out = []
+    for b in range(B):
+        sl = slice(b * H, (b + 1) * H)
+        R_ii, R_qq, R_qi = torch.eye(S, dtype=dtype), torch.eye(Q, dtype=dtype), torch.zeros(Q, S, dtype=dtype)
+        for A, G in zip(A_e, G_e):                                                   # :314-322
+            R_ii = R_.avg_heads(A[sl].detach(), G[sl]) @ R_ii
+        for A, G, Ac, Gc in zip(A_ds, G_ds, A_dc, G_dc):
+            R_qq, R_qi = R_.apply_self_attention_rules(R_qq, R_qi, R_.avg_heads(A[sl].detach(), G[sl]))   # :324-333
+            R_qi = R_.apply_mm_attention_rules_detr(R_qq, R_ii, R_.avg_heads(Ac[sl].detach(), Gc[sl]),    # :335-344
+                                                    normalize_self_attention, apply_self_in_rule_10)
+        out.append(R_qi[tq[b]])
+    return torch.stack(out)
+
+
 def synthetic_inputs(cfg: DetrConfig, B: int, h: int, w: int, seed: int = 0):
     g = torch.Generator().manual_seed(seed)
     src = torch.randn(B, cfg.d_model, h, w, generator=g)

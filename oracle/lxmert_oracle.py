@@ -206,3 +206,44 @@ def generate_ours(sd, cfg: LxmertConfig, ids, feats, boxes, index=None, normaliz
         R_tt[0, 0] = 0                                                               # EG:210
         Rtt.append(R_tt); Rti.append(R_ti)
     return torch.stack(Rtt), torch.stack(Rti), logits.detach()
+
+
+def generate_ours_no_agg(sd, cfg: LxmertConfig, ids, feats, boxes, index=None, normalize_self_attention=True,
+                         dtype=torch.float32):
+    """GeneratorOursAblationNoAggregation.generate_ours_no_agg(use_lrp=False) per sample
+    (lxmert/lxmert/src/ExplanationGenerator.py:215-365): every update replaces the relevancy.  Returns
+    (R_t_t [B,T,T], R_t_i [B,T,I])."""
+    sd = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd.items()}
+    feats, boxes = feats.to(dtype), boxes.to(dtype)
+    logits, st = lxmert_forward(sd, cfg, ids, feats, boxes)
+    B, T = ids.shape
+    I = feats.shape[1]
+    idx = logits.argmax(-1) if index is None else torch.as_tensor(index).reshape(B)
+    names = ["lang", "vis", "x_lang", "x_vis", "x_lang_self", "x_vis_self"]
+    flat = [a for n in names for a in st[n]]
+    grads = torch.autograd.grad(logits[torch.arange(B), idx].sum(), flat, allow_unused=True)
+    G, k = {}, 0
+    for n in names:
+        G[n] = grads[k:k + len(st[n])]
+        k += len(st[n])
+    nx, norm = cfg.x_layers, normalize_self_attention
+    Rtt, Rti = [], []
+    for b in range(B):
+        cam = lambda n, i: R_.avg_heads(st[n][i][b].detach(), G[n][i][b])
+        R_tt, R_ii = torch.eye(T, dtype=dtype), torch.eye(I, dtype=dtype)
+        R_ti, R_it = torch.zeros(T, I, dtype=dtype), torch.zeros(I, T, dtype=dtype)
+        for i in range(cfg.l_layers):
+            R_tt, R_ti = R_.apply_self_attention_rules(R_tt, R_ti, cam("lang", i))
+        for i in range(cfg.r_layers):
+            R_ii, R_it = R_.apply_self_attention_rules(R_ii, R_it, cam("vis", i))
+        for i in range(nx - 1):                                                       # EG:330-350
+            ti, tt = R_.apply_mm_attention_rules_lxmert(R_tt, R_ii, R_it, cam("x_lang", i), norm)
+            it, ii = R_.apply_mm_attention_rules_lxmert(R_ii, R_tt, R_ti, cam("x_vis", i), norm)
+            R_ti, R_tt, R_it, R_ii = ti, tt, it, ii
+            R_tt, R_ti = R_.apply_self_attention_rules(R_tt, R_ti, cam("x_lang_self", i))
+            R_ii, R_it = R_.apply_self_attention_rules(R_ii, R_it, cam("x_vis_self", i))
+        R_ti, R_tt = R_.apply_mm_attention_rules_lxmert(R_tt, R_ii, R_it, cam("x_lang", nx - 1), norm)   # EG:353-358
+        R_tt, R_ti = R_.apply_self_attention_rules(R_tt, R_ti, cam("x_lang_self", nx - 1))
+        R_tt[0, 0] = 0
+        Rtt.append(R_tt); Rti.append(R_ti)
+    return torch.stack(Rtt), torch.stack(Rti)

@@ -114,6 +114,8 @@ def golden_detr():
             out[f"R.n{int(norm)}s{int(s10)}"] = r.numpy()
     for method in ("raw_attn", "rollout", "attn_gradcam"):          # baselines behind the same API
         out["base." + method] = ref_detr.generate_baseline(cfg, sd, src, pos, tq, method).numpy()
+    out["abl.noagg"] = ref_detr.generate_ours_abl(cfg, sd, src, pos, tq).numpy()    # GeneratorAlbationNoAgg (EG:306-403)
+    out["abl.noagg.s0"] = ref_detr.generate_ours_abl(cfg, sd, src, pos, tq, apply_self_in_rule_10=False).numpy()
     np.savez_compressed(os.path.join(OUT, "detr_tiny.npz"), **out)
     print("wrote detr_tiny", out["R.n1s1"].shape)
 
@@ -134,15 +136,39 @@ def golden_lxmert():
     for method in ("raw_attn", "rollout", "attn_gradcam"):
         rtt, rti = ref_lxmert.generate_baseline(cfg, sd, ids, feats, boxes, method)
         out[f"base.{method}.Rtt"], out[f"base.{method}.Rti"] = rtt.numpy(), rti.numpy()
+    rtt, rti = ref_lxmert.generate_ours_no_agg(cfg, sd, ids, feats, boxes, normalize_self_attention=False)   # EG:215-365
+    out["abl.noagg.Rtt"], out["abl.noagg.Rti"] = rtt.numpy(), rti.numpy()
     np.savez_compressed(os.path.join(OUT, "lxmert_tiny.npz"), **out)
     print("wrote lxmert_tiny", out["Rtt.n1s1"].shape, out["Rti.n1s1"].shape)
 
 
+def golden_visualbert():
+    from . import visualbert_oracle as vo, ref_visualbert
+    cfg = vo.VISUALBERT_TINY
+    sd = vo.init_state_dict(cfg, 3)
+    inp = vo.synthetic_inputs(cfg, 3, 7, 6, seed=4)
+    inp["attention_mask"][1, -2:] = 0                     # sample 1: two padded boxes (image_mask, visual_bert.py:548-555)
+    out = {"inp." + k: v.numpy() for k, v in inp.items()}
+    for k, v in sd.items():
+        out["sd." + k] = v.numpy()
+    for method in ("ours", "raw_attn", "rollout", "attn_gradcam"):
+        out["R." + method] = ref_visualbert.generate(cfg, sd, inp, method).numpy()
+    out["R.ours.index5"] = ref_visualbert.generate(cfg, sd, inp, "ours", index=5).numpy()
+    out["R.rollout.sl1"] = ref_visualbert.generate(cfg, sd, inp, "rollout", start_layer=1).numpy()
+    np.savez_compressed(os.path.join(OUT, "visualbert_tiny.npz"), **out)
+    print("wrote visualbert_tiny", out["R.ours"].shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if "--only-new" in __import__("sys").argv:
+    argv = __import__("sys").argv
+    if "--visualbert" in argv:
+        golden_visualbert()
+        return
+    if "--only-new" in argv:
         golden_detr()
         golden_lxmert()
+        golden_visualbert()
         return
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     golden_rules()
@@ -150,6 +176,7 @@ def main():
     golden_clip("small", co.SMALL, 4, wseed=2, iseed=11)
     golden_detr()
     golden_lxmert()
+    golden_visualbert()
 
 
 if __name__ == "__main__":

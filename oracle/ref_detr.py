@@ -64,3 +64,16 @@ def generate_baseline(cfg, sd, src, pos, tq, method):
             r = fn((src[b:b + 1], pos[b:b + 1]), torch.tensor([int(tq[b])]))
             outs.append(r.reshape(-1).detach())
     return torch.stack(outs)
+
+
+def generate_ours_abl(cfg, sd, src, pos, tq, **kw):
+    """The reference's GeneratorAlbationNoAgg.generate_ours_abl (DETR/modules/ExplanationGenerator.py:306-403), per sample."""
+    m, _ = build(cfg, sd)
+    from DETR.modules.ExplanationGenerator import GeneratorAlbationNoAgg
+    gen = GeneratorAlbationNoAgg(m)
+    outs = []
+    with rs.cuda_is_identity():
+        for b in range(src.shape[0]):
+            r = gen.generate_ours_abl((src[b:b + 1], pos[b:b + 1]), torch.tensor([int(tq[b])]), use_lrp=False, **kw)
+            outs.append(r.reshape(-1).detach())
+    return torch.stack(outs)

@@ -112,3 +112,24 @@ def generate_baseline(cfg, sd, ids, feats, boxes, method):
             a, c = getattr(gen, "generate_" + method)(None)
             Rtt.append(a.detach().clone()); Rti.append(c.detach().clone())
     return torch.stack(Rtt), torch.stack(Rti)
+
+
+def generate_ours_no_agg(cfg, sd, ids, feats, boxes, **kw):
+    """The reference's GeneratorOursAblationNoAggregation.generate_ours_no_agg (ExplanationGenerator.py:215-365), per sample."""
+    m, eg = build(cfg, sd)
+    Rtt, Rti = [], []
+    with rs.cuda_is_identity():
+        for b in range(ids.shape[0]):
+            class Usage:
+                model = m
+                text_len = ids.shape[1]
+                image_boxes_len = feats.shape[1]
+
+                def forward(self, item):
+                    out = types.SimpleNamespace()
+                    out.question_answering_score = m(ids[b:b + 1], feats[b:b + 1], boxes[b:b + 1])
+                    return out
+            gen = eg.GeneratorOursAblationNoAggregation(Usage())
+            a, c = gen.generate_ours_no_agg(None, use_lrp=False, **kw)
+            Rtt.append(a.detach().clone()); Rti.append(c.detach().clone())
+    return torch.stack(Rtt), torch.stack(Rti)

@@ -116,3 +116,86 @@ def test_lxmert_baselines_golden(golden_dir, method):
     assert rel_err(rtt, g[f"base.{method}.Rtt"]) < TOL and rel_err(rti, g[f"base.{method}.Rti"]) < TOL
     with pytest.raises(NotImplementedError):
         gen.generate_transformer_attr((ids.cuda(), feats.cuda(), boxes.cuda()))
+
+
+def _vb_inputs(g):
+    return {k[4:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith("inp.")}
+
+
+@pytest.mark.parametrize("method", ["ours", "ours.index5", "raw_attn", "rollout", "rollout.sl1", "attn_gradcam"])
+def test_visualbert_golden(golden_dir, method):
+    """VisualBERT single-stream generator vs the reference SelfAttentionGenerator's own outputs."""
+    import mmx_b200
+    from oracle import visualbert_oracle as vo
+    g = np.load(os.path.join(golden_dir, "visualbert_tiny.npz"))
+    eng = mmx_b200.VisualBertEngine(_sd(g), num_heads=vo.VISUALBERT_TINY.heads, device="cuda:0")
+    gen = mmx_b200.SelfAttentionGenerator(eng)
+    inp = _vb_inputs(g)
+    if method.startswith("ours"):
+        out = gen.generate_ours(inp, index=5 if method.endswith("index5") else None)
+    elif method.startswith("rollout"):
+        out = gen.generate_rollout(inp, start_layer=1 if method.endswith("sl1") else 0)
+    else:
+        out = getattr(gen, "generate_" + method)(inp)
+    assert out.shape == g["R." + method].shape
+    assert rel_err(out, g["R." + method]) < TOL
+    one = {k: v[:1] for k, v in inp.items()}                         # the reference's call form: one sample -> [1, S]
+    if method == "ours":
+        assert rel_err(gen.generate_ours(one), g["R.ours"][:1]) < TOL
+        with pytest.raises(NotImplementedError):
+            gen.generate_transformer_att(inp)
+
+
+def test_visualbert_base_shape_vs_oracle():
+    """VisualBERT base dims (768 hidden, 12 heads, 12 layers), 14 tokens + 100 boxes of 2048-d features, mmf-style
+    ``model.``-prefixed checkpoint keys."""
+    import mmx_b200
+    from oracle import visualbert_oracle as vo
+    cfg = vo.VisualBertConfig(vocab=2000, num_labels=300)
+    sd = vo.init_state_dict(cfg, seed=2)
+    inp = vo.synthetic_inputs(cfg, 2, 14, 100, seed=3)
+    ref, scores = vo.generate_ours(sd, cfg, inp)
+    eng = mmx_b200.VisualBertEngine({"model." + k: v for k, v in sd.items()}, num_heads=cfg.heads, device="cuda:0")
+    out = mmx_b200.SelfAttentionGenerator(eng).generate_ours({k: v.cuda() for k, v in inp.items()})
+    assert rel_err(eng.scores, scores) < TOL
+    assert rel_err(out, ref) < TOL
+    assert (out[torch.arange(2), eng.cls_index] == 0).all()
+
+
+def test_minmax_normalize():
+    import mmx_b200
+    x = torch.randn(3, 17, 23, device="cuda")
+    ref = torch.stack([(m - m.min()) / (m.max() - m.min()) for m in x])
+    assert torch.equal(mmx_b200.minmax_normalize(x), ref)
+
+
+# The no-aggregation ablations chain ~12 un-aggregated products of small matrices (the map is ~1e-8 .. 1e-12 at random
+# init), so the relative errors of the factors multiply up; 5e-4 on these two ablation-only outputs.
+ABL_TOL = 5e-4
+
+
+def test_detr_ablation_no_agg_golden(golden_dir):
+    """GeneratorAlbationNoAgg.generate_ours_abl vs the reference class's own outputs."""
+    import mmx_b200
+    g = np.load(os.path.join(golden_dir, "detr_tiny.npz"))
+    eng = mmx_b200.DetrEngine(_sd(g), nhead=do.DETR_TINY.nhead, device="cuda:0")
+    gen = mmx_b200.GeneratorAlbationNoAgg(eng)
+    src, pos, tq = (torch.from_numpy(g[k]) for k in ("src", "pos", "tq"))
+    out = gen.generate_ours_abl((src.cuda(), pos.cuda()), tq)
+    assert rel_err(out, g["abl.noagg"]) < ABL_TOL
+    out = gen.generate_ours_abl((src.cuda(), pos.cuda()), tq, apply_self_in_rule_10=False)
+    assert rel_err(out, g["abl.noagg.s0"]) < ABL_TOL
+    with pytest.raises(AssertionError):                   # like the reference: eq. 8-9 asserts on the un-aggregated R
+        gen.generate_ours_abl((src.cuda(), pos.cuda()), tq, normalize_self_attention=True)
+
+
+def test_lxmert_ablation_no_agg_golden(golden_dir):
+    import mmx_b200
+    g = np.load(os.path.join(golden_dir, "lxmert_tiny.npz"))
+    eng = mmx_b200.LxmertEngine(_sd(g), num_heads=lo.LXMERT_TINY.heads, device="cuda:0")
+    gen = mmx_b200.GeneratorOursAblationNoAggregation(eng)
+    ids, feats, boxes = (torch.from_numpy(g[k]).cuda() for k in ("ids", "feats", "boxes"))
+    rtt, rti = gen.generate_ours_no_agg((ids, feats, boxes), normalize_self_attention=False)
+    assert rel_err(rtt, g["abl.noagg.Rtt"]) < ABL_TOL and rel_err(rti, g["abl.noagg.Rti"]) < ABL_TOL
+    with pytest.raises(AssertionError):
+        gen.generate_ours_no_agg((ids, feats, boxes))   # default normalize_self_attention=True asserts in the reference too

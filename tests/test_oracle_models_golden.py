@@ -1,12 +1,12 @@
 """CPU: the DETR and LXMERT oracle restatements reproduce the committed outputs of the UNMODIFIED reference
-generators (tests/golden/detr_tiny.npz, lxmert_tiny.npz made by oracle/make_golden.py)."""
+generators (tests/golden/detr_tiny.npz, lxmert_tiny.npz, visualbert_tiny.npz made by oracle/make_golden.py)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-from oracle import detr_oracle as do, lxmert_oracle as lo
+from oracle import detr_oracle as do, lxmert_oracle as lo, visualbert_oracle as vo
 from util import rel_err
 
 
@@ -31,3 +31,34 @@ def test_lxmert_oracle_golden(golden_dir, norm, s10):
                                    torch.from_numpy(g["boxes"]), normalize_self_attention=norm, apply_self_in_rule_10=s10)
     key = f"n{int(norm)}s{int(s10)}"
     assert rel_err(rtt, g["Rtt." + key]) < 1e-5 and rel_err(rti, g["Rti." + key]) < 1e-5
+
+
+def _vb_inputs(g):
+    return {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("inp.")}
+
+
+@pytest.mark.parametrize("method", ["ours", "ours.index5", "raw_attn", "rollout", "rollout.sl1", "attn_gradcam"])
+def test_visualbert_oracle_golden(golden_dir, method):
+    g = np.load(os.path.join(golden_dir, "visualbert_tiny.npz"))
+    sd, inp, cfg = _sd(g), _vb_inputs(g), vo.VISUALBERT_TINY
+    if method.startswith("ours"):
+        r = vo.generate_ours(sd, cfg, inp, index=5 if method.endswith("index5") else None)[0]
+    elif method.startswith("rollout"):
+        r = vo.generate_rollout(sd, cfg, inp, start_layer=1 if method.endswith("sl1") else 0)
+    else:
+        r = getattr(vo, "generate_" + method)(sd, cfg, inp)
+    assert rel_err(r, g["R." + method]) < 1e-5
+
+
+def test_detr_ablation_no_agg_oracle_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "detr_tiny.npz"))
+    args = (_sd(g), do.DETR_TINY, torch.from_numpy(g["src"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["tq"]))
+    assert rel_err(do.generate_ours_abl(*args), g["abl.noagg"]) < 1e-5
+    assert rel_err(do.generate_ours_abl(*args, apply_self_in_rule_10=False), g["abl.noagg.s0"]) < 1e-5
+
+
+def test_lxmert_ablation_no_agg_oracle_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "lxmert_tiny.npz"))
+    rtt, rti = lo.generate_ours_no_agg(_sd(g), lo.LXMERT_TINY, torch.from_numpy(g["ids"]), torch.from_numpy(g["feats"]),
+                                       torch.from_numpy(g["boxes"]), normalize_self_attention=False)
+    assert rel_err(rtt, g["abl.noagg.Rtt"]) < 1e-5 and rel_err(rti, g["abl.noagg.Rti"]) < 1e-5

@@ -33,3 +33,17 @@ def test_repeat_mode_small():
     rt, ri = rs.reference_interpret(images[:1], tokens, model, "cpu", 0, 0)
     ot, oi = co.clip_interpret(sd, cfg, images[:1], tokens, 0, 0)
     assert text_rel_err(ot, rt.detach()) < 1e-5 and rel_err(oi, ri.detach()) < 1e-5
+
+
+@pytest.mark.parametrize("method", ["ours", "raw_attn", "rollout", "attn_gradcam"])
+def test_visualbert_live_reference(method):
+    """The unmodified BertEncoder / BertPredictionHeadTransform / SelfAttentionGenerator of the reference at a
+    wider shape than the golden file (hidden 128, 8 heads, 4 layers, 9 tokens + 12 boxes)."""
+    from oracle import visualbert_oracle as vo, ref_visualbert as rv
+    cfg = vo.VisualBertConfig(hidden=128, heads=8, intermediate=256, layers=4, vocab=80, max_pos=32, visual_dim=48, num_labels=31)
+    sd = vo.init_state_dict(cfg, 11)
+    inp = vo.synthetic_inputs(cfg, 2, 9, 12, seed=5)
+    ref = rv.generate(cfg, sd, inp, method)
+    got = getattr(vo, "generate_" + method)(sd, cfg, inp)
+    got = got[0] if isinstance(got, tuple) else got
+    assert rel_err(got, ref) < 1e-5

@@ -356,6 +356,24 @@ int copy2d(const float* src, int lds, float* dst, int ldd, long long rows, int c
   return 0;
 }
 
+// y = (x - min(x)) / (max(x) - min(x)) over each of B contiguous maps of n floats (one CTA per map).  A constant map
+// gives 0/0 = NaN exactly as the reference expression does.
+__global__ void __launch_bounds__(256) minmax_normalize_kernel(const float* __restrict__ X, float* __restrict__ Y, long long n) {
+  const float* x = X + (long long)blockIdx.x * n;
+  float* y = Y + (long long)blockIdx.x * n;
+  float mn = INFINITY, mx = -INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) { const float v = x[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  __shared__ float smn[8], smx[8];
+  mn = -warp_max(-mn); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  mn = smn[0]; mx = smx[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+  const float d = mx - mn;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) y[i] = (x[i] - mn) / d;
+}
+
 }  // namespace mmx
 
 using namespace mmx;
@@ -470,6 +488,14 @@ int mmx_rollout(const float* mats, int L, int B, int S, int start_layer, int nor
                     S, S, 0, st));
     joint = nxt;
   }
+  return 0;
+}
+
+int mmx_minmax_normalize(const float* X, float* Y, int B, long long n, void* stream) {
+  MMX_REQUIRE(B >= 0 && n > 0, "empty map");
+  if (B == 0) return 0;
+  minmax_normalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(X, Y, n);
+  MMX_LAUNCH_CHECK();
   return 0;
 }
 

@@ -234,3 +234,31 @@ class Generator:
 
     def generate_transformer_att(self, img, target_index, index=None):
         raise NotImplementedError("transformer attribution needs the relprop sweep: outside the hot-path scope")
+
+
+class GeneratorAlbationNoAgg(Generator):
+    """DETR/modules/ExplanationGenerator.py:306-403 (sic): the ablation without aggregation - every update REPLACES the
+    relevancy instead of adding to it (``R = cam R`` for the self-attention rules, ``R_q_i = rule 10`` for the
+    cross-attention)."""
+
+    def handle_self_attention_image(self, blocks):                                 # :314-322
+        for blk in blocks:
+            self.R_i_i = rules.bmm(rules.avg_heads_record(blk.self_attn["rec"], self.B), self.R_i_i)
+
+    def handle_co_attn_self_query(self, block):                                    # :324-333
+        cam = rules.avg_heads_record(block.self_attn["rec"], self.B)
+        self.R_q_q, self.R_q_i = rules.bmm(cam, self.R_q_q), rules.bmm(cam, self.R_q_i)
+
+    def handle_co_attn_query(self, block):                                         # :335-344
+        cam_q_i = rules.avg_heads_record(block.multihead_attn["rec"], self.B)
+        self.R_q_i, _, md = rules.mm_update_batched(self.R_q_q, self.R_i_i, None, cam_q_i,
+                                                    apply_normalization=self.normalize_self_attention,
+                                                    apply_self_in_rule_10=self.apply_self_in_rule_10, nan_to_zero=True)
+        self._min_diag.append(md)
+
+    def generate_ours_abl(self, img, target_index, index=None, use_lrp=False, normalize_self_attention=False,
+                          apply_self_in_rule_10=True):                             # :346-403
+        return Generator.generate_ours(self, img, target_index, index, use_lrp, normalize_self_attention, apply_self_in_rule_10)
+
+    def generate_ours(self, *a, **k):
+        raise AttributeError("GeneratorAlbationNoAgg has generate_ours_abl only (DETR/modules/ExplanationGenerator.py:346)")

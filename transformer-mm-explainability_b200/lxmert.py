@@ -286,3 +286,63 @@ class GeneratorBaselines:
 
     def generate_partial_lrp(self, input, index=None, method_name="partial_lrp"):
         raise NotImplementedError("partial LRP needs the relprop sweep: outside the hot-path scope")
+
+
+class GeneratorOursAblationNoAggregation:
+    """lxmert/lxmert/src/ExplanationGenerator.py:215-365: ``generate_ours_no_agg`` - the updates replace the relevancy
+    matrices instead of adding to them."""
+
+    def __init__(self, model_usage: LxmertEngine, save_visualization=False):
+        if not isinstance(model_usage, LxmertEngine):
+            raise MmxError("model_usage must be a mmx_b200.LxmertEngine")
+        self.model_usage = model_usage
+        self.save_visualization = save_visualization
+
+    def _self(self, rec, lang: bool):                                            # EG:220-268
+        cam = rules.avg_heads_record(rec, self.B)
+        if lang:
+            self.R_t_t, self.R_t_i = rules.bmm(cam, self.R_t_t), rules.bmm(cam, self.R_t_i)
+        else:
+            self.R_i_i, self.R_i_t = rules.bmm(cam, self.R_i_i), rules.bmm(cam, self.R_i_t)
+
+    def _mm(self, R_ss, R_qq, R_qs, rec):                                        # EG:270-288 (rule 10 always with R_ss, R_qq)
+        cam = rules.avg_heads_record(rec, self.B)
+        sq, ss, md = rules.mm_update_batched(R_ss, R_qq, R_qs, cam, self.normalize_self_attention, True)
+        self._min_diag.append(md)
+        return sq, ss
+
+    def generate_ours_no_agg(self, input, index=None, use_lrp=False, normalize_self_attention=True, method_name="ours_no_agg"):
+        if use_lrp:
+            raise NotImplementedError("use_lrp=True needs the relprop sweep (lxmert_lrp.py:422-461): outside the hot-path scope")
+        self.use_lrp = use_lrp
+        self.normalize_self_attention = normalize_self_attention
+        m = self.model_usage
+        ids, feats, boxes = input
+        m.forward_backward(ids, feats, boxes, index)
+        B, T, I = m._shape
+        self.B = B
+        dev = m.device
+        self._min_diag: List[torch.Tensor] = []
+        self.R_t_t = torch.eye(T, device=dev).repeat(B, 1, 1)                   # EG:296-304
+        self.R_i_i = torch.eye(I, device=dev).repeat(B, 1, 1)
+        self.R_t_i = torch.zeros(B, T, I, device=dev)
+        self.R_i_t = torch.zeros(B, I, T, device=dev)
+        for b in m.layer:
+            self._self(b.att.recs[0], True)
+        for b in m.r_layers:
+            self._self(b.att.recs[0], False)
+        for b in m.x_layers[:-1]:                                                # EG:330-350
+            ti, tt = self._mm(self.R_t_t, self.R_i_i, self.R_i_t, b.cross.recs[0])
+            it, ii = self._mm(self.R_i_i, self.R_t_t, self.R_t_i, b.cross.recs[1])
+            self.R_t_i, self.R_t_t, self.R_i_t, self.R_i_i = ti, tt, it, ii
+            self._self(b.lang_self.recs[0], True)
+            self._self(b.visn_self.recs[0], False)
+        last = m.x_layers[-1]                                                    # EG:353-361: text side only
+        self.R_t_i, self.R_t_t = self._mm(self.R_t_t, self.R_i_i, self.R_i_t, last.cross.recs[0])
+        self._self(last.lang_self.recs[0], True)
+        if normalize_self_attention:
+            assert torch.stack(self._min_diag).min().item() >= 0                 # handle_residual's assert (EG:50)
+        self.R_t_t[:, 0, 0] = 0                                                  # EG:364
+        if B == 1:
+            self.R_t_t, self.R_t_i, self.R_i_i, self.R_i_t = self.R_t_t[0], self.R_t_i[0], self.R_i_i[0], self.R_i_t[0]
+        return self.R_t_t, self.R_t_i

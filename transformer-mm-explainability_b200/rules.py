@@ -215,3 +215,24 @@ def gradcam_record(rec, batch: int) -> torch.Tensor:
     gbar = torch.empty(B * H, device=A.device, dtype=torch.float32)
     check(lib().mmx_attn_gradcam(ptr(A), ptr(dA), ptr(out), ptr(gbar), B, H, T, rec.S, ld, rec.S, current_stream()))
     return out
+
+
+def minmax_normalize(maps: torch.Tensor) -> torch.Tensor:
+    """(x - x.min()) / (x.max() - x.min()) per leading-dim map (VisualBERT ExplanationGenerator.py:203,
+    DETR/mask_generator.py:115-121)."""
+    x = _prep(maps)
+    out = torch.empty_like(x)
+    B = x.shape[0]
+    check(lib().mmx_minmax_normalize(ptr(x), ptr(out), B, x.numel() // max(B, 1), current_stream()))
+    return out
+
+
+def bmm(cam: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
+    """Batched ``torch.matmul(cam, R)`` ([B,T,S] x [B,S,Q]) on the rule GEMM kernel: the un-aggregated update of the
+    no-aggregation ablations (``self.R_i_i = torch.matmul(cam, self.R_i_i)``, DETR/modules/ExplanationGenerator.py:323)."""
+    A, Bm = _prep(cam), _prep(R)
+    B, T, S = A.shape
+    Q = Bm.shape[-1]
+    out = torch.empty(B, T, Q, device=A.device, dtype=torch.float32)
+    check(lib().mmx_bmm_add(ptr(A), S, T * S, 0, ptr(Bm), Q, S * Q, None, 0, 0, ptr(out), Q, T * Q, B, T, Q, S, current_stream()))
+    return out
