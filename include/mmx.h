@@ -112,6 +112,12 @@ int mmx_rollout(const float* mats, int L, int B, int S, int start_layer, int nor
  * (DETR/mask_generator.py:115-121).  A constant map yields NaN, as in the reference. */
 int mmx_minmax_normalize(const float* X, float* Y, int B, long long n, void* stream);
 
+/* Otsu masks for B relevance maps of n floats (the step right after the path in the DETR segmentation driver):
+ * masks[b] = 255 where uint8((cam - min) / (max - min) * 255) > otsu_threshold else 0, thresholds[b] (optional) = the
+ * threshold.  Replaces DETR/mask_generator.py:115-121 (`cv2.threshold(..., THRESH_BINARY + THRESH_OTSU)` on the CPU with
+ * a device->host->device round trip per query); bit-identical to OpenCV's getThreshVal_Otsu_8u. */
+int mmx_otsu_masks(const float* cams, float* masks, int* thresholds, int B, int n, void* stream);
+
 /* Generic batched C[b] = beta_src[b] + op(A[b]) * B[b]  (fp32, used by the rule entry points above; exported
  * for the host-side generators).  transA: 0 = A is [M,K], 1 = A is stored [K,M].  add may be NULL. */
 int mmx_bmm_add(const float* A, int lda, long long strideA, int transA, const float* Bm, int ldb, long long strideB,

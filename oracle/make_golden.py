@@ -142,6 +142,35 @@ def golden_lxmert():
     print("wrote lxmert_tiny", out["Rtt.n1s1"].shape, out["Rti.n1s1"].shape)
 
 
+def golden_otsu():
+    """cv2.threshold(THRESH_BINARY + THRESH_OTSU) itself on seeded maps, through the exact expression of
+    DETR/mask_generator.py:115-121."""
+    import cv2
+    rng = np.random.default_rng(0)
+    maps, n = [], 625
+    for t in range(48):
+        kind = t % 4
+        if kind == 0:
+            x = rng.random(n)
+        elif kind == 1:
+            x = rng.random(n) ** 6
+        elif kind == 2:
+            x = np.concatenate([rng.normal(0.2, 0.05, n // 2), rng.normal(0.8, 0.1, n - n // 2)])
+        else:
+            x = rng.integers(0, 3, n).astype(np.float64)
+        maps.append(x.astype(np.float32))
+    cams = torch.tensor(np.stack(maps))
+    masks, ths = [], []
+    for cam in cams:
+        c = (cam - cam.min()) / (cam.max() - cam.min()) * 255
+        img = c.reshape(25, 25).data.cpu().numpy().astype(np.uint8)
+        ret, th = cv2.threshold(img, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        masks.append(th.reshape(-1).astype(np.float32)); ths.append(int(ret))
+    np.savez_compressed(os.path.join(OUT, "otsu.npz"), cams=cams.numpy(), masks=np.stack(masks), thresholds=np.array(ths),
+                        cv2_version=np.array(cv2.__version__))
+    print("wrote otsu", len(ths), "cv2", cv2.__version__)
+
+
 def golden_visualbert():
     from . import visualbert_oracle as vo, ref_visualbert
     cfg = vo.VISUALBERT_TINY
@@ -165,6 +194,9 @@ def main():
     if "--visualbert" in argv:
         golden_visualbert()
         return
+    if "--otsu" in argv:
+        golden_otsu()
+        return
     if "--only-new" in argv:
         golden_detr()
         golden_lxmert()
@@ -177,6 +209,7 @@ def main():
     golden_detr()
     golden_lxmert()
     golden_visualbert()
+    golden_otsu()
 
 
 if __name__ == "__main__":

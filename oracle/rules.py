@@ -83,3 +83,50 @@ def compute_rollout_attention(all_layer_matrices, start_layer=0, normalize=True)
     for i in range(start_layer + 1, len(mats)):
         joint = mats[i].matmul(joint)
     return joint
+
+
+def otsu_threshold_u8(img) -> int:
+    """Otsu's threshold of a uint8 image as OpenCV computes it for ``cv2.threshold(..., THRESH_BINARY + THRESH_OTSU)``
+    (DETR/mask_generator.py:119).  OpenCV is a third-party dependency (reference pin: opencv_python == 3.4.2.17,
+    requirements.txt:6; 4.13.0 in this image), absent from the reference tree, so its published algorithm
+    (imgproc/thresh.cpp ``getThreshVal_Otsu_8u``) is restated: 256-bin histogram, one pass over the bins in double
+    precision maximising the between-class variance q1*q2*(mu1-mu2)^2, first maximum wins, bins with a class weight
+    below FLT_EPSILON skipped.  Pinned against cv2 itself in tests/golden/otsu.npz (oracle/make_golden.py)."""
+    import numpy as np
+    img = np.asarray(img, dtype=np.uint8).reshape(-1)
+    h = np.bincount(img, minlength=256).astype(np.float64)
+    scale = 1.0 / img.size
+    mu = 0.0
+    for i in range(256):
+        mu += i * h[i]
+    mu *= scale
+    mu1 = q1 = max_sigma = 0.0
+    max_val = 0
+    eps = float(np.finfo(np.float32).eps)
+    for i in range(256):
+        p_i = h[i] * scale
+        mu1 *= q1
+        q1 += p_i
+        q2 = 1.0 - q1
+        if min(q1, q2) < eps or max(q1, q2) > 1.0 - eps:
+            continue
+        mu1 = (mu1 + i * p_i) / q1
+        mu2 = (mu - q1 * mu1) / q2
+        sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2)
+        if sigma > max_sigma:
+            max_sigma, max_val = sigma, i
+    return max_val
+
+
+def otsu_masks(cams: torch.Tensor):
+    """The mask step of ``MaskGenerator.get_panoptic`` (DETR/mask_generator.py:115-121) for a batch of maps [B, n]:
+    ``(cam - min) / (max - min) * 255`` -> uint8 (truncation) -> Otsu -> ``255 where pixel > threshold else 0``.
+    Returns (masks [B,n] float32, thresholds [B] int64)."""
+    import numpy as np
+    masks, ths = [], []
+    for cam in cams.float():
+        q = ((cam - cam.min()) / (cam.max() - cam.min()) * 255).numpy().astype(np.uint8)
+        t = otsu_threshold_u8(q)
+        masks.append(torch.from_numpy(np.where(q > t, 255, 0).astype(np.float32)))
+        ths.append(t)
+    return torch.stack(masks), torch.tensor(ths)

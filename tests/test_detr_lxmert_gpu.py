@@ -199,3 +199,48 @@ def test_lxmert_ablation_no_agg_golden(golden_dir):
     assert rel_err(rtt, g["abl.noagg.Rtt"]) < ABL_TOL and rel_err(rti, g["abl.noagg.Rti"]) < ABL_TOL
     with pytest.raises(AssertionError):
         gen.generate_ours_no_agg((ids, feats, boxes))   # default normalize_self_attention=True asserts in the reference too
+
+
+def test_otsu_masks_bit_exact(golden_dir):
+    """mmx_otsu_masks vs cv2.threshold(THRESH_BINARY + THRESH_OTSU) outputs (golden) - integer / byte work: bit-exact."""
+    import mmx_b200
+    g = np.load(os.path.join(golden_dir, "otsu.npz"))
+    masks, thr = mmx_b200.otsu_masks(torch.from_numpy(g["cams"]).cuda())
+    assert np.array_equal(thr.cpu().numpy(), g["thresholds"])
+    assert np.array_equal(masks.cpu().numpy(), g["masks"])
+    # ragged sizes and a large map against the oracle
+    from oracle import rules as R
+    gen = torch.Generator().manual_seed(3)
+    for n in (1, 2, 7, 255, 256, 850, 20000):
+        x = torch.rand(5, n, generator=gen) ** 3
+        if n == 1:
+            continue                                        # a constant map is 0/0 in the reference too
+        m, t = mmx_b200.otsu_masks(x.cuda())
+        om, ot = R.otsu_masks(x)
+        assert np.array_equal(t.cpu().numpy(), ot.numpy()) and np.array_equal(m.cpu().numpy(), om.numpy()), n
+
+
+@pytest.mark.parametrize("method", ["ours_no_lrp", "ablation_no_self_in_10", "raw_attn", "rollout"])
+def test_detr_mask_generator(golden_dir, method):
+    """MaskGenerator.get_masks: all kept queries of one image in one batch == the per-query reference maps (golden) pushed
+    through the oracle's Otsu step."""
+    import mmx_b200
+    from oracle import rules as R
+    g = np.load(os.path.join(golden_dir, "detr_tiny.npz"))
+    eng = mmx_b200.DetrEngine(_sd(g), nhead=do.DETR_TINY.nhead, device="cuda:0")
+    mg = mmx_b200.MaskGenerator(eng)
+    src, pos = torch.from_numpy(g["src"])[:1], torch.from_numpy(g["pos"])[:1]
+    queries = torch.tensor([0, 2, 3])
+    masks, thr, cams = mg.get_masks((src.cuda(), pos.cuda()), queries, method)
+    assert masks.shape == (3, src.shape[-2], src.shape[-1])
+    # per-query oracle maps of the same image
+    kw = {"ours_no_lrp": {}, "ablation_no_self_in_10": {"apply_self_in_rule_10": False}}
+    if method in kw:
+        ref = do.generate_ours(_sd(g), do.DETR_TINY, src.expand(3, -1, -1, -1), pos.expand(3, -1, -1, -1), queries, **kw[method])
+        assert rel_err(cams, ref) < TOL
+    om, ot = R.otsu_masks(cams.cpu())
+    assert np.array_equal(thr.cpu().numpy(), ot.numpy())
+    assert np.array_equal(masks.reshape(3, -1).cpu().numpy(), om.numpy())
+    assert mg.get_masks((src.cuda(), pos.cuda()), queries, "no_such_method") is None
+    with pytest.raises(NotImplementedError):
+        mg.get_masks((src.cuda(), pos.cuda()), queries, "transformer_att")

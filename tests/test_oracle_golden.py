@@ -67,3 +67,16 @@ def test_handle_residual_asserts_like_reference():
     R[1, 1] = 0.5           # diag(R - I) < 0
     with pytest.raises(AssertionError):
         orules.handle_residual(R)
+
+
+def test_otsu_oracle_matches_cv2_golden(golden_dir):
+    """The restated OpenCV Otsu + the mask expression of DETR/mask_generator.py:115-121 against cv2.threshold's own
+    outputs (tests/golden/otsu.npz, made with the cv2 of the build image), bit for bit."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import rules as R
+    g = np.load(os.path.join(golden_dir, "otsu.npz"))
+    masks, ths = R.otsu_masks(torch.from_numpy(g["cams"]))
+    assert np.array_equal(ths.numpy(), g["thresholds"])
+    assert np.array_equal(masks.numpy(), g["masks"])

@@ -374,6 +374,60 @@ __global__ void __launch_bounds__(256) minmax_normalize_kernel(const float* __re
   for (long long i = threadIdx.x; i < n; i += blockDim.x) y[i] = (x[i] - mn) / d;
 }
 
+// Otsu mask of one map per CTA (DETR/mask_generator.py:115-121): min-max -> *255 -> uint8 (truncation) -> 256-bin
+// histogram (shared-memory integer atomics: order-independent) -> OpenCV's getThreshVal_Otsu_8u scan in double by one
+// thread (256 steps, the same operation order as the CPU library so the threshold is bit-identical) -> 0 / 255.
+__global__ void __launch_bounds__(256) otsu_mask_kernel(const float* __restrict__ X, float* __restrict__ M,
+                                                       int* __restrict__ thresholds, int n) {
+  const float* x = X + (long long)blockIdx.x * n;
+  float* m = M + (long long)blockIdx.x * n;
+  __shared__ float smn[8], smx[8];
+  __shared__ int hist[256];
+  __shared__ int s_thr;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = x[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  mn = -warp_max(-mn); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  mn = smn[0]; mx = smx[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+  const float d = mx - mn;
+  auto quant = [&](float v) -> int {                       // ((v - min) / (max - min)) * 255 in fp32, then astype(uint8)
+    const float q = __fmul_rn(__fdiv_rn(__fsub_rn(v, mn), d), 255.f);
+    return q >= 0.f ? (int)q & 255 : 0;                      // NaN (constant map) -> 0, as numpy's cast gives on x86
+  };
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[quant(x[i])], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double scale = 1.0 / (double)n;
+    double mu = 0.0;
+    for (int i = 0; i < 256; ++i) mu += (double)i * (double)hist[i];
+    mu *= scale;
+    double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
+    int max_val = 0;
+    const double eps = 1.1920928955078125e-07;              // FLT_EPSILON
+    for (int i = 0; i < 256; ++i) {
+      const double p_i = (double)hist[i] * scale;
+      mu1 = __dmul_rn(mu1, q1);
+      q1 += p_i;
+      const double q2 = 1.0 - q1;
+      if (fmin(q1, q2) < eps || fmax(q1, q2) > 1.0 - eps) continue;
+      mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+      const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+      const double diff = __dsub_rn(mu1, mu2);
+      const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), diff), diff);
+      if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    s_thr = max_val;
+    if (thresholds) thresholds[blockIdx.x] = max_val;
+  }
+  __syncthreads();
+  const int thr = s_thr;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m[i] = quant(x[i]) > thr ? 255.f : 0.f;
+}
+
 }  // namespace mmx
 
 using namespace mmx;
@@ -495,6 +549,14 @@ int mmx_minmax_normalize(const float* X, float* Y, int B, long long n, void* str
   MMX_REQUIRE(B >= 0 && n > 0, "empty map");
   if (B == 0) return 0;
   minmax_normalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(X, Y, n);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+int mmx_otsu_masks(const float* cams, float* masks, int* thresholds, int B, int n, void* stream) {
+  MMX_REQUIRE(B >= 0 && n > 0, "empty map");
+  if (B == 0) return 0;
+  otsu_mask_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cams, masks, thresholds, n);
   MMX_LAUNCH_CHECK();
   return 0;
 }

@@ -262,3 +262,50 @@ class GeneratorAlbationNoAgg(Generator):
 
     def generate_ours(self, *a, **k):
         raise AttributeError("GeneratorAlbationNoAgg has generate_ours_abl only (DETR/modules/ExplanationGenerator.py:346)")
+
+
+class MaskGenerator:
+    """The relevance -> segmentation-mask step of DETR/mask_generator.py:39-125 (``get_panoptic``): one relevance map per
+    kept query through the ``method`` switch (:93-113), then min-max / Otsu (:115-121).  The reference loops over the
+    kept queries with one forward + backward and one CPU cv2 call each; here the queries of an image form ONE batch and
+    the masks come from one kernel launch.  The visualisation / COCO panoptic bookkeeping around it is out of scope."""
+
+    METHODS = ("ours_no_lrp", "ablation_no_self_in_10", "ablation_no_aggregation", "ours_no_lrp_no_norm", "raw_attn",
+               "attn_gradcam", "rollout")
+
+    def __init__(self, model: DetrEngine):
+        self.gen = Generator(model)
+        self.abl = GeneratorAlbationNoAgg(model)
+        self.model = model
+
+    def get_masks(self, img, queries, method: str = "ours_no_lrp"):
+        """img = (src [1,C,h,w], pos [1,C,h,w]); queries: the kept query indices [K].  Returns (masks [K,h,w] in {0,255},
+        thresholds [K], cams [K,h*w])."""
+        src, pos = img
+        q = torch.as_tensor(queries).reshape(-1).long()
+        K = q.numel()
+        if K == 0:
+            raise MmxError("no queries to segment")
+        batch = (src.expand(K, *src.shape[1:]).contiguous(), pos.expand(K, *pos.shape[1:]).contiguous())
+        if method == "ours_no_lrp":
+            cam = self.gen.generate_ours(batch, q, use_lrp=False)
+        elif method == "ablation_no_self_in_10":
+            cam = self.gen.generate_ours(batch, q, use_lrp=False, apply_self_in_rule_10=False)
+        elif method == "ablation_no_aggregation":
+            cam = self.abl.generate_ours_abl(batch, q, use_lrp=False, normalize_self_attention=False)
+        elif method == "ours_no_lrp_no_norm":
+            cam = self.gen.generate_ours(batch, q, use_lrp=False, normalize_self_attention=False)
+        elif method == "raw_attn":
+            cam = self.gen.generate_raw_attn(batch, q)
+        elif method == "attn_gradcam":
+            cam = self.gen.generate_attn_gradcam(batch, q)
+        elif method == "rollout":
+            cam = self.gen.generate_rollout(batch, q)
+        elif method in ("ours_with_lrp", "transformer_att", "partial_lrp"):
+            raise NotImplementedError(f"{method} needs the relprop sweep (DETR/modules/layers.py:770-801): outside the hot-path scope")
+        else:
+            print("please provide a valid explainability method")            # mask_generator.py:111-113
+            return None
+        cam = cam.reshape(K, -1)
+        masks, thr = rules.otsu_masks(cam)
+        return masks.view(K, src.shape[-2], src.shape[-1]), thr, cam

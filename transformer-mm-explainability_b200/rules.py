@@ -236,3 +236,14 @@ def bmm(cam: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
     out = torch.empty(B, T, Q, device=A.device, dtype=torch.float32)
     check(lib().mmx_bmm_add(ptr(A), S, T * S, 0, ptr(Bm), Q, S * Q, None, 0, 0, ptr(out), Q, T * Q, B, T, Q, S, current_stream()))
     return out
+
+
+def otsu_masks(cams: torch.Tensor):
+    """Min-max -> uint8 -> Otsu -> 0/255 for a batch of maps [B, ...] (DETR/mask_generator.py:115-121).  Returns
+    (masks, same shape, float32; thresholds [B] int32)."""
+    x = _prep(cams)
+    B = x.shape[0]
+    masks = torch.empty_like(x)
+    thr = torch.empty(B, device=x.device, dtype=torch.int32)
+    check(lib().mmx_otsu_masks(ptr(x), ptr(masks), ptr(thr), B, x.numel() // max(B, 1), current_stream()))
+    return masks, thr
