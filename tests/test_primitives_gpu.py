@@ -155,7 +155,8 @@ def _attn_ref(q, k, v, H, scale, causal, key_bias, scale_scores):
 @pytest.mark.parametrize("B,H,T,S,hd,causal,bias,ss", [
     (2, 12, 50, 50, 64, 0, 0, 0), (2, 8, 77, 77, 64, 1, 0, 0), (1, 2, 8, 8, 16, 1, 0, 0), (2, 2, 17, 17, 64, 0, 0, 0),
     (2, 12, 20, 36, 64, 0, 1, 1), (2, 12, 36, 20, 64, 0, 1, 1), (1, 8, 100, 625, 32, 0, 0, 0), (1, 8, 625, 625, 32, 0, 0, 0),
-    (1, 16, 577, 577, 64, 0, 0, 0), (1, 2, 1, 1, 32, 0, 0, 0)])
+    (1, 16, 577, 577, 64, 0, 0, 0), (1, 2, 1, 1, 32, 0, 0, 0),
+    (1, 8, 100, 850, 32, 0, 0, 0), (1, 8, 850, 850, 32, 0, 0, 0)])      # DETR at 800x1066: 850 keys -> the 32-row tile variant
 def test_attention_fwd_bwd(L, B, H, T, S, hd, causal, bias, ss):
     lib, check, ptr, st = L["lib"], L["check"], L["ptr"], L["st"]
     gen = torch.Generator().manual_seed(T * 31 + S)

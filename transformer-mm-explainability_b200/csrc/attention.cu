@@ -15,9 +15,11 @@ struct Ragged {
   const int* lens = nullptr;
 };
 
-constexpr int TQ = 64;    // query rows per CTA (four m16 row blocks): one CTA covers a whole CLIP ViT-B/32 head (50 rows)
+// Query rows per CTA: TQ = 64 (four m16 row blocks, 8 warps: one CTA covers a whole CLIP ViT-B/32 head of 50 rows)
+// while the score rows fit in shared memory (S <= ~730), TQ = 32 (4 warps) beyond that (DETR at 800x1066: 850 keys).
+// A CTA has TQ/8 warps; warp w owns row block w % (TQ/16) and half w / (TQ/16) of the keys (scores) or of d (P.V).
 constexpr int TKEY = 64;  // keys per shared-memory tile
-constexpr int ATT_THREADS = 256, ATT_WARPS = ATT_THREADS / 32;
+constexpr int KV_THREADS = 256;
 
 // The three small matrix products per head (scores, P.V and their backward twins) run on the tensor cores as
 // mma.sync.m16n8k8 TF32 with the same fp32-faithful 3-pass split as the linear GEMMs (gemm_tcgen05.cu): x = hi + lo,
@@ -87,7 +89,7 @@ template <int HD>
 struct AttnSmem {
   static constexpr int LDX = HD + 4;   // [row / key][d] operands (Q, dO tiles; K, V as the scores' B operand)
   static constexpr int LDV = HD + 8;   // [key][d] operand of the P.V product
-  static size_t bytes(int S) { return sizeof(float) * ((size_t)TQ * score_ld(S) + (size_t)TQ * LDX + (size_t)TKEY * LDV); }
+  static size_t bytes(int S, int TQ) { return sizeof(float) * ((size_t)TQ * score_ld(S) + (size_t)TQ * LDX + (size_t)TKEY * LDV); }
 };
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching src
@@ -103,7 +105,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int HD, int ROWS>
 __device__ __forceinline__ void load_rows_async(const float* __restrict__ Y, int ldy, long long ybase, int r0, int limit,
                                                 float* sY, int ld) {
-  for (int e = threadIdx.x; e < ROWS * (HD / 4); e += ATT_THREADS) {
+  for (int e = threadIdx.x; e < ROWS * (HD / 4); e += blockDim.x) {
     const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
     const bool ok = r0 + r < limit;
     cp_async16(sY + r * ld + d, ok ? Y + ybase + (long long)(r0 + r) * ldy + d : Y, ok);
@@ -113,13 +115,13 @@ __device__ __forceinline__ void load_rows_async(const float* __restrict__ Y, int
 // scores[i][j] (i in the 64-row tile, j in [0,S)) = post_scale * sum_d (pre_scale * X[i][d]) * Y[j][d].  The caller has
 // issued (cp.async, committed) the X tile into sX and the FIRST key tile into sY; later key tiles stream through sY.
 // Warp w owns row block w&3 and the 32-key half w>>2 of each key tile.
-template <int HD>
+template <int HD, int MB>
 __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy, long long ybase, int S,
                                             const float* sX, float* sY, float* sP, int ldP, float pre_scale, float post_scale,
                                             int live_rows) {
   constexpr int LDX = AttnSmem<HD>::LDX;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 3) * 16, kh = (warp >> 2) * 32;
+  const int m0 = (warp % MB) * 16, kh = (warp / MB) * 32;
   for (int j0 = 0; j0 < S; j0 += TKEY) {
     if (j0 > 0) {
       __syncthreads();
@@ -166,12 +168,12 @@ __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy
 // out[i][d] = sum_j sP[i][j] * Y[j][d].  Warp w owns row block w&3 and the d half w>>2; its HD/16 accumulator
 // fragments hold rows m0+g, m0+g+8 and columns d0 + 8*nt + 2t, +1.  The caller has issued the first Y tile into sY
 // (stride LDV) with cp.async and passed a __syncthreads after the last write of sP.
-template <int HD>
+template <int HD, int MB>
 __device__ __forceinline__ void tile_pv(const float* __restrict__ Y, int ldy, long long ybase, int S, const float* sP,
                                         int ldP, float* sY, float (&out)[HD / 16][4], int live_rows) {
   constexpr int LDV = AttnSmem<HD>::LDV, NT = HD / 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 3) * 16, d0 = (warp >> 2) * (HD / 2);
+  const int m0 = (warp % MB) * 16, d0 = (warp / MB) * (HD / 2);
   float crs[NT][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
@@ -204,11 +206,11 @@ __device__ __forceinline__ void tile_pv(const float* __restrict__ Y, int ldy, lo
 }
 
 // stores the P.V fragments of tile_pv: rows i0 + m0 + g (+8), columns h*HD + d0 + 8*nt + 2t
-template <int HD>
+template <int HD, int MB>
 __device__ __forceinline__ void store_pv(float* __restrict__ O, int ldo, long long row0, int i0, int T, int h,
                                          const float (&out)[HD / 16][4], float mul) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int m0 = (warp & 3) * 16, d0 = (warp >> 2) * (HD / 2);
+  const int m0 = (warp % MB) * 16, d0 = (warp / MB) * (HD / 2);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int i = i0 + m0 + g + 8 * half;
@@ -220,12 +222,12 @@ __device__ __forceinline__ void store_pv(float* __restrict__ O, int ldo, long lo
   }
 }
 
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
+template <int HD, int TQ>
+__global__ void __launch_bounds__(TQ * 4) attention_fwd_kernel(
     const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
     const float* __restrict__ key_bias, float* __restrict__ A, int ldA, float* __restrict__ O, int ldo, int H, int T, int S,
     float scale, int flags, Ragged rg) {
-  constexpr int LDH = AttnSmem<HD>::LDX;
+  constexpr int LDH = AttnSmem<HD>::LDX, ATT_THREADS = TQ * 4, ATT_WARPS = TQ / 8, MB = TQ / 16;
   extern __shared__ float smem[];
   const int S_pad = score_ld(S);  // shared-memory stride of a score row (from the dense S, also for ragged samples)
   float* sP = smem;
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
   load_rows_async<HD, TQ>(Q, ldq, qrow0 * ldq + h * HD, i0, T, sQ, LDH);                 // Q tile and the first K tile together
   load_rows_async<HD, TKEY>(K, ldk, krow0 * ldk + h * HD, 0, S, sKV, LDH);
   cp_async_commit();
-  tile_scores<HD>(K, ldk, krow0 * ldk + h * HD, S, sQ, sKV, sP, S_pad, scale_scores ? 1.f : scale, scale_scores ? scale : 1.f,
+  tile_scores<HD, MB>(K, ldk, krow0 * ldk + h * HD, S, sQ, sKV, sP, S_pad, scale_scores ? 1.f : scale, scale_scores ? scale : 1.f,
                   T - i0);
   load_rows_async<HD, TKEY>(V, ldv, krow0 * ldv + h * HD, 0, S, sKV, AttnSmem<HD>::LDV);     // lands during the softmax
   cp_async_commit();
@@ -280,17 +282,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(
   }
   __syncthreads();
   float out[HD / 16][4];
-  tile_pv<HD>(V, ldv, krow0 * ldv + h * HD, S, sP, S_pad, sKV, out, T - i0);
-  store_pv<HD>(O, ldo, qrow0, i0, T, h, out, 1.f);
+  tile_pv<HD, MB>(V, ldv, krow0 * ldv + h * HD, S, sP, S_pad, sKV, out, T - i0);
+  store_pv<HD, MB>(O, ldo, qrow0, i0, T, h, out, 1.f);
 }
 
 // backward, query side: dA (staged), delta, dQ
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
+template <int HD, int TQ>
+__global__ void __launch_bounds__(TQ * 4) attention_bwd_q_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
     const float* __restrict__ A, float* __restrict__ dA, int ldA, float* __restrict__ delta, float* __restrict__ dQ,
     int lddq, int H, int T, int S, float scale, Ragged rg) {
-  constexpr int LDH = AttnSmem<HD>::LDX;
+  constexpr int LDH = AttnSmem<HD>::LDX, ATT_THREADS = TQ * 4, ATT_WARPS = TQ / 8, MB = TQ / 16;
   extern __shared__ float smem[];
   const int S_pad = score_ld(S);
   float* sP = smem;
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
   load_rows_async<HD, TQ>(dO, lddo, qrow0 * lddo + h * HD, i0, T, sX, LDH);
   load_rows_async<HD, TKEY>(V, ldv, krow0 * ldv + h * HD, 0, S, sKV, LDH);
   cp_async_commit();
-  tile_scores<HD>(V, ldv, krow0 * ldv + h * HD, S, sX, sKV, sP, S_pad, 1.f, 1.f, T - i0);
+  tile_scores<HD, MB>(V, ldv, krow0 * ldv + h * HD, S, sX, sKV, sP, S_pad, 1.f, 1.f, T - i0);
   if (dQ != nullptr) {                                                                    // lands while dA is staged
     load_rows_async<HD, TKEY>(K, ldk, krow0 * ldk + h * HD, 0, S, sKV, AttnSmem<HD>::LDV);
     cp_async_commit();
@@ -339,8 +341,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
   if (dQ == nullptr) return;
   __syncthreads();
   float out[HD / 16][4];
-  tile_pv<HD>(K, ldk, krow0 * ldk + h * HD, S, sP, S_pad, sKV, out, T - i0);
-  store_pv<HD>(dQ, lddq, qrow0, i0, T, h, out, scale);
+  tile_pv<HD, MB>(K, ldk, krow0 * ldk + h * HD, S, sP, S_pad, sKV, out, T - i0);
+  store_pv<HD, MB>(dQ, lddq, qrow0, i0, T, h, out, scale);
 }
 
 // backward, key side: one CTA = 64 keys of one (b,h) (a whole CLIP ViT-B/32 head); walks the query rows in tiles of 64.
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_q_kernel(
 // Warp w owns the 16-key block w&3 and the d half w>>2 of both products.
 constexpr int KV_KEYS = 64, KV_ROWS = 64;
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
+__global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ Q, int ldq, const float* __restrict__ A,
     const float* __restrict__ dA, int ldA, const float* __restrict__ delta, float* __restrict__ dK, int lddk,
     float* __restrict__ dV, int lddv, int H, int T, int S, float scale, Ragged rg) {
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
     cp_async_commit();
     // A and dS tiles: 4 keys per 128-bit load.  Staged rows are ldA (% 4 == 0) wide and zero beyond this sample's
     // keys, so a float4 that starts below ldA is entirely readable and entirely correct.
-    for (int e = tid; e < KV_ROWS * (KV_KEYS / 4); e += ATT_THREADS) {
+    for (int e = tid; e < KV_ROWS * (KV_KEYS / 4); e += KV_THREADS) {
       const int r = e / (KV_KEYS / 4), c = (e % (KV_KEYS / 4)) * 4;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), ds = a;
       if (i0 + r < T && j0 + c < ldA) {
@@ -421,16 +423,40 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kv_kernel(
   }
 }
 
+constexpr size_t ATT_SMEM_MAX = 227 * 1024;
+
+template <int HD, int TQ>
+static int launch_fwd_tq(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const float* key_bias,
+                         float* A, int ldA, float* O, int ldo, int B, int H, int T, int S, float scale, int flags,
+                         Ragged rg, cudaStream_t st) {
+  const size_t smem = AttnSmem<HD>::bytes(S, TQ);
+  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<HD, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(T, TQ), H, B);
+  attention_fwd_kernel<HD, TQ><<<grid, TQ * 4, smem, st>>>(Q, ldq, K, ldk, V, ldv, key_bias, A, ldA, O, ldo, H, T, S, scale,
+                                                          flags, rg);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int HD>
 static int launch_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const float* key_bias,
                       float* A, int ldA, float* O, int ldo, int B, int H, int T, int S, float scale, int flags,
                       Ragged rg, cudaStream_t st) {
-  const size_t smem = AttnSmem<HD>::bytes(S);
-  MMX_REQUIRE(smem <= 227 * 1024, "sequence too long for the single-pass attention kernel");
-  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (AttnSmem<HD>::bytes(S, 64) <= ATT_SMEM_MAX)
+    return launch_fwd_tq<HD, 64>(Q, ldq, K, ldk, V, ldv, key_bias, A, ldA, O, ldo, B, H, T, S, scale, flags, rg, st);
+  MMX_REQUIRE(AttnSmem<HD>::bytes(S, 32) <= ATT_SMEM_MAX, "sequence too long for the single-pass attention kernel");
+  return launch_fwd_tq<HD, 32>(Q, ldq, K, ldk, V, ldv, key_bias, A, ldA, O, ldo, B, H, T, S, scale, flags, rg, st);
+}
+
+template <int HD, int TQ>
+static int launch_bwd_q_tq(const float* dO, int lddo, const float* K, int ldk, const float* V, int ldv, const float* A,
+                           float* dA, int ldA, float* delta, float* dQ, int lddq, int B, int H, int T, int S, float scale,
+                           Ragged rg, cudaStream_t st) {
+  const size_t smem = AttnSmem<HD>::bytes(S, TQ);
+  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<HD, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, TQ), H, B);
-  attention_fwd_kernel<HD><<<grid, ATT_THREADS, smem, st>>>(Q, ldq, K, ldk, V, ldv, key_bias, A, ldA, O, ldo, H, T, S, scale,
-                                                            flags, rg);
+  attention_bwd_q_kernel<HD, TQ><<<grid, TQ * 4, smem, st>>>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, H, T, S,
+                                                            scale, rg);
   MMX_LAUNCH_CHECK();
   return 0;
 }
@@ -439,19 +465,18 @@ template <int HD>
 static int launch_bwd(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                       const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, float* dK, int lddk, float* dV,
                       int lddv, int B, int H, int T, int S, float scale, Ragged rg, cudaStream_t st) {
-  const size_t smem = AttnSmem<HD>::bytes(S);
-  MMX_REQUIRE(smem <= 227 * 1024, "sequence too long for the single-pass attention kernel");
-  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(T, TQ), H, B);
-  attention_bwd_q_kernel<HD><<<grid, ATT_THREADS, smem, st>>>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, H, T, S,
-                                                              scale, rg);
-  MMX_LAUNCH_CHECK();
+  if (AttnSmem<HD>::bytes(S, 64) <= ATT_SMEM_MAX) {
+    MMX_TRY((launch_bwd_q_tq<HD, 64>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, st)));
+  } else {
+    MMX_REQUIRE(AttnSmem<HD>::bytes(S, 32) <= ATT_SMEM_MAX, "sequence too long for the single-pass attention kernel");
+    MMX_TRY((launch_bwd_q_tq<HD, 32>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, st)));
+  }
   if (dQ == nullptr) return 0;
   const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 8) + 2 * KV_ROWS * (KV_KEYS + 8));
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   dim3 grid2(cdiv(S, KV_KEYS), H, B);
-  attention_bwd_kv_kernel<HD><<<grid2, ATT_THREADS, smem2, st>>>(dO, lddo, Q, ldq, A, dA, ldA, delta, dK, lddk, dV, lddv, H,
-                                                                 T, S, scale, rg);
+  attention_bwd_kv_kernel<HD><<<grid2, KV_THREADS, smem2, st>>>(dO, lddo, Q, ldq, A, dA, ldA, delta, dK, lddk, dV, lddv, H,
+                                                                T, S, scale, rg);
   MMX_LAUNCH_CHECK();
   return 0;
 }
