@@ -118,6 +118,11 @@ int mmx_minmax_normalize(const float* X, float* Y, int B, long long n, void* str
  * a device->host->device round trip per query); bit-identical to OpenCV's getThreshVal_Otsu_8u. */
 int mmx_otsu_masks(const float* cams, float* masks, int* thresholds, int B, int n, void* stream);
 
+/* Top-k selection for the perturbation drivers: for each of B rows of n scores, keep[b][i] = 1 for the k[b] highest
+ * scores (ties: lower index first), pos[b][i] = rank of i among the kept elements in index order, -1 when dropped.
+ * Replaces `cam.topk(k)` + host-side `sorted(...)` + gather (lxmert/lxmert/perturbation.py:110-117,160-178). */
+int mmx_topk_select(const float* scores, const int* k, int* keep, int* pos, int B, int n, void* stream);
+
 /* Generic batched C[b] = beta_src[b] + op(A[b]) * B[b]  (fp32, used by the rule entry points above; exported
  * for the host-side generators).  transA: 0 = A is [M,K], 1 = A is stored [K,M].  add may be NULL. */
 int mmx_bmm_add(const float* A, int lda, long long strideA, int transA, const float* Bm, int ldb, long long strideB,

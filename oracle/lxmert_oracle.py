@@ -247,3 +247,38 @@ def generate_ours_no_agg(sd, cfg: LxmertConfig, ids, feats, boxes, index=None, n
         R_tt[0, 0] = 0
         Rtt.append(R_tt); Rti.append(R_ti)
     return torch.stack(Rtt), torch.stack(Rti)
+
+
+PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]      # lxmert/lxmert/perturbation.py:42
+
+
+def perturbation_image(sd, cfg, ids, feats, boxes, cam_image, is_positive_pert=False, pert_steps=PERT_STEPS):
+    """ModelPert.perturbation_image (lxmert/lxmert/perturbation.py:85-133) on one item: per step keep the top
+    ``int((1 - step) * I)`` boxes of ``cam_image`` (gathered in topk order, like the reference) and re-run the model.
+    Returns the answer scores per step [steps, num_labels].  PARITY UNPINNED for the driver loop itself (the reference's
+    ModelPert needs the Faster-RCNN extractor, the tokenizer and COCO files); the model it calls is pinned through the
+    LXMERT goldens."""
+    cam = cam_image.reshape(-1) * (-1 if is_positive_pert else 1)
+    out = []
+    with torch.no_grad():
+        for step in pert_steps:
+            k = int((1 - step) * cam.numel())
+            _, top = cam.topk(k=k, dim=-1)
+            logits, _ = lxmert_forward(sd, cfg, ids, feats[:, top, :], boxes[:, top, :])
+            out.append(logits[0])
+    return torch.stack(out)
+
+
+def perturbation_text(sd, cfg, ids, feats, boxes, cam_text, is_positive_pert=False, pert_steps=PERT_STEPS):
+    """ModelPert.perturbation_text (perturbation.py:135-194): [CLS] / [SEP] kept, top tokens kept in sentence order."""
+    cam = cam_text.reshape(-1) * (-1 if is_positive_pert else 1)
+    out = []
+    with torch.no_grad():
+        for step in pert_steps:
+            pure = cam[1:-1]
+            k = int((1 - step) * pure.shape[0])
+            _, top = pure.topk(k=k, dim=-1)
+            idx = sorted([0, cam.shape[0] - 1] + [int(t) + 1 for t in top])
+            logits, _ = lxmert_forward(sd, cfg, ids[:, idx], feats, boxes)
+            out.append(logits[0])
+    return torch.stack(out)

@@ -44,6 +44,7 @@ _SIGS = {
     "mmx_rollout": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p]),
     "mmx_minmax_normalize": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_longlong, C.c_void_p]),
     "mmx_otsu_masks": (C.c_int, [c_float_p, c_float_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_topk_select": (C.c_int, [c_float_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mmx_bmm_add": (C.c_int, [c_float_p, C.c_int, C.c_longlong, C.c_int, c_float_p, C.c_int, C.c_longlong,
                               c_float_p, C.c_int, C.c_longlong, c_float_p, C.c_int, C.c_longlong,
                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

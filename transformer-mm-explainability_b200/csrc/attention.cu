@@ -270,13 +270,17 @@ __global__ void __launch_bounds__(TQ * 4) attention_fwd_kernel(
       mx = fmaxf(mx, v);
     }
     mx = warp_max(mx);
+    // A key whose bias is -inf is REMOVED (exp(-inf) = 0 exactly, the same bits a -10000 mask gives); a row whose keys are
+    // all removed is the softmax over an empty set: A row = 0, output 0, like the reference's empty tensors when the
+    // perturbation drivers drop every box (lxmert/lxmert/perturbation.py:110-117 at step 1.0).
+    const float mref = mx == -CUDART_INF_F ? 0.f : mx;
     float sum = 0.f;
-    for (int j = lane; j < S; j += 32) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
+    for (int j = lane; j < S; j += 32) { const float e = expf(row[j] - mref); row[j] = e; sum += e; }
     sum = warp_sum(sum);
     float* arow = A + (((long long)b * H + h) * Tm + i) * ldA;
     for (int j = lane; j < ldA; j += 32) {
       float p = 0.f;
-      if (j < S) { p = row[j] / sum; row[j] = p; }
+      if (j < S) { p = sum > 0.f ? row[j] / sum : 0.f; row[j] = p; }
       arow[j] = p;
     }
   }

@@ -428,6 +428,34 @@ __global__ void __launch_bounds__(256) otsu_mask_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < n; i += blockDim.x) m[i] = quant(x[i]) > thr ? 255.f : 0.f;
 }
 
+// Top-k selection by rank for the perturbation drivers (lxmert/lxmert/perturbation.py:110-113,160-172: `cam.topk(k)` then
+// gather): keep[i] = 1 if fewer than k elements beat element i (greater score, or equal score and lower index),
+// pos[i] = number of kept elements before i in INDEX order (the compacted position after the reference's `sorted`), or -1.
+// One CTA per row; n <= 4096.
+__global__ void __launch_bounds__(256) topk_select_kernel(const float* __restrict__ scores, int n, const int* __restrict__ k,
+                                                         int* __restrict__ keep, int* __restrict__ pos) {
+  extern __shared__ float sh[];
+  float* sv = sh;
+  int* sk = reinterpret_cast<int*>(sh + n);
+  const float* x = scores + (long long)blockIdx.x * n;
+  const int kk = k[blockIdx.x];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sv[i] = x[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = sv[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (sv[j] > v) || (sv[j] == v && j < i);
+    sk[i] = rank < kk;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int before = 0;
+    for (int j = 0; j < i; ++j) before += sk[j];
+    keep[(long long)blockIdx.x * n + i] = sk[i];
+    pos[(long long)blockIdx.x * n + i] = sk[i] ? before : -1;
+  }
+}
+
 }  // namespace mmx
 
 using namespace mmx;
@@ -557,6 +585,14 @@ int mmx_otsu_masks(const float* cams, float* masks, int* thresholds, int B, int 
   MMX_REQUIRE(B >= 0 && n > 0, "empty map");
   if (B == 0) return 0;
   otsu_mask_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cams, masks, thresholds, n);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+int mmx_topk_select(const float* scores, const int* k, int* keep, int* pos, int B, int n, void* stream) {
+  MMX_REQUIRE(B >= 0 && n > 0 && n <= 4096, "row length must be in 1..4096");
+  if (B == 0) return 0;
+  topk_select_kernel<<<B, 256, (size_t)n * 8, (cudaStream_t)stream>>>(scores, n, k, keep, pos);
   MMX_LAUNCH_CHECK();
   return 0;
 }

@@ -106,7 +106,7 @@ class LxmertEngine:
         return tape.layernorm(tape.add(tape.linear(tape.linear(x, f.fc1, ACT_GELU), f.fc2), x), *f.ln, EPS)
 
     def forward_backward(self, input_ids, visual_feats, visual_pos, index=None, attention_mask=None,
-                         visual_attention_mask=None, backward: bool = True):
+                         visual_attention_mask=None, backward: bool = True, lang_key_bias=None, vis_key_bias=None):
         """Forward staging every A (29 attention maps for the base model), one-hot on the answer logit, backward
         staging every dA.  input_ids [B,T] int, visual_feats [B,I,F], visual_pos [B,I,4]."""
         dev, l = self.device, lib()
@@ -120,6 +120,10 @@ class LxmertEngine:
             tape = Tape(dev)
             bias_t = None if attention_mask is None else ((1.0 - _f32(attention_mask, dev)) * -10000.0).contiguous()
             bias_i = None if visual_attention_mask is None else ((1.0 - _f32(visual_attention_mask, dev)) * -10000.0).contiguous()
+            if lang_key_bias is not None:          # additive key biases given directly ([B,T] / [B,I]); -inf removes a key
+                bias_t = _f32(lang_key_bias, dev)
+            if vis_key_bias is not None:
+                bias_i = _f32(vis_key_bias, dev)
             # embeddings: (type + position) + word, LayerNorm  (lxmert_lrp.py:285-310).  No gradient is needed below
             # the first attention layer, so these run outside the tape.
             emb = torch.empty(B * T, Hd, device=dev)
