@@ -256,7 +256,7 @@ def main():
     tms, tfl, nl = C.c_double(), C.c_double(), C.c_int()
     lib.mmx_profile_gemm_report(C.byref(tms), C.byref(tfl), C.byref(nl))
     gemm_tflops = tfl.value / (tms.value * 1e-3) / 1e12 if tms.value > 0 else 0.0
-    roofline = {"kernel": "transformer GEMMs (" + {0: "fp32 FFMA", 1: "tcgen05 3xTF32, 1 CTA/tile", 2: "tcgen05 3xTF32, cta_group::2"}[gemm_backend] + ")",
+    roofline = {"kernel": "transformer GEMMs (" + {0: "fp32 FFMA", 1: "tcgen05 3xTF32, 1 CTA/tile, tile width 128/144/160 per launch", 2: "tcgen05 3xTF32, cta_group::2"}[gemm_backend] + ")",
                 "bound": "tensor", "achieved": gemm_tflops, "peak": tf_sust, "unit": "TFLOP/s",
                 "frac": gemm_tflops / tf_sust, "traffic": None,
                 "traffic_captured": {"launch": "M=3200 N=2304 K=768 (vision QKV)", "dram_bytes": 17351168,

@@ -192,3 +192,47 @@ def generate_attn_gradcam(sd, cfg, inp, index=None, dtype=torch.float32):
     cam = (st[-1].detach() * G.mean(dim=[2, 3], keepdim=True)).mean(1).clamp(min=0)
     mn, mx = cam.amin(dim=(1, 2), keepdim=True), cam.amax(dim=(1, 2), keepdim=True)
     return _cls_row((cam - mn) / (mx - mn), inp)
+
+
+PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]      # VisualBERT/mmf/trainers/core/evaluation_loop.py:96
+
+
+def perturbation_image(sd, cfg, inp, method_cam, is_positive_pert=False, steps=PERT_STEPS):
+    """evaluation_loop.py:105-124 on one sample: per step keep the top ``int((1-step)*V)`` visual tokens (gathered in topk
+    order) and re-run the model; returns the scores per step.  PARITY UNPINNED for the loop itself (the mmf trainer and
+    dataset cannot be imported here); the model it calls is pinned through the VisualBERT goldens."""
+    cam = method_cam.reshape(-1) * (-1 if is_positive_pert else 1)
+    T = int(inp["input_mask"].sum())
+    bbox_scores = cam[T:]
+    out = []
+    with torch.no_grad():
+        for step in steps:
+            k = int((1 - step) * bbox_scores.numel())
+            _, top = bbox_scores.topk(k=k, dim=-1)
+            cur = dict(inp)
+            cur["visual_embeddings"] = inp["visual_embeddings"][:, top, :]
+            cur["visual_embeddings_type"] = inp["visual_embeddings_type"][:, top]
+            cur["attention_mask"] = torch.cat((inp["attention_mask"][:, :T], inp["attention_mask"][:, T:][:, top]), dim=1)
+            out.append(visualbert_forward(sd, cfg, cur)[0][0])
+    return torch.stack(out)
+
+
+def perturbation_text(sd, cfg, inp, method_cam, is_positive_pert=False, steps=PERT_STEPS):
+    """evaluation_loop.py:126-160: tokens 1..cls_index-1 ranked; token 0, cls_index and cls_index+1 always kept, order kept."""
+    cam = method_cam.reshape(-1) * (-1 if is_positive_pert else 1)
+    T = int(inp["input_mask"].sum())
+    cls_index = T - 2
+    text_scores = cam[1:cls_index]
+    out = []
+    with torch.no_grad():
+        for step in steps:
+            k = int((1 - step) * text_scores.numel())
+            _, top = text_scores.topk(k=k, dim=-1)
+            idx = sorted([0, cls_index, cls_index + 1] + [int(t) + 1 for t in top])
+            cur = dict(inp)
+            cur["input_ids"] = inp["input_ids"][:, idx]
+            cur["token_type_ids"] = inp["token_type_ids"][:, idx]
+            cur["input_mask"] = inp["input_mask"][:, :len(idx)]
+            cur["attention_mask"] = torch.cat((inp["attention_mask"][:, :len(idx)], inp["attention_mask"][:, T:]), dim=1)
+            out.append(visualbert_forward(sd, cfg, cur)[0][0])
+    return torch.stack(out)

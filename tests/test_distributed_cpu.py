@@ -41,6 +41,11 @@ def _worker(rank, world, port, B, repeat, q):
     rt, ri = interpret_sharded(_fake_interpret, images, tokens, 2, 3)
     ref_t, ref_i = _fake_interpret(images, tokens, 2, 3)
     ok = torch.equal(rt, ref_t) and torch.equal(ri, ref_i)
+    # the generic unit form used by the DETR / LXMERT / VisualBERT / ViT generators
+    from mmx_b200.distributed import map_sharded
+    units = torch.arange(B * 3, dtype=torch.float32).reshape(B, 3)
+    got = map_sharded(lambda lo, hi: units[lo:hi] * 2 + 1, B)
+    ok = ok and torch.equal(got, units * 2 + 1)
     lo, hi = shard_range(B, rank, world)
     q.put((rank, ok, lo, hi))
     dist.destroy_process_group()

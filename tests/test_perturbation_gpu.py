@@ -80,3 +80,24 @@ def test_lxmert_perturbation_vs_oracle(modality, positive):
     assert torch.isfinite(pert.scores).all()
     assert rel_err(pert.scores, ref) < TOL
     assert torch.equal(ans.cpu(), ref.argmax(-1))
+
+
+@pytest.mark.parametrize("positive", [False, True])
+@pytest.mark.parametrize("modality", ["image", "text"])
+def test_visualbert_perturbation_vs_oracle(modality, positive):
+    import mmx_b200
+    from oracle import visualbert_oracle as vo
+    cfg = vo.VISUALBERT_TINY
+    sd = vo.init_state_dict(cfg, 3)
+    inp = vo.synthetic_inputs(cfg, 1, 10, 9, seed=8)
+    inp["attention_mask"][0, -1] = 0                                        # one padded box (image_mask)
+    eng = mmx_b200.VisualBertEngine(sd, num_heads=cfg.heads, device="cuda:0")
+    dinp = {k: v.cuda() for k, v in inp.items()}
+    cam = mmx_b200.SelfAttentionGenerator(eng).generate_ours(dinp)           # [1, T+V]
+    pert = mmx_b200.VisualBertPerturbation(eng)
+    fn = "perturbation_" + modality
+    ans = getattr(pert, fn)(dinp, cam, positive)
+    ref = getattr(vo, fn)(sd, cfg, inp, cam.cpu(), positive)
+    assert pert.scores.shape == ref.shape == (len(vo.PERT_STEPS), cfg.num_labels)
+    assert rel_err(pert.scores, ref) < TOL
+    assert torch.equal(ans.cpu(), ref.argmax(-1))

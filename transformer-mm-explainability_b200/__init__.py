@@ -18,7 +18,7 @@ from .vit import ViTEngine, generate_relevance  # noqa: F401
 from .detr import DetrEngine, Generator, GeneratorAlbationNoAgg, MaskGenerator  # noqa: F401
 from .lxmert import LxmertEngine, GeneratorOurs, GeneratorBaselines, GeneratorOursAblationNoAggregation  # noqa: F401
 from .visualbert import VisualBertEngine, SelfAttentionGenerator  # noqa: F401
-from .perturbation import LxmertPerturbation, PERT_STEPS, topk_select  # noqa: F401
+from .perturbation import LxmertPerturbation, VisualBertPerturbation, PERT_STEPS, topk_select  # noqa: F401
 
 __all__ = ["MmxError", "lib", "interpret", "ClipEngine", "ClipConfig", "avg_heads", "avg_heads_batched",
            "apply_self_attention_rules", "apply_mm_attention_rules", "apply_mm_attention_rules_lxmert",

@@ -59,3 +59,19 @@ def interpret_sharded(interpret_fn: Callable, images: torch.Tensor, tokens: torc
     if world == 1:
         return rt, ri
     return all_gather_maps(rt, B, group), all_gather_maps(ri, B, group)
+
+
+def map_sharded(unit_fn: Callable[[int, int], torch.Tensor], n_units: int, group=None) -> torch.Tensor:
+    """Generic form for the other generators (DETR (image, query) pairs, LXMERT / VisualBERT questions, ViT images:
+    SURVEY.md §8e "independent by construction"): rank r calls ``unit_fn(lo, hi)`` -> maps ``[hi-lo, ...]`` for its
+    contiguous slice of ``n_units`` and every rank receives all ``[n_units, ...]`` maps through the one all-gather."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_range(n_units, rank, world)
+    if hi > lo:
+        local = unit_fn(lo, hi)
+    else:
+        local = unit_fn(0, 1)[:0]
+    if world == 1:
+        return local
+    return all_gather_maps(local, n_units, group)

@@ -20,6 +20,7 @@ import torch
 
 from ._lib import lib, check, ptr, current_stream, MmxError
 from .lxmert import LxmertEngine
+from .visualbert import VisualBertEngine
 
 PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]          # perturbation.py:42
 
@@ -86,4 +87,70 @@ class LxmertPerturbation:
                                                           float("-inf"))
         rep = lambda t: t.to(m.device).expand(n, *t.shape[1:]).contiguous()
         self.scores = m.forward_backward(new_ids, rep(feats), rep(boxes), backward=False, lang_key_bias=bias)
+        return self.scores.argmax(-1)
+
+
+class VisualBertPerturbation:
+    """The perturbation branch of VisualBERT/mmf/trainers/core/evaluation_loop.py:99-169 on a :class:`VisualBertEngine`:
+    ``input`` is one sample's fields (see visualbert.py), ``method_cam`` the generator's ``cls_per_token_score`` [1, T+V].
+    Image test: the visual tokens are ranked (:107-120); text test: tokens 1 .. cls_index-1 are ranked and token 0, the
+    pooled token ``cls_index`` and the final [SEP] always stay (:133-150).  All steps run as one batch."""
+
+    def __init__(self, model: VisualBertEngine, pert_steps: Sequence[float] = PERT_STEPS):
+        if not isinstance(model, VisualBertEngine):
+            raise MmxError("model must be a mmx_b200.VisualBertEngine")
+        self.model = model
+        self.pert_steps = list(pert_steps)
+        self.scores: torch.Tensor | None = None
+
+    def _base(self, input, n):
+        dev = self.model.device
+        inp = {k: v.to(dev).expand(n, *v.shape[1:]).contiguous() for k, v in input.items() if k != "key_bias"}
+        T = int(input["input_mask"].sum())
+        S = T + input["visual_embeddings"].shape[1]
+        am = input.get("attention_mask")
+        bias = torch.zeros(n, S, device=dev) if am is None else ((1.0 - am.to(dev).float()) * -10000.0).expand(n, S).contiguous()
+        return inp, bias, T
+
+    def perturbation_image(self, input, method_cam: torch.Tensor, is_positive_pert: bool = False):
+        cam = method_cam.reshape(-1) * (-1 if is_positive_pert else 1)
+        n = len(self.pert_steps)
+        inp, bias, T = self._base(input, n)
+        bbox_scores = cam[T:].contiguous()                                           # :107
+        k = [int((1 - step) * bbox_scores.numel()) for step in self.pert_steps]     # :112
+        keep, _ = topk_select(bbox_scores, k)
+        bias[:, T:] = bias[:, T:].masked_fill(keep == 0, float("-inf"))
+        inp["key_bias"] = bias
+        self.scores = self.model.forward_backward(inp, backward=False)
+        return self.scores.argmax(-1)
+
+    def perturbation_text(self, input, method_cam: torch.Tensor, is_positive_pert: bool = False):
+        cam = method_cam.reshape(-1) * (-1 if is_positive_pert else 1)
+        n = len(self.pert_steps)
+        inp, bias, T = self._base(input, n)
+        dev = self.model.device
+        cls_index = T - 2                                                            # :130
+        text_scores = cam[1:cls_index].contiguous()                                  # :134
+        text_len = text_scores.numel()
+        k = [int((1 - step) * text_len) for step in self.pert_steps]
+        keep, pos = topk_select(text_scores, k)
+        kk = torch.tensor(k, device=dev)
+        ar = torch.arange(n, device=dev)
+        kept = keep.bool()
+        rows = ar.unsqueeze(1).expand(n, text_len)
+        for name in ("input_ids", "token_type_ids"):
+            if inp.get(name) is None:
+                continue
+            src = inp[name][0].clone()
+            new = torch.zeros_like(inp[name])
+            new[:, 0] = src[0]
+            new[rows[kept], (pos[kept] + 1).long()] = src[1:cls_index].unsqueeze(0).expand(n, text_len)[kept]
+            new[ar, kk + 1] = src[cls_index]                                        # the pooled token, then [SEP] (:146-148)
+            new[ar, kk + 2] = src[cls_index + 1]
+            inp[name] = new
+        live = torch.arange(T, device=dev).unsqueeze(0) < (kk + 3).unsqueeze(1)
+        inp["input_mask"] = live.long()
+        bias[:, :T] = bias[:, :T].masked_fill(~live, float("-inf"))
+        inp["key_bias"] = bias
+        self.scores = self.model.forward_backward(inp, backward=False)
         return self.scores.argmax(-1)

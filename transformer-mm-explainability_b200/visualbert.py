@@ -92,6 +92,8 @@ class VisualBertEngine:
             check(l.mmx_add(ptr(emb), Hd, ptr(const), Hd, C.c_float(1.0), ptr(emb), Hd, B * S, Hd, current_stream()))
             am = input.get("attention_mask")
             key_bias = None if am is None else ((1.0 - _f32(am, dev)) * -10000.0).contiguous()      # visual_bert.py:85-97
+            if input.get("key_bias") is not None:      # additive key bias given directly [B, T+V]; -inf removes a key
+                key_bias = _f32(input["key_bias"], dev)
             tape = Tape(dev)
             x = tape.layernorm(Var(emb.view(B * S, Hd)), *self.emb_ln, EPS)
             scale = 1.0 / math.sqrt(Hd // H)
