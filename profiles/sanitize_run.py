@@ -42,5 +42,30 @@ mmx_b200.GeneratorBaselines(le).generate_rollout((ids.cuda(), feats.cuda(), boxe
 vcfg = vo.VIT_TINY
 ve = mmx_b200.ViTEngine(vo.init_state_dict(vcfg, 3), heads=vcfg.heads, device="cuda:0")
 mmx_b200.generate_relevance(ve, torch.randn(2, 3, vcfg.image, vcfg.image).cuda())
+# tile-width instantiations of the tcgen05 GEMM
+for bn in (128, 144, 160, 0):
+    l.mmx_set_gemm_tile_n(bn)
+    check(l.mmx_linear(ptr(A), K, ptr(W), K, ptr(b), ptr(res), N, ptr(C), N, ptr(Ca), 2, M, N, K, current_stream()))
+# VisualBERT generator + perturbation drivers, Otsu masks, min-max, top-k
+from oracle import visualbert_oracle as vbo
+vbcfg = vbo.VISUALBERT_TINY
+vinp = {k: v.cuda() for k, v in vbo.synthetic_inputs(vbcfg, 1, 8, 7, seed=2).items()}
+vbe = mmx_b200.VisualBertEngine(vbo.init_state_dict(vbcfg, 3), num_heads=vbcfg.heads, device="cuda:0")
+vgen = mmx_b200.SelfAttentionGenerator(vbe)
+cam = vgen.generate_ours(vinp); vgen.generate_rollout(vinp); vgen.generate_attn_gradcam(vinp)
+vp = mmx_b200.VisualBertPerturbation(vbe)
+vp.perturbation_image(vinp, cam); vp.perturbation_text(vinp, cam, True)
+item = (ids[:1].cuda(), feats[:1].cuda(), boxes[:1].cuda())
+rtt, rti = mmx_b200.GeneratorOurs(le).generate_ours(item, use_lrp=False)
+lp = mmx_b200.LxmertPerturbation(le)
+lp.perturbation_image(item, rti[0], rtt[0]); lp.perturbation_text(item, rti[0], rtt[0], True)
+mmx_b200.GeneratorOursAblationNoAggregation(le).generate_ours_no_agg(item, normalize_self_attention=False)
+mmx_b200.MaskGenerator(g.model).get_masks((src[:1].cuda(), pos[:1].cuda()), torch.tensor([0, 1]), "ours_no_lrp")
+mmx_b200.otsu_masks(torch.rand(3, 850, device="cuda")); mmx_b200.minmax_normalize(torch.rand(2, 77, device="cuda"))
+# long-sequence attention (32-row tile instantiation)
+q = torch.randn(1, 850, 64, device="cuda"); Aa = torch.empty(1, 2, 850, 852, device="cuda"); Oo = torch.empty(1, 850, 64, device="cuda")
+import ctypes as C
+check(l.mmx_attention_fwd(ptr(q), 64, ptr(q), 64, ptr(q), 64, None, ptr(Aa), 852, ptr(Oo), 64, 1, 2, 850, 850, 32, C.c_float(0.17), 0,
+                          current_stream()))
 torch.cuda.synchronize()
 print("sanitize_run: all kernels executed")

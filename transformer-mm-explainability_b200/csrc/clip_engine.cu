@@ -9,8 +9,17 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3 (ranges for `ncu --nvtx --nvtx-include "vision/backward/"`, Nsight Systems)
 
 namespace mmx {
+
+// Host-side NVTX range around the launches of one pipeline stage (no cost when no tool is attached).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // kernels from the other translation units
 int layernorm_fwd(const float*, int, const int*, const float*, const float*, float*, int, float*, float*, int, int, float, cudaStream_t,
@@ -326,6 +335,7 @@ int run_chunk(mmx_clip* h, const float* images, int n_images, const int32_t* tok
   MMX_CHECK_CUDA(cudaStreamWaitEvent(Tx.st, h->ev_fork, 0));
   // ---- vision tower
   {
+    NvtxRange r("vision/forward");
     const int p = c.vision_patch_size, G = h->G, Kp = 3 * p * p;
     MMX_TRY(im2col_patches(images, h->patches, n_images, c.image_resolution, p, V.st));
     GemmEpilogue e;
@@ -337,6 +347,7 @@ int run_chunk(mmx_clip* h, const float* images, int n_images, const int32_t* tok
   }
   // ---- text tower
   {
+    NvtxRange r("text/forward");
     if (Tx.ragged)
       MMX_TRY(text_embed_packed(tokens, h->tok_emb, h->pos_t, Tx.x, Tx.offs, Tx.lens, Tx.rows, Tx.total, B, Tx.S, Tx.D,
                                 c.vocab_size, Tx.st));
@@ -358,12 +369,24 @@ int run_chunk(mmx_clip* h, const float* images, int n_images, const int32_t* tok
   }
   // ---- backward + rules, towers independent again
   int rv = 0, rt = 0;
-  MMX_TRY(tower_backward(V, B, E, start_v));
-  MMX_TRY(tower_rules(V, B, start_v, &rv));
-  MMX_TRY(slice_out(V.R[rv], (long long)V.S * V.ld, V.ld, 0, 1, R_image, B, 1, V.S - 1, V.st));       // R[:,0,1:]
-  MMX_TRY(tower_backward(Tx, B, E, start_t));
-  MMX_TRY(tower_rules(Tx, B, start_t, &rt));
-  MMX_TRY(slice_out(Tx.R[rt], (long long)Tx.S * Tx.ld, Tx.ld, 0, 0, R_text, B, Tx.S, Tx.S, Tx.st));
+  {
+    NvtxRange r("vision/backward");
+    MMX_TRY(tower_backward(V, B, E, start_v));
+  }
+  {
+    NvtxRange r("vision/rules");
+    MMX_TRY(tower_rules(V, B, start_v, &rv));
+    MMX_TRY(slice_out(V.R[rv], (long long)V.S * V.ld, V.ld, 0, 1, R_image, B, 1, V.S - 1, V.st));       // R[:,0,1:]
+  }
+  {
+    NvtxRange r("text/backward");
+    MMX_TRY(tower_backward(Tx, B, E, start_t));
+  }
+  {
+    NvtxRange r("text/rules");
+    MMX_TRY(tower_rules(Tx, B, start_t, &rt));
+    MMX_TRY(slice_out(Tx.R[rt], (long long)Tx.S * Tx.ld, Tx.ld, 0, 0, R_text, B, Tx.S, Tx.S, Tx.st));
+  }
   MMX_CHECK_CUDA(cudaEventRecord(h->ev_v, V.st));
   MMX_CHECK_CUDA(cudaEventRecord(h->ev_t, Tx.st));
   MMX_CHECK_CUDA(cudaStreamWaitEvent(caller, h->ev_v, 0));
