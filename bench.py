@@ -166,7 +166,6 @@ def main():
     import torch.distributed as dist
     import mmx_b200
     from mmx_b200.distributed import all_gather_maps
-    from oracle import clip_oracle as co   # ONLY for synthetic weights/inputs and the cpu_baseline leg
 
     world = _env_int("WORLD_SIZE", 1)
     rank = _env_int("RANK", 0)
@@ -177,11 +176,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warm = max(3, args.warmup)
     B = args.batch
-    cfg = co.VIT_B32
-    sd = co.init_state_dict(cfg, seed=0)                      # identical weights on every rank (replicated)
-    eng = mmx_b200.ClipEngine(mmx_b200.ClipConfig(*cfg.ref_args()), sd, max_batch=B, device=dev)
+    cfg = mmx_b200.VIT_B32
+    sd = mmx_b200.clip_init_state_dict(cfg, seed=0)           # identical weights on every rank (replicated)
+    eng = mmx_b200.ClipEngine(cfg, sd, max_batch=B, device=dev)
     lib = mmx_b200.lib()
-    images, tokens = co.synthetic_inputs(cfg, B, seed=1234 + rank)
+    images, tokens = mmx_b200.clip_synthetic_inputs(cfg, B, seed=1234 + rank)
     images_pin, tokens_pin = images.pin_memory(), tokens.to(torch.int32).pin_memory()
     d_images, d_tokens = images.to(dev), tokens.to(dev)
     n_total = B * world
