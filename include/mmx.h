@@ -186,7 +186,10 @@ int mmx_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const 
 /* A = softmax(scale * Q K^T + mask) staged to HBM, O = A V.   Q [B,T,H*hd] (ldq), K,V [B,S,H*hd] (ldk, ldv),
  * key_bias [B,S] additive or NULL, A [B,H,T,S] row stride ldA, O [B,T,H*hd] (ldo).
  * Replaces the bmm/softmax/bmm of CLIP/clip/auxilary.py:225-252, DETR/modules/layers.py:753-762,
- * lxmert/lxmert/src/lxmert_lrp.py:398-414, including the "save A" hook sites (:247-250 / :758 / :407). */
+ * lxmert/lxmert/src/lxmert_lrp.py:398-414, including the "save A" hook sites (:247-250 / :758 / :407).
+ * hd in {16, 32, 64}; S up to ~1500 keys (score rows live in shared memory).  The products are 3xTF32 tensor-core
+ * passes (error vs fp64 ~1e-6), the softmax is fp32.  A key_bias of -inf REMOVES the key (its probability is exactly 0,
+ * the same bits a -10000 mask gives); a row whose keys are all removed gets A = 0 and O = 0 (softmax over an empty set). */
 int mmx_attention_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                       const float* key_bias, float* A, int ldA, float* O, int ldo,
                       int B, int H, int T, int S, int hd, float scale, int flags, void* stream);
