@@ -207,6 +207,39 @@ def generate_ours_abl(sd, cfg: DetrConfig, src, pos, target_index, index=None, n
     return torch.stack(out)
 
 
+def generate_ours_lrp(sd, cfg: DetrConfig, src, pos, target_index, index=None, normalize_self_attention=True,
+                      apply_self_in_rule_10=True, dtype=torch.float32):
+    """Generator.generate_ours(use_lrp=True) per sample (DETR/modules/ExplanationGenerator.py:142-195 with the
+    ``use_lrp`` branches :112-115,:122-125,:132-135): rule 5 takes the LRP relevance of A (oracle/lrp.py) instead of A."""
+    from . import lrp
+    B = src.shape[0]
+    tq = torch.as_tensor(target_index).reshape(B)
+    out = []
+    for b in range(B):
+        sdg = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd.items()}
+        s_b = src[b:b + 1].to(dtype).requires_grad_(True)
+        p_b = pos[b:b + 1].to(dtype)
+        logits, A_e, A_ds, A_dc = detr_forward(sdg, cfg, s_b, p_b)
+        cls = logits[0, tq[b], :-1].argmax(-1) if index is None else torch.as_tensor(index).reshape(B)[b]
+        grads = torch.autograd.grad(logits[0, tq[b], cls], A_e + A_ds + A_dc)
+        ne, nd = len(A_e), len(A_ds)
+        G_e, G_ds, G_dc = grads[:ne], grads[ne:ne + nd], grads[ne + nd:]
+        with torch.no_grad():
+            sdd = {k: v.detach() for k, v in sdg.items()}
+            _, enc, dec = lrp.detr_lrp_sweep(sdd, cfg, s_b.detach(), p_b, int(tq[b]), int(cls))
+            S, Q = A_e[0].shape[-1], A_ds[0].shape[-1]
+            R_ii, R_qq, R_qi = torch.eye(S, dtype=dtype), torch.eye(Q, dtype=dtype), torch.zeros(Q, S, dtype=dtype)
+            for layer, G in zip(enc, G_e):
+                R_ii = R_ii + R_.avg_heads(layer.attn.attn_cam, G) @ R_ii
+            for layer, G, Gc in zip(dec, G_ds, G_dc):
+                a_qq, a_qi = R_.apply_self_attention_rules(R_qq, R_qi, R_.avg_heads(layer.self_attn.attn_cam, G))
+                R_qq, R_qi = R_qq + a_qq, R_qi + a_qi
+                R_qi = R_qi + R_.apply_mm_attention_rules_detr(R_qq, R_ii, R_.avg_heads(layer.cross.attn_cam, Gc),
+                                                               normalize_self_attention, apply_self_in_rule_10)
+            out.append(R_qi[tq[b]])
+    return torch.stack(out)
+
+
 def synthetic_inputs(cfg: DetrConfig, B: int, h: int, w: int, seed: int = 0):
     g = torch.Generator().manual_seed(seed)
     src = torch.randn(B, cfg.d_model, h, w, generator=g)

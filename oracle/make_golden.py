@@ -114,6 +114,14 @@ def golden_detr():
             out[f"R.n{int(norm)}s{int(s10)}"] = r.numpy()
     for method in ("raw_attn", "rollout", "attn_gradcam"):          # baselines behind the same API
         out["base." + method] = ref_detr.generate_baseline(cfg, sd, src, pos, tq, method).numpy()
+    for norm in (True, False):                                   # use_lrp=True (the reference default): target for §8f-4
+        for s10 in (True, False):
+            out[f"R.lrp.n{int(norm)}s{int(s10)}"] = ref_detr.generate_ours(cfg, sd, src, pos, tq, use_lrp=True, normalize_self_attention=norm,
+                                                                         apply_self_in_rule_10=s10).numpy()
+    for name, cam in ref_detr.lrp_attn_cams(cfg, sd, src[:1], pos[:1], int(tq[0])).items():
+        out["lrp.cam." + name] = cam.numpy()                     # per-layer LRP relevance of A, sample 0 (debugging aid)
+    for name, cam in ref_detr.lrp_attn_cams(cfg, sd, src[:1], pos[:1], int(tq[0]), double=True).items():
+        out["lrp.cam64." + name] = cam.numpy()                   # the same from the reference run in float64
     out["abl.noagg"] = ref_detr.generate_ours_abl(cfg, sd, src, pos, tq).numpy()    # GeneratorAlbationNoAgg (EG:306-403)
     out["abl.noagg.s0"] = ref_detr.generate_ours_abl(cfg, sd, src, pos, tq, apply_self_in_rule_10=False).numpy()
     np.savez_compressed(os.path.join(OUT, "detr_tiny.npz"), **out)

@@ -63,8 +63,17 @@ def build(cfg, sd):
         def forward(self, ids, feats, boxes):
             emb = self.lxmert.embeddings(ids, torch.zeros_like(ids))
             vis_out, lang_out, _ = self.lxmert.encoder(emb, None, feats, boxes, None, output_attentions=False)
+            self.vis_shape = vis_out[0][-1].shape                      # lxmert_lrp.py:1677
             pooled = self.lxmert.pooler(lang_out[0][-1])
             return self.answer_head(pooled)
+
+        def relprop(self, cam, **kwargs):
+            # LxmertForQuestionAnswering.relprop (lxmert_lrp.py:1689-1693) + LxmertModel.relprop (:1253-1257): the
+            # PreTrainedModel subclasses cannot be instantiated here, their five relprop lines are restated
+            cam_lang = self.answer_head.relprop(cam, **kwargs)
+            cam_vis = torch.zeros(self.vis_shape).to(cam_lang.device)
+            cam_lang = self.lxmert.pooler.relprop(cam_lang, **kwargs)
+            return self.lxmert.encoder.relprop((cam_lang, cam_vis), **kwargs)
 
     m = QA().eval()
     missing, unexpected = m.load_state_dict(sd, strict=False)
@@ -73,7 +82,7 @@ def build(cfg, sd):
     return m, eg
 
 
-def generate_ours(cfg, sd, ids, feats, boxes, **kw):
+def generate_ours(cfg, sd, ids, feats, boxes, use_lrp=False, **kw):
     m, eg = build(cfg, sd)
     Rtt, Rti = [], []
     with rs.cuda_is_identity():
@@ -88,7 +97,7 @@ def generate_ours(cfg, sd, ids, feats, boxes, **kw):
                     out.question_answering_score = m(ids[b:b + 1], feats[b:b + 1], boxes[b:b + 1])
                     return out
             gen = eg.GeneratorOurs(Usage())
-            a, c = gen.generate_ours(None, use_lrp=False, **kw)
+            a, c = gen.generate_ours(None, use_lrp=use_lrp, **kw)
             Rtt.append(a.detach().clone()); Rti.append(c.detach().clone())
     return torch.stack(Rtt), torch.stack(Rti)
 

@@ -62,3 +62,33 @@ def test_lxmert_ablation_no_agg_oracle_golden(golden_dir):
     rtt, rti = lo.generate_ours_no_agg(_sd(g), lo.LXMERT_TINY, torch.from_numpy(g["ids"]), torch.from_numpy(g["feats"]),
                                        torch.from_numpy(g["boxes"]), normalize_self_attention=False)
     assert rel_err(rtt, g["abl.noagg.Rtt"]) < 1e-5 and rel_err(rti, g["abl.noagg.Rti"]) < 1e-5
+
+
+@pytest.mark.parametrize("norm", [True, False])
+@pytest.mark.parametrize("s10", [True, False])
+def test_detr_lrp_oracle_golden(golden_dir, norm, s10):
+    """use_lrp=True: the restated relprop sweep (oracle/lrp.py) against the reference generator's own
+    outputs.  fp32 through ~60 chained safe-divides: 1e-4 relative."""
+    g = np.load(os.path.join(golden_dir, "detr_tiny.npz"))
+    r = do.generate_ours_lrp(_sd(g), do.DETR_TINY, torch.from_numpy(g["src"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["tq"]),
+                             normalize_self_attention=norm, apply_self_in_rule_10=s10)
+    assert rel_err(r, g[f"R.lrp.n{int(norm)}s{int(s10)}"]) < 1e-4
+
+
+def test_detr_lrp_attention_relevance_golden(golden_dir):
+    """The per-layer LRP relevance of A (get_attn_cam) of sample 0.  Structure: float64 restatement vs the reference run
+    in float64 (1e-10).  fp32 vs fp32 only agrees to ~3e-4 - the sweep divides by many small numbers."""
+    from oracle import lrp
+    g = np.load(os.path.join(golden_dir, "detr_tiny.npz"))
+    src, pos, tq = torch.from_numpy(g["src"])[:1], torch.from_numpy(g["pos"])[:1], int(g["tq"][0])
+    for dtype, key, tol in ((torch.float64, "lrp.cam64.", 1e-10), (torch.float32, "lrp.cam.", 2e-3)):
+        sd = {k: v.to(dtype) for k, v in _sd(g).items()}
+        with torch.no_grad():
+            logits = do.detr_forward(sd, do.DETR_TINY, src.to(dtype), pos.to(dtype))[0]
+            cls = int(logits[0, tq, :-1].argmax())                      # the generator's class choice (EG:151-152)
+            _, enc, dec = lrp.detr_lrp_sweep(sd, do.DETR_TINY, src.to(dtype), pos.to(dtype), tq, cls)
+        for i, layer in enumerate(enc):
+            assert rel_err(layer.attn.attn_cam, g[f"{key}enc{i}"]) < tol
+        for i, layer in enumerate(dec):
+            assert rel_err(layer.self_attn.attn_cam, g[f"{key}dec{i}.self"]) < tol
+            assert rel_err(layer.cross.attn_cam, g[f"{key}dec{i}.cross"]) < tol
