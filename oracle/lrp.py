@@ -230,3 +230,184 @@ def detr_lrp_sweep(sd: Dict[str, torch.Tensor], cfg, src, pos, target_index: int
     for layer in reversed(enc):
         cam = layer.relprop(cam)
     return logits, enc, dec
+
+
+# ======================================================================================================================
+# LXMERT flavour (lxmert/lxmert/src/layers.py + lxmert_lrp.py).  Differences from DETR's layer library: Linear.relprop
+# does NOT renormalise to R.sum() (layers.py:219-242), the attention products are RelPropSimple MatMuls on [B,H,T,S]
+# tensors (layers.py:89-91), and the scores are divided by sqrt(d) after the product (a plain tensor op: relevance
+# passes through).  Reference relprop lines: LxmertAttention :422-461, LxmertAttentionOutput :479-484,
+# LxmertCrossAttentionLayer :505-509, LxmertSelfAttentionLayer :535-539, LxmertIntermediate :554-557, LxmertOutput
+# :575-580, LxmertLayer :601-606, LxmertXLayer :657-733, LxmertEncoder :855-863, LxmertPooler :886-892,
+# LxmertVisualAnswerHead :955-958, LxmertModel :1253-1257, LxmertForQuestionAnswering :1689-1693.
+# ======================================================================================================================
+def _lx_linear_relprop(R, X, W):
+    pw, nw = W.clamp(min=0), W.clamp(max=0)
+    px, nx = X.clamp(min=0), X.clamp(max=0)
+    S = safe_divide(R, F.linear(px, pw) + F.linear(nx, nw))             # alpha = 1, beta = 0: activator term only
+    S2 = safe_divide(R, F.linear(px, nw) + F.linear(nx, pw))
+    inhib = px * (S2 @ nw) + nx * (S2 @ pw)
+    return 1.0 * (px * (S @ pw) + nx * (S @ nw)) - 0.0 * inhib
+
+
+def _matmul_relprop(R, a, b):
+    """RelPropSimple on torch.matmul(a, b): returns (R_a, R_b)."""
+    S = safe_divide(R, a @ b)
+    return a * (S @ b.transpose(-1, -2)), b * (a.transpose(-1, -2) @ S)
+
+
+class _LxAttention:
+    def __init__(self, sd, p, H):
+        self.sd, self.p, self.H = sd, p, H
+
+    def _heads(self, x):
+        B, T, D = x.shape
+        return x.view(B, T, self.H, D // self.H).permute(0, 2, 1, 3)
+
+    def forward(self, hidden, context):
+        sd, p = self.sd, self.p
+        self.hidden, self.context = hidden, context
+        lin = lambda n, x: F.linear(x, sd[p + n + ".weight"], sd[p + n + ".bias"])
+        self.q, self.k, self.v = self._heads(lin("query", hidden)), self._heads(lin("key", context)), self._heads(lin("value", context))
+        hd = self.q.shape[-1]
+        self.probs = (self.q @ self.k.transpose(-1, -2) / (hd ** 0.5)).softmax(dim=-1)
+        ctx = (self.probs @ self.v).permute(0, 2, 1, 3).contiguous()
+        return ctx.view(ctx.shape[0], ctx.shape[1], -1)
+
+    def relprop(self, cam):
+        sd, p = self.sd, self.p
+        merge = lambda x: x.permute(0, 2, 1, 3).flatten(2)
+        cam = self._heads(cam)
+        cam1, cam2 = _matmul_relprop(cam, self.probs, self.v)
+        cam1, cam2 = cam1 / 2, cam2 / 2
+        self.attn_cam = cam1
+        kT = self.k.transpose(-1, -2)
+        cam_q, cam_kT = _matmul_relprop(cam1, self.q, kT)
+        cam_q, cam_kT = cam_q / 2, cam_kT / 2
+        cam_q = _lx_linear_relprop(merge(cam_q), self.hidden, sd[p + "query.weight"])
+        cam_k = _lx_linear_relprop(merge(cam_kT.transpose(-1, -2)), self.context, sd[p + "key.weight"])
+        cam_v = _lx_linear_relprop(merge(cam2), self.context, sd[p + "value.weight"])
+        return cam_q, clone_relprop((cam_k, cam_v), self.context)
+
+
+class _LxAttBlock:
+    """LxmertCrossAttentionLayer / LxmertSelfAttentionLayer: attention + (dense, +input, LayerNorm)."""
+
+    def __init__(self, sd, p_att, p_out, H):
+        self.sd, self.p_out = sd, p_out
+        self.att = _LxAttention(sd, p_att, H)
+
+    def forward(self, x, ctx):
+        sd, p = self.sd, self.p_out
+        self.x = x
+        self.ctx_out = self.att.forward(x, ctx)
+        self.dense = F.linear(self.ctx_out, sd[p + "dense.weight"], sd[p + "dense.bias"])
+        return F.layer_norm(self.dense + x, (x.shape[-1],), sd[p + "LayerNorm.weight"], sd[p + "LayerNorm.bias"], 1e-12)
+
+    def relprop(self, cam, self_attention: bool):
+        cam_dense, cam_res = add_relprop(cam, self.dense, self.x)
+        cam_out = _lx_linear_relprop(cam_dense, self.ctx_out, self.sd[self.p_out + "dense.weight"])
+        cam_hidden, cam_ctx = self.att.relprop(cam_out)
+        if self_attention:                                               # clone(input, 3): query, context, residual
+            return clone_relprop((cam_hidden, cam_ctx, cam_res), self.x)
+        return clone_relprop((cam_hidden, cam_res), self.x), cam_ctx       # clone(input, 2) + the context relevance
+
+
+class _LxFfn:
+    """LxmertIntermediate + LxmertOutput around a Clone (LxmertLayer :592-606, LxmertXLayer.output_fc :680-697)."""
+
+    def __init__(self, sd, pi, po):
+        self.sd, self.pi, self.po = sd, pi, po
+
+    def forward(self, x):
+        sd = self.sd
+        self.x = x
+        self.inter = F.gelu(F.linear(x, sd[self.pi + "dense.weight"], sd[self.pi + "dense.bias"]))
+        self.dense = F.linear(self.inter, sd[self.po + "dense.weight"], sd[self.po + "dense.bias"])
+        return F.layer_norm(self.dense + x, (x.shape[-1],), sd[self.po + "LayerNorm.weight"], sd[self.po + "LayerNorm.bias"], 1e-12)
+
+    def relprop(self, cam):
+        cam1, cam2 = add_relprop(cam, self.dense, self.x)
+        cam1 = _lx_linear_relprop(cam1, self.inter, self.sd[self.po + "dense.weight"])
+        cam1 = _lx_linear_relprop(cam1, self.x, self.sd[self.pi + "dense.weight"])
+        return clone_relprop((cam1, cam2), self.x)
+
+
+class _LxLayer:
+    def __init__(self, sd, p, H):
+        self.att = _LxAttBlock(sd, p + "attention.self.", p + "attention.output.", H)
+        self.ffn = _LxFfn(sd, p + "intermediate.", p + "output.")
+
+    def forward(self, x):
+        return self.ffn.forward(self.att.forward(x, x))
+
+    def relprop(self, cam):
+        return self.att.relprop(self.ffn.relprop(cam), True)
+
+
+class _LxXLayer:
+    def __init__(self, sd, p, H):
+        mk = lambda: _LxAttBlock(sd, p + "visual_attention.att.", p + "visual_attention.output.", H)
+        self.cross, self.cross_copy = mk(), mk()                       # the deepcopy: same weights, own activations
+        self.lang_self = _LxAttBlock(sd, p + "lang_self_att.self.", p + "lang_self_att.output.", H)
+        self.visn_self = _LxAttBlock(sd, p + "visn_self_att.self.", p + "visn_self_att.output.", H)
+        self.lang_ffn = _LxFfn(sd, p + "lang_inter.", p + "lang_output.")
+        self.visn_ffn = _LxFfn(sd, p + "visn_inter.", p + "visn_output.")
+
+    def forward(self, lang, vis):
+        self.lang_in, self.vis_in = lang, vis
+        l2, v2 = self.cross.forward(lang, vis), self.cross_copy.forward(vis, lang)
+        l3, v3 = self.lang_self.forward(l2, l2), self.visn_self.forward(v2, v2)
+        return self.lang_ffn.forward(l3), self.visn_ffn.forward(v3)
+
+    def relprop(self, cam_lang, cam_vis):
+        cam_vis, cam_lang = self.visn_ffn.relprop(cam_vis), self.lang_ffn.relprop(cam_lang)            # relprop_output
+        cam_vis, cam_lang = self.visn_self.relprop(cam_vis, True), self.lang_self.relprop(cam_lang, True)  # relprop_self
+        cam_vis2, cam_lang2 = self.cross_copy.relprop(cam_vis, False)                                   # relprop_cross
+        cam_lang1, cam_vis1 = self.cross.relprop(cam_lang, False)
+        return clone_relprop((cam_lang1, cam_lang2), self.lang_in), clone_relprop((cam_vis1, cam_vis2), self.vis_in)
+
+
+def lxmert_lrp_sweep(sd: Dict[str, torch.Tensor], cfg, ids, feats, boxes, index=None):
+    """One sample (ids [1,T], feats [1,I,F], boxes [1,I,4]).  Forward + relprop; returns (logits, dict of layer lists
+    lang / vis / x) whose attention objects carry ``probs`` and ``attn_cam`` ([1,H,T,S])."""
+    assert ids.shape[0] == 1
+    H = cfg.heads
+    e = "lxmert.embeddings."
+    T = ids.shape[1]
+    ln = lambda p, x: F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-12)
+    lin = lambda p, x: F.linear(x, sd[p + ".weight"], sd[p + ".bias"])
+    lang = ln(e + "LayerNorm", sd[e + "token_type_embeddings.weight"][torch.zeros_like(ids)]
+              + sd[e + "position_embeddings.weight"][torch.arange(T)] + sd[e + "word_embeddings.weight"][ids])
+    v = "lxmert.encoder.visn_fc."
+    vis = (ln(v + "visn_layer_norm", lin(v + "visn_fc", feats)) + ln(v + "box_layer_norm", lin(v + "box_fc", boxes))) / 2
+    L = [_LxLayer(sd, f"lxmert.encoder.layer.{i}.", H) for i in range(cfg.l_layers)]
+    R = [_LxLayer(sd, f"lxmert.encoder.r_layers.{i}.", H) for i in range(cfg.r_layers)]
+    X = [_LxXLayer(sd, f"lxmert.encoder.x_layers.{i}.", H) for i in range(cfg.x_layers)]
+    for layer in L:
+        lang = layer.forward(lang)
+    for layer in R:
+        vis = layer.forward(vis)
+    for layer in X:
+        lang, vis = layer.forward(lang, vis)
+    first = lang[:, 0]
+    pooled = torch.tanh(lin("lxmert.pooler.dense", first))
+    h_pre = lin("answer_head.logit_fc.0", pooled)
+    h = F.layer_norm(F.gelu(h_pre), (h_pre.shape[-1],), sd["answer_head.logit_fc.2.weight"], sd["answer_head.logit_fc.2.bias"], 1e-12)
+    logits = lin("answer_head.logit_fc.3", h)
+    # ---- relprop from the one-hot answer (ExplanationGenerator.py:152-165)
+    idx = int(logits.argmax(-1)) if index is None else int(index)
+    cam = torch.zeros_like(logits)
+    cam[0, idx] = 1
+    cam = _lx_linear_relprop(cam, h, sd["answer_head.logit_fc.3.weight"])
+    cam = _lx_linear_relprop(cam, pooled, sd["answer_head.logit_fc.0.weight"])      # LayerNorm / GELU pass through
+    cam = _lx_linear_relprop(cam, first, sd["lxmert.pooler.dense.weight"])          # Tanh passes through
+    cam_lang = index_select_relprop(cam.unsqueeze(1), lang, 1, torch.tensor([0]))
+    cam_vis = torch.zeros_like(vis)
+    for layer in reversed(X):
+        cam_lang, cam_vis = layer.relprop(cam_lang, cam_vis)
+    for layer in reversed(R):
+        cam_vis = layer.relprop(cam_vis)
+    for layer in reversed(L):
+        cam_lang = layer.relprop(cam_lang)
+    return logits, {"lang": L, "vis": R, "x": X}

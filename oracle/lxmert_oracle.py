@@ -249,6 +249,57 @@ def generate_ours_no_agg(sd, cfg: LxmertConfig, ids, feats, boxes, index=None, n
     return torch.stack(Rtt), torch.stack(Rti)
 
 
+def generate_ours_lrp(sd, cfg: LxmertConfig, ids, feats, boxes, index=None, normalize_self_attention=True,
+                      apply_self_in_rule_10=True, dtype=torch.float32):
+    """GeneratorOurs.generate_ours(use_lrp=True) per sample: rule 5 takes the LRP relevance of A (oracle/lrp.py) in place
+    of A (lxmert/lxmert/src/ExplanationGenerator.py:64-66,76-78,...).  Returns (R_t_t [B,T,T], R_t_i [B,T,I])."""
+    from . import lrp
+    B, T = ids.shape
+    I = feats.shape[1]
+    nx = cfg.x_layers
+    norm, s10 = normalize_self_attention, apply_self_in_rule_10
+    Rtt, Rti = [], []
+    for b in range(B):
+        sdg = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd.items()}
+        f_b, x_b = feats[b:b + 1].to(dtype), boxes[b:b + 1].to(dtype)
+        logits, st = lxmert_forward(sdg, cfg, ids[b:b + 1], f_b, x_b)
+        idx = int(logits.argmax(-1)) if index is None else int(torch.as_tensor(index).reshape(B)[b])
+        names = ["lang", "vis", "x_lang", "x_vis", "x_lang_self", "x_vis_self"]
+        flat = [a for n in names for a in st[n]]
+        grads = torch.autograd.grad(logits[0, idx], flat, allow_unused=True)
+        G, k = {}, 0
+        for n in names:
+            G[n] = grads[k:k + len(st[n])]
+            k += len(st[n])
+        with torch.no_grad():
+            _, layers = lrp.lxmert_lrp_sweep({k_: v.detach() for k_, v in sdg.items()}, cfg, ids[b:b + 1], f_b, x_b, idx)
+            cams = {"lang": [l.att.att.attn_cam for l in layers["lang"]], "vis": [l.att.att.attn_cam for l in layers["vis"]],
+                    "x_lang": [l.cross.att.attn_cam for l in layers["x"]], "x_vis": [l.cross_copy.att.attn_cam for l in layers["x"]],
+                    "x_lang_self": [l.lang_self.att.attn_cam for l in layers["x"]],
+                    "x_vis_self": [l.visn_self.att.attn_cam for l in layers["x"]]}
+            cam = lambda n, i: R_.avg_heads(cams[n][i][0], G[n][i][0])
+            R_tt, R_ii = torch.eye(T, dtype=dtype), torch.eye(I, dtype=dtype)
+            R_ti, R_it = torch.zeros(T, I, dtype=dtype), torch.zeros(I, T, dtype=dtype)
+            for i in range(cfg.l_layers):
+                a, c = R_.apply_self_attention_rules(R_tt, R_ti, cam("lang", i)); R_tt, R_ti = R_tt + a, R_ti + c
+            for i in range(cfg.r_layers):
+                a, c = R_.apply_self_attention_rules(R_ii, R_it, cam("vis", i)); R_ii, R_it = R_ii + a, R_it + c
+            for i in range(nx):
+                last = i == nx - 1
+                ti_add, tt_add = R_.apply_mm_attention_rules_lxmert(R_tt, R_ii, R_it, cam("x_lang", i), norm, s10)
+                if not last:
+                    it_add, ii_add = R_.apply_mm_attention_rules_lxmert(R_ii, R_tt, R_ti, cam("x_vis", i), norm, s10)
+                R_ti, R_tt = R_ti + ti_add, R_tt + tt_add
+                if not last:
+                    R_it, R_ii = R_it + it_add, R_ii + ii_add
+                a, c = R_.apply_self_attention_rules(R_tt, R_ti, cam("x_lang_self", i)); R_tt, R_ti = R_tt + a, R_ti + c
+                if not last:
+                    a, c = R_.apply_self_attention_rules(R_ii, R_it, cam("x_vis_self", i)); R_ii, R_it = R_ii + a, R_it + c
+            R_tt[0, 0] = 0
+        Rtt.append(R_tt); Rti.append(R_ti)
+    return torch.stack(Rtt), torch.stack(Rti)
+
+
 PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]      # lxmert/lxmert/perturbation.py:42
 
 

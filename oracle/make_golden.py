@@ -144,6 +144,11 @@ def golden_lxmert():
     for method in ("raw_attn", "rollout", "attn_gradcam"):
         rtt, rti = ref_lxmert.generate_baseline(cfg, sd, ids, feats, boxes, method)
         out[f"base.{method}.Rtt"], out[f"base.{method}.Rti"] = rtt.numpy(), rti.numpy()
+    for norm in (True, False):                                   # use_lrp=True (the reference default): target for §8f-4
+        for s10 in (True, False):
+            rtt, rti = ref_lxmert.generate_ours(cfg, sd, ids, feats, boxes, use_lrp=True, normalize_self_attention=norm,
+                                                apply_self_in_rule_10=s10)
+            out[f"Rtt.lrp.n{int(norm)}s{int(s10)}"], out[f"Rti.lrp.n{int(norm)}s{int(s10)}"] = rtt.numpy(), rti.numpy()
     rtt, rti = ref_lxmert.generate_ours_no_agg(cfg, sd, ids, feats, boxes, normalize_self_attention=False)   # EG:215-365
     out["abl.noagg.Rtt"], out["abl.noagg.Rti"] = rtt.numpy(), rti.numpy()
     np.savez_compressed(os.path.join(OUT, "lxmert_tiny.npz"), **out)

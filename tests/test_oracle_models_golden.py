@@ -92,3 +92,14 @@ def test_detr_lrp_attention_relevance_golden(golden_dir):
         for i, layer in enumerate(dec):
             assert rel_err(layer.self_attn.attn_cam, g[f"{key}dec{i}.self"]) < tol
             assert rel_err(layer.cross.attn_cam, g[f"{key}dec{i}.cross"]) < tol
+
+
+@pytest.mark.parametrize("norm", [True, False])
+@pytest.mark.parametrize("s10", [True, False])
+def test_lxmert_lrp_oracle_golden(golden_dir, norm, s10):
+    """use_lrp=True for LXMERT (the reference default of GeneratorOurs.generate_ours): oracle/lrp.py vs the reference."""
+    g = np.load(os.path.join(golden_dir, "lxmert_tiny.npz"))
+    rtt, rti = lo.generate_ours_lrp(_sd(g), lo.LXMERT_TINY, torch.from_numpy(g["ids"]), torch.from_numpy(g["feats"]),
+                                    torch.from_numpy(g["boxes"]), normalize_self_attention=norm, apply_self_in_rule_10=s10)
+    key = f"lrp.n{int(norm)}s{int(s10)}"
+    assert rel_err(rtt, g["Rtt." + key]) < 1e-5 and rel_err(rti, g["Rti." + key]) < 1e-5
