@@ -411,3 +411,93 @@ def lxmert_lrp_sweep(sd: Dict[str, torch.Tensor], cfg, ids, feats, boxes, index=
     for layer in reversed(L):
         cam_lang = layer.relprop(cam_lang)
     return logits, {"lang": L, "vis": R, "x": X}
+
+
+# ======================================================================================================================
+# VisualBERT flavour (VisualBERT/mmf/models/transformers/backends/BERT_ours.py + layers_ours.py: the same primitive
+# library as LXMERT).  BertSelfAttention.relprop :352-395 (clone of the hidden state into q / k / v, the additive mask goes
+# through Add.relprop because ``self.attention_mask`` is set), BertAttention :227-232, BertSelfOutput :412-419,
+# BertIntermediate :436-441, BertOutput :459-472, BertLayer :506-514, BertEncoder :152-156, BertPredictionHeadTransform
+# :533-537; VisualBERTForClassification.relprop VisualBERT/mmf/models/visual_bert.py:398-403.
+# ======================================================================================================================
+class _BertLayer:
+    def __init__(self, sd, p, H):
+        self.sd, self.p, self.H = sd, p, H
+        self.ffn = _LxFfn(sd, p + "intermediate.", p + "output.")
+
+    def _heads(self, x):
+        B, T, D = x.shape
+        return x.view(B, T, self.H, D // self.H).permute(0, 2, 1, 3)
+
+    def forward(self, x, mask):
+        sd, p = self.sd, self.p
+        self.x, self.mask = x, mask
+        lin = lambda n, t: F.linear(t, sd[p + n + ".weight"], sd[p + n + ".bias"])
+        self.q, self.k, self.v = (self._heads(lin("attention.self." + n, x)) for n in ("query", "key", "value"))
+        hd = self.q.shape[-1]
+        self.scores = self.q @ self.k.transpose(-1, -2) / (hd ** 0.5)
+        self.probs = (self.scores + mask).softmax(dim=-1) if mask is not None else self.scores.softmax(dim=-1)
+        ctx = (self.probs @ self.v).permute(0, 2, 1, 3).contiguous()
+        self.ctx = ctx.view(ctx.shape[0], ctx.shape[1], -1)
+        self.dense = lin("attention.output.dense", self.ctx)
+        self.att_out = F.layer_norm(self.dense + x, (x.shape[-1],), sd[p + "attention.output.LayerNorm.weight"],
+                                    sd[p + "attention.output.LayerNorm.bias"], 1e-12)
+        return self.ffn.forward(self.att_out)
+
+    def relprop(self, cam):
+        sd, p = self.sd, self.p
+        merge = lambda t: t.permute(0, 2, 1, 3).flatten(2)
+        cam = self.ffn.relprop(cam)                                       # BertLayer: output, intermediate, clone
+        cam_dense, cam_res = add_relprop(cam, self.dense, self.x)         # BertSelfOutput
+        cam_ctx = _lx_linear_relprop(cam_dense, self.ctx, sd[p + "attention.output.dense.weight"])
+        cam1, cam2 = _matmul_relprop(self._heads(cam_ctx), self.probs, self.v)
+        cam1, cam2 = cam1 / 2, cam2 / 2
+        self.attn_cam = cam1
+        if self.mask is not None:
+            cam1, _ = add_relprop(cam1, self.scores, self.mask.expand_as(self.scores))
+        cam_q, cam_kT = _matmul_relprop(cam1, self.q, self.k.transpose(-1, -2))
+        cam_q, cam_kT = cam_q / 2, cam_kT / 2
+        cam_q = _lx_linear_relprop(merge(cam_q), self.x, sd[p + "attention.self.query.weight"])
+        cam_k = _lx_linear_relprop(merge(cam_kT.transpose(-1, -2)), self.x, sd[p + "attention.self.key.weight"])
+        cam_v = _lx_linear_relprop(merge(cam2), self.x, sd[p + "attention.self.value.weight"])
+        cam_h1 = clone_relprop((cam_q, cam_k, cam_v), self.x)            # BertSelfAttention's clone(hidden, 3)
+        return clone_relprop((cam_h1, cam_res), self.x)                   # BertAttention's clone(hidden, 2)
+
+
+def visualbert_lrp_sweep(sd: Dict[str, torch.Tensor], cfg, inp, index=None):
+    """One sample (the dict of oracle/visualbert_oracle.py).  Forward + relprop; returns (scores, layers) whose
+    ``probs`` / ``attn_cam`` are [1,H,S,S]."""
+    ids, vis = inp["input_ids"], inp["visual_embeddings"]
+    assert ids.shape[0] == 1
+    T, V, H = ids.shape[1], vis.shape[1], cfg.heads
+    e = "bert.embeddings."
+    ln = lambda p, x: F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-12)
+    lin = lambda p, x: F.linear(x, sd[p + ".weight"], sd[p + ".bias"])
+    tt = inp.get("token_type_ids")
+    tt = torch.zeros_like(ids) if tt is None else tt
+    vt = inp.get("visual_embeddings_type")
+    vt = torch.zeros(1, V, dtype=torch.long) if vt is None else vt
+    text = sd[e + "word_embeddings.weight"][ids] + sd[e + "position_embeddings.weight"][torch.arange(T)] \
+        + sd[e + "token_type_embeddings.weight"][tt]
+    v_emb = lin(e + "projection", vis.to(text.dtype)) + sd[e + "position_embeddings_visual.weight"][torch.zeros(1, V, dtype=torch.long)] \
+        + sd[e + "token_type_embeddings_visual.weight"][vt]
+    x = ln(e + "LayerNorm", torch.cat((text, v_emb), dim=1))
+    am = inp.get("attention_mask")
+    mask = None if am is None else ((1.0 - am.to(x.dtype)) * -10000.0)[:, None, None, :]
+    layers = [_BertLayer(sd, f"bert.encoder.layer.{i}.", H) for i in range(cfg.layers)]
+    for layer in layers:
+        x = layer.forward(x, mask)
+    cls_index = inp["input_mask"].sum(1) - 2
+    pooled = x.index_select(1, cls_index)                                 # vqa_pooler (IndexSelect)
+    t_pre = lin("classifier.0.dense", pooled)
+    h = ln("classifier.0.LayerNorm", F.gelu(t_pre))
+    scores = lin("classifier.1", h).contiguous().view(-1, cfg.num_labels)
+    idx = int(scores.argmax(-1)) if index is None else int(index)
+    cam = torch.zeros(1, cfg.num_labels, dtype=scores.dtype)
+    cam[0, idx] = 1
+    cam = _lx_linear_relprop(cam, h, sd["classifier.1.weight"])
+    cam = _lx_linear_relprop(cam, pooled, sd["classifier.0.dense.weight"])      # LayerNorm / GELU pass through
+    cam = index_select_relprop(cam, x, 1, cls_index)
+    for layer in reversed(layers):
+        cam = layer.relprop(cam)
+    return scores, layers

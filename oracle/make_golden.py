@@ -197,6 +197,9 @@ def golden_visualbert():
         out["R." + method] = ref_visualbert.generate(cfg, sd, inp, method).numpy()
     out["R.ours.index5"] = ref_visualbert.generate(cfg, sd, inp, "ours", index=5).numpy()
     out["R.rollout.sl1"] = ref_visualbert.generate(cfg, sd, inp, "rollout", start_layer=1).numpy()
+    out["R.transformer_att"] = ref_visualbert.generate(cfg, sd, inp, "transformer_att").numpy()        # LRP-based (§8f-4 targets)
+    out["R.transformer_att.sl1"] = ref_visualbert.generate(cfg, sd, inp, "transformer_att", start_layer=1).numpy()
+    out["R.partial_lrp"] = ref_visualbert.generate(cfg, sd, inp, "partial_lrp").numpy()
     np.savez_compressed(os.path.join(OUT, "visualbert_tiny.npz"), **out)
     print("wrote visualbert_tiny", out["R.ours"].shape)
 

@@ -72,6 +72,9 @@ def build(cfg, sd):
             self.embeddings = Embeddings()
             self.encoder = bo.BertEncoder(hc)
 
+        def relprop(self, cam, **kwargs):          # VisualBERTBase.relprop, visual_bert.py:150-152
+            return self.encoder.relprop(cam, **kwargs)
+
     class ForClassification(nn.Module):     # visual_bert.py:263-396, pooler_strategy "vqa"
         def __init__(self):
             super().__init__()
@@ -89,6 +92,12 @@ def build(cfg, sd):
             pooled = self.vqa_pooler(seq, 1, idx.clone().detach())
             return self.classifier(pooled).contiguous().view(-1, cfg.num_labels)
 
+        def relprop(self, cam, **kwargs):          # VisualBERTForClassification.relprop, visual_bert.py:398-403
+            for m_ in reversed(self.classifier._modules.values()):
+                cam = m_.relprop(cam, **kwargs)
+            cam = self.vqa_pooler.relprop(cam, **kwargs)
+            return self.bert.relprop(cam, **kwargs)
+
     class Wrapper(nn.Module):               # the mmf ``VisualBERT`` model: model(input)['scores'], .model.bert.encoder.layer
         def __init__(self):
             super().__init__()
@@ -97,6 +106,9 @@ def build(cfg, sd):
         def forward(self, inp):
             return {"scores": self.model(inp)}
 
+        def relprop(self, cam, **kwargs):          # VisualBERT.relprop, visual_bert.py:615-616
+            return self.model.relprop(cam, **kwargs)
+
     w = Wrapper().eval()
     missing, unexpected = w.model.load_state_dict(sd, strict=False)
     assert not missing and not unexpected, (missing, unexpected)
@@ -104,7 +116,8 @@ def build(cfg, sd):
 
 
 def generate(cfg, sd, inp, method="ours", **kw):
-    """method in {"ours", "raw_attn", "rollout", "attn_gradcam"}: the reference generator, one sample at a time."""
+    """method in {"ours", "raw_attn", "rollout", "attn_gradcam", "transformer_att", "partial_lrp"}: the reference
+    generator, one sample at a time (the last two run the relprop sweep)."""
     w, eg = build(cfg, sd)
     outs = []
     with rs.cuda_is_identity():

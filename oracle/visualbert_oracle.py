@@ -194,6 +194,45 @@ def generate_attn_gradcam(sd, cfg, inp, index=None, dtype=torch.float32):
     return _cls_row((cam - mn) / (mx - mn), inp)
 
 
+def _lrp_per_sample(sd, cfg, inp, index, dtype):
+    """(grads of the staged A, LRP layers) per sample; the relprop sweep normalises by whole-tensor sums, so one at a time."""
+    from . import lrp
+    B = inp["input_ids"].shape[0]
+    for b in range(B):
+        one = {k: v[b:b + 1] for k, v in inp.items()}
+        sdg, one = _prep(sd, one, dtype)
+        scores, st = visualbert_forward(sdg, cfg, one)
+        idx = int(scores.argmax(-1)) if index is None else int(torch.as_tensor(index).reshape(-1).expand(B)[b])
+        grads = torch.autograd.grad(scores[0, idx], st)
+        with torch.no_grad():
+            _, layers = lrp.visualbert_lrp_sweep({k: v.detach() for k, v in sdg.items()}, cfg, one, idx)
+        yield one, grads, layers
+
+
+def generate_transformer_att(sd, cfg, inp, index=None, start_layer=0, dtype=torch.float32):
+    """SelfAttentionGenerator.generate_transformer_att (EG:24-66): rule 5 on (grad, LRP relevance of A) per layer, then the
+    non-normalising rollout (EG:5-18) from ``start_layer``."""
+    out = []
+    for one, grads, layers in _lrp_per_sample(sd, cfg, inp, index, dtype):
+        S = grads[0].shape[-1]
+        mats = [(G[0] * L.attn_cam[0]).clamp(min=0).mean(dim=0).unsqueeze(0) + torch.eye(S, dtype=dtype) for G, L in zip(grads, layers)]
+        joint = mats[start_layer]
+        for m in mats[start_layer + 1:]:
+            joint = m.bmm(joint)
+        out.append(_cls_row(joint, one)[0])
+    return torch.stack(out)
+
+
+def generate_partial_lrp(sd, cfg, inp, index=None, dtype=torch.float32):
+    """SelfAttentionGenerator.generate_partial_lrp (EG:109-131): head mean of the last layer's LRP relevance, min-max."""
+    out = []
+    for one, _, layers in _lrp_per_sample(sd, cfg, inp, index, dtype):
+        cam = layers[-1].attn_cam[0].mean(dim=0).unsqueeze(0)
+        cam = (cam - cam.min()) / (cam.max() - cam.min())
+        out.append(_cls_row(cam, one)[0])
+    return torch.stack(out)
+
+
 PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]      # VisualBERT/mmf/trainers/core/evaluation_loop.py:96
 
 

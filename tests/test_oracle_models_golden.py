@@ -103,3 +103,15 @@ def test_lxmert_lrp_oracle_golden(golden_dir, norm, s10):
                                     torch.from_numpy(g["boxes"]), normalize_self_attention=norm, apply_self_in_rule_10=s10)
     key = f"lrp.n{int(norm)}s{int(s10)}"
     assert rel_err(rtt, g["Rtt." + key]) < 1e-5 and rel_err(rti, g["Rti." + key]) < 1e-5
+
+
+@pytest.mark.parametrize("method", ["transformer_att", "transformer_att.sl1", "partial_lrp"])
+def test_visualbert_lrp_oracle_golden(golden_dir, method):
+    """The LRP-based VisualBERT methods (generate_transformer_att, generate_partial_lrp) vs the reference generator."""
+    g = np.load(os.path.join(golden_dir, "visualbert_tiny.npz"))
+    sd, inp, cfg = _sd(g), _vb_inputs(g), vo.VISUALBERT_TINY
+    if method.startswith("transformer_att"):
+        r = vo.generate_transformer_att(sd, cfg, inp, start_layer=1 if method.endswith("sl1") else 0)
+    else:
+        r = vo.generate_partial_lrp(sd, cfg, inp)
+    assert rel_err(r, g["R." + method]) < 1e-5
