@@ -240,6 +240,32 @@ def generate_ours_lrp(sd, cfg: DetrConfig, src, pos, target_index, index=None, n
     return torch.stack(out)
 
 
+def generate_lrp_baseline(sd, cfg: DetrConfig, src, pos, target_index, method: str, dtype=torch.float32):
+    """The two LRP-based baselines of the DETR Generator, per sample: ``transformer_att`` = rule 5 on the LAST decoder
+    cross-attention (grad, LRP relevance) (DETR/modules/ExplanationGenerator.py:64-108); ``partial_lrp`` = head mean of that
+    relevance, min-max normalised (:197-224).  Returns the target query's row [B, S_i]."""
+    from . import lrp
+    B = src.shape[0]
+    tq = torch.as_tensor(target_index).reshape(B)
+    out = []
+    for b in range(B):
+        sdg = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd.items()}
+        s_b, p_b = src[b:b + 1].to(dtype).requires_grad_(True), pos[b:b + 1].to(dtype)
+        logits, A_e, A_ds, A_dc = detr_forward(sdg, cfg, s_b, p_b)
+        cls = logits[0, tq[b], :-1].argmax(-1)
+        (G,) = torch.autograd.grad(logits[0, tq[b], cls], [A_dc[-1]])
+        with torch.no_grad():
+            _, enc, dec = lrp.detr_lrp_sweep({k: v.detach() for k, v in sdg.items()}, cfg, s_b.detach(), p_b, int(tq[b]), int(cls))
+            cam = dec[-1].cross.attn_cam
+            if method == "transformer_att":
+                R = R_.avg_heads(cam, G)
+            else:
+                R = cam.mean(dim=0)
+                R = (R - R.min()) / (R.max() - R.min())
+            out.append(R[tq[b]])
+    return torch.stack(out)
+
+
 def synthetic_inputs(cfg: DetrConfig, B: int, h: int, w: int, seed: int = 0):
     g = torch.Generator().manual_seed(seed)
     src = torch.randn(B, cfg.d_model, h, w, generator=g)

@@ -300,6 +300,50 @@ def generate_ours_lrp(sd, cfg: LxmertConfig, ids, feats, boxes, index=None, norm
     return torch.stack(Rtt), torch.stack(Rti)
 
 
+def generate_lrp_baseline(sd, cfg: LxmertConfig, ids, feats, boxes, method: str, index=None, dtype=torch.float32):
+    """GeneratorBaselines.generate_transformer_attr (lxmert/lxmert/src/ExplanationGenerator.py:373-460: rule 5 + rule 6
+    with the LRP relevance, self-attention layers only, R_t_i = the last cross layer's cam) and generate_partial_lrp
+    (:462-507: head means of the last layer's relevances, min-max normalised), per sample."""
+    from . import lrp
+    B, T = ids.shape
+    I = feats.shape[1]
+    Rtt, Rti = [], []
+    for b in range(B):
+        sdg = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd.items()}
+        f_b, x_b = feats[b:b + 1].to(dtype), boxes[b:b + 1].to(dtype)
+        logits, st = lxmert_forward(sdg, cfg, ids[b:b + 1], f_b, x_b)
+        idx = int(logits.argmax(-1)) if index is None else int(torch.as_tensor(index).reshape(B)[b])
+        names = ["lang", "vis", "x_lang", "x_vis", "x_lang_self", "x_vis_self"]
+        flat = [a for n in names for a in st[n]]
+        grads = torch.autograd.grad(logits[0, idx], flat, allow_unused=True)
+        G, k = {}, 0
+        for n in names:
+            G[n] = grads[k:k + len(st[n])]
+            k += len(st[n])
+        with torch.no_grad():
+            _, layers = lrp.lxmert_lrp_sweep({k_: v.detach() for k_, v in sdg.items()}, cfg, ids[b:b + 1], f_b, x_b, idx)
+            last = layers["x"][-1]
+            if method == "partial_lrp":
+                R_ti = last.cross.att.attn_cam[0].mean(dim=0)
+                R_tt = last.lang_self.att.attn_cam[0].mean(dim=0)
+                R_tt = (R_tt - R_tt.min()) / (R_tt.max() - R_tt.min())
+                R_ti = (R_ti - R_ti.min()) / (R_ti.max() - R_ti.min())
+            else:
+                R_tt, R_ii = torch.eye(T, dtype=dtype), torch.eye(I, dtype=dtype)
+                for i, l in enumerate(layers["lang"]):
+                    R_tt = R_tt + R_.avg_heads(l.att.att.attn_cam[0], G["lang"][i][0]) @ R_tt
+                for i, l in enumerate(layers["vis"]):
+                    R_ii = R_ii + R_.avg_heads(l.att.att.attn_cam[0], G["vis"][i][0]) @ R_ii
+                for i, l in enumerate(layers["x"][:-1]):
+                    R_tt = R_tt + R_.avg_heads(l.lang_self.att.attn_cam[0], G["x_lang_self"][i][0]) @ R_tt
+                    R_ii = R_ii + R_.avg_heads(l.visn_self.att.attn_cam[0], G["x_vis_self"][i][0]) @ R_ii
+                R_ti = R_.avg_heads(last.cross.att.attn_cam[0], G["x_lang"][-1][0])
+                R_tt = R_tt + R_.avg_heads(last.lang_self.att.attn_cam[0], G["x_lang_self"][-1][0]) @ R_tt
+            R_tt[0, 0] = 0
+        Rtt.append(R_tt); Rti.append(R_ti)
+    return torch.stack(Rtt), torch.stack(Rti)
+
+
 PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]      # lxmert/lxmert/perturbation.py:42
 
 

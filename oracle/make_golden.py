@@ -122,6 +122,8 @@ def golden_detr():
         out["lrp.cam." + name] = cam.numpy()                     # per-layer LRP relevance of A, sample 0 (debugging aid)
     for name, cam in ref_detr.lrp_attn_cams(cfg, sd, src[:1], pos[:1], int(tq[0]), double=True).items():
         out["lrp.cam64." + name] = cam.numpy()                   # the same from the reference run in float64
+    for method in ("transformer_att", "partial_lrp"):               # the LRP-based baselines (EG:64-108, :197-224)
+        out["base." + method] = ref_detr.generate_baseline(cfg, sd, src, pos, tq, method).numpy()
     out["abl.noagg"] = ref_detr.generate_ours_abl(cfg, sd, src, pos, tq).numpy()    # GeneratorAlbationNoAgg (EG:306-403)
     out["abl.noagg.s0"] = ref_detr.generate_ours_abl(cfg, sd, src, pos, tq, apply_self_in_rule_10=False).numpy()
     np.savez_compressed(os.path.join(OUT, "detr_tiny.npz"), **out)
@@ -149,6 +151,9 @@ def golden_lxmert():
             rtt, rti = ref_lxmert.generate_ours(cfg, sd, ids, feats, boxes, use_lrp=True, normalize_self_attention=norm,
                                                 apply_self_in_rule_10=s10)
             out[f"Rtt.lrp.n{int(norm)}s{int(s10)}"], out[f"Rti.lrp.n{int(norm)}s{int(s10)}"] = rtt.numpy(), rti.numpy()
+    for method in ("transformer_attr", "partial_lrp"):              # the LRP-based baselines (EG:373-507)
+        rtt, rti = ref_lxmert.generate_baseline(cfg, sd, ids, feats, boxes, method)
+        out[f"base.{method}.Rtt"], out[f"base.{method}.Rti"] = rtt.numpy(), rti.numpy()
     rtt, rti = ref_lxmert.generate_ours_no_agg(cfg, sd, ids, feats, boxes, normalize_self_attention=False)   # EG:215-365
     out["abl.noagg.Rtt"], out["abl.noagg.Rti"] = rtt.numpy(), rti.numpy()
     np.savez_compressed(os.path.join(OUT, "lxmert_tiny.npz"), **out)

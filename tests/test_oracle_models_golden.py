@@ -115,3 +115,19 @@ def test_visualbert_lrp_oracle_golden(golden_dir, method):
     else:
         r = vo.generate_partial_lrp(sd, cfg, inp)
     assert rel_err(r, g["R." + method]) < 1e-5
+
+
+@pytest.mark.parametrize("method", ["transformer_att", "partial_lrp"])
+def test_detr_lrp_baselines_oracle_golden(golden_dir, method):
+    g = np.load(os.path.join(golden_dir, "detr_tiny.npz"))
+    r = do.generate_lrp_baseline(_sd(g), do.DETR_TINY, torch.from_numpy(g["src"]), torch.from_numpy(g["pos"]),
+                                 torch.from_numpy(g["tq"]), method)
+    assert rel_err(r, g["base." + method]) < 2e-4          # fp32 conditioning of the relprop sweep, see oracle/lrp.py
+
+
+@pytest.mark.parametrize("method", ["transformer_attr", "partial_lrp"])
+def test_lxmert_lrp_baselines_oracle_golden(golden_dir, method):
+    g = np.load(os.path.join(golden_dir, "lxmert_tiny.npz"))
+    rtt, rti = lo.generate_lrp_baseline(_sd(g), lo.LXMERT_TINY, torch.from_numpy(g["ids"]), torch.from_numpy(g["feats"]),
+                                        torch.from_numpy(g["boxes"]), method)
+    assert rel_err(rtt, g[f"base.{method}.Rtt"]) < 1e-5 and rel_err(rti, g[f"base.{method}.Rti"]) < 1e-5
