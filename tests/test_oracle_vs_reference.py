@@ -47,3 +47,27 @@ def test_visualbert_live_reference(method):
     got = getattr(vo, "generate_" + method)(sd, cfg, inp)
     got = got[0] if isinstance(got, tuple) else got
     assert rel_err(got, ref) < 1e-5
+
+
+def test_detr_lrp_live_reference_wider():
+    """use_lrp=True at a shape other than the golden one (d=128, 4 heads, 3 encoder / 3 decoder layers, 5x6 features,
+    9 queries): the restated relprop sweep against the unmodified reference generator."""
+    from oracle import detr_oracle as do, ref_detr
+    cfg = do.DetrConfig(128, 4, 3, 3, 192, 9, 6)
+    sd = do.init_state_dict(cfg, 9)
+    src, pos, tq = do.synthetic_inputs(cfg, 2, 5, 6, seed=4)
+    ref = ref_detr.generate_ours(cfg, sd, src, pos, tq, use_lrp=True, normalize_self_attention=False)
+    got = do.generate_ours_lrp(sd, cfg, src, pos, tq, normalize_self_attention=False)
+    assert ref.abs().max() > 0
+    assert rel_err(got, ref) < 2e-4
+
+
+def test_lxmert_lrp_live_reference_wider():
+    from oracle import lxmert_oracle as lo, ref_lxmert
+    cfg = lo.LxmertConfig(hidden=128, heads=4, intermediate=160, l_layers=3, x_layers=3, r_layers=2, vocab=70, max_pos=20,
+                          feat_dim=40, pos_dim=4, num_labels=17)
+    sd = lo.init_state_dict(cfg, 6)
+    ids, feats, boxes = lo.synthetic_inputs(cfg, 2, 9, 7, seed=3)
+    rtt, rti = ref_lxmert.generate_ours(cfg, sd, ids, feats, boxes, use_lrp=True)
+    gtt, gti = lo.generate_ours_lrp(sd, cfg, ids, feats, boxes)
+    assert rel_err(gtt, rtt) < 1e-5 and rel_err(gti, rti) < 1e-5
