@@ -38,3 +38,14 @@ def test_reference_arm_under_torchrun_prints_once():
     assert r.returncode == 0, r.stderr[-2000:]
     lines = _json_lines(r.stdout)
     assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2
+
+
+def test_gpu_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a machine without a GPU the product arm must die with an error, not print a number."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "0"], cwd=ROOT, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode != 0 and not _json_lines(r.stdout)
