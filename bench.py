@@ -246,7 +246,7 @@ def main():
 
     # ---- roofline of the dominant kernel (the transformer GEMMs), CUDA events per launch inside the pipeline
     hbm_peak, tf_burst, tf_sust, peak_src = _peaks()
-    gemm_backend = lib.mmx_set_gemm_backend(int(os.environ.get('MMX_GEMM_BACKEND', '1')))
+    gemm_backend = lib.mmx_set_gemm_backend(int(os.environ.get('MMX_GEMM_BACKEND', '2')))
     lib.mmx_profile_gemm(1)
     prof_steps = 3
     for _ in range(prof_steps):
@@ -255,7 +255,7 @@ def main():
     tms, tfl, nl = C.c_double(), C.c_double(), C.c_int()
     lib.mmx_profile_gemm_report(C.byref(tms), C.byref(tfl), C.byref(nl))
     gemm_tflops = tfl.value / (tms.value * 1e-3) / 1e12 if tms.value > 0 else 0.0
-    roofline = {"kernel": "transformer GEMMs (" + {0: "fp32 FFMA", 1: "tcgen05 3xTF32, 1 CTA/tile, tile width 128/144/160 per launch", 2: "tcgen05 3xTF32, cta_group::2"}[gemm_backend] + ")",
+    roofline = {"kernel": "transformer GEMMs (" + {0: "fp32 FFMA", 1: "tcgen05 3xTF32, 1 CTA/tile, tile width 128/144/160 per launch", 2: "tcgen05 fp16x3 (packed weight planes), tile width 128/144/160 per launch"}[gemm_backend] + ")",
                 "bound": "tensor", "achieved": gemm_tflops, "peak": tf_sust, "unit": "TFLOP/s",
                 "frac": gemm_tflops / tf_sust, "traffic": None,
                 "traffic_captured": {"launch": "M=3200 N=2304 K=768 (vision QKV)", "dram_bytes": 17351168,

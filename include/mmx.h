@@ -32,9 +32,10 @@ int mmx_version(void);
 /* Number of kernels this library has launched since load (all streams); the bench reports it as gpu_launches. */
 uint64_t mmx_launch_count(void);
 /* Selects the GEMM backend for the transformer linears: 0 = fp32 FFMA (bisecting reference), 1 = tcgen05 3xTF32
- * one CTA per tile (default when available), 2 = tcgen05 3xTF32 CTA pairs (cta_group::2; correct, but measured
- * slower in round 1 - see profiles/gemm_ablation_r1.md).  Env MMX_GEMM_BACKEND overrides the default.  Returns the
- * backend in effect. */
+ * (raw fp32 operands split on the SM), 2 = tcgen05 fp16x3 (default when available: three kind::f16 passes over fp16
+ * hi / lo planes, the weights pre-split once with mmx_pack_weight; linears whose weight is not packed run as backend 1).
+ * All three are fp32-faithful (<= 2e-5 of max|C| against fp64).  Env MMX_GEMM_BACKEND overrides the default.
+ * Returns the backend in effect. */
 int mmx_set_gemm_backend(int backend);
 /* Tile width of the tcgen05 backend: 0 = automatic (the width in {128, 144, 160} whose tile count best fills whole
  * waves of SMs), or one of 128 / 144 / 160 to force it (profiling and the bit-equality test: the width never changes a
@@ -150,6 +151,22 @@ int mmx_linear(const float* A, int lda, const float* W, int ldw, const float* bi
 int mmx_linear_dgrad(const float* dY, int lddy, const float* Wt, int ldwt, const float* pre, int ldpre, int act,
                      float* dX, int lddx, int M, int N, int K, void* stream);
 
+/* fp16x3 operand packing for STATIC weights (backend 2): packed holds the fp16 planes hi = fp16(w) and
+ * lo = fp16((w - hi) * 2048), each [N, round_up(K, 8)], mmx_pack_weight_bytes(N, K) bytes in total (4 bytes per element,
+ * like the fp32 original), 16-byte aligned device memory owned by the caller.  Re-pack after the weight changes.
+ * mmx_linear_packed / mmx_linear_dgrad_packed are mmx_linear / mmx_linear_dgrad with the packed copy of the SAME matrix
+ * (W for the forward, W^T for the dgrad) beside the fp32 pointer; packed == NULL is exactly the unpacked call.
+ * Range: |x| <= 65504 for both operands (larger values produce inf / NaN, never a silently wrong number); magnitudes
+ * below ~1e-5 keep an absolute precision of 3e-11 (scale tiny gradient streams by a power of two, see
+ * mmx_attention_bwd_scaled). */
+size_t mmx_pack_weight_bytes(int N, int K);
+int mmx_pack_weight(const float* W, int ldw, int N, int K, void* packed, void* stream);
+int mmx_linear_packed(const float* A, int lda, const float* W, int ldw, const void* packed, const float* bias,
+                      const float* residual, int ldres, float* C, int ldc, float* C_act, int act, int M, int N, int K,
+                      void* stream);
+int mmx_linear_dgrad_packed(const float* dY, int lddy, const float* Wt, int ldwt, const void* packed_t, const float* pre,
+                            int ldpre, int act, float* dX, int lddx, int M, int N, int K, void* stream);
+
 /* Small glue kernels for the host-side generators (DETR / LXMERT / ViT orchestration; row-major [rows, cols] with
  * row strides in elements).  They replace elementwise torch ops of the reference models (positional-embedding adds
  * DETR/models/transformer.py:236,378-390; residual adds; x[:,0] / embedding gathers). */
@@ -236,6 +253,15 @@ int mmx_clip_interpret_host(mmx_clip* h, const float* images, int n_images, cons
  * first micro-batch).  what: "A" / "dA" / "Abar" (tower 0 = vision, 1 = text, layer index), "logits" ([B,B]).
  * Writes the pointer, the dims (up to 4) and the row stride of the last dim. */
 int mmx_clip_tap(mmx_clip* h, const char* what, int tower, int layer, const float** ptr, int dims[4], int* ld);
+
+/* mmx_attention_bwd for a gradient stream that carries a per-sample power-of-two factor: dO (and hence delta, dQ, dK,
+ * dV) are gscale[b] times the true gradients, the staged dA is divided by gscale[b] (exact) so that it is the tensor the
+ * reference's hook sees.  gscale: [B] device floats, or NULL (= mmx_attention_bwd).  Used with the fp16x3 backend to keep
+ * the dgrad operands inside fp16's exponent range. */
+int mmx_attention_bwd_scaled(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk,
+                             const float* V, int ldv, const float* A, float* dA, int ldA, float* delta,
+                             float* dQ, int lddq, float* dK, int lddk, float* dV, int lddv,
+                             int B, int H, int T, int S, int hd, float scale, int flags, const float* gscale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,14 @@ def L():
     return dict(lib=lib(), check=check, ptr=ptr, st=current_stream)
 
 
+def _pack(lib, check, ptr, st, Wd):
+    """fp16x3 packed copy of a device [N, K] matrix (None below the tensor-core kernel's minimum tile)."""
+    N, K = Wd.shape
+    buf = torch.empty(lib.mmx_pack_weight_bytes(N, K), dtype=torch.uint8, device="cuda")
+    check(lib.mmx_pack_weight(ptr(Wd), K, N, K, ptr(buf), st()))
+    return buf
+
+
 ACTS = {0: lambda x: x, 1: lambda x: x * torch.sigmoid(1.702 * x), 2: lambda x: F.gelu(x), 3: lambda x: F.relu(x)}
 
 
@@ -31,8 +39,9 @@ def test_linear_and_dgrad(L, backend, M, N, K):
     if got != backend:
         pytest.skip("tcgen05 backend not available")
     try:
-        # fp32 FFMA: plain fp32 rounding.  tcgen05 3xTF32: the tensor core accumulates with truncation, measured
-        # ~2e-6 (K=768) .. 6e-6 (K=3072) of max|C|; both far inside the 1e-4 budget of the maps.
+        # fp32 FFMA: plain fp32 rounding.  tcgen05 3xTF32 / fp16x3: the tensor core accumulates with truncation, measured
+        # ~2e-6 (K=768) .. 6e-6 (K=3072) of max|C|; all far inside the 1e-4 budget of the maps.  Backend 2 takes the
+        # packed fp16 hi / lo planes of the weight (mmx_pack_weight) beside the fp32 pointer.
         tol = 5e-6 if backend == 0 else 2e-5
         gen = torch.Generator().manual_seed(M + N + K)
         A = torch.randn(M, K, generator=gen)
@@ -43,7 +52,9 @@ def test_linear_and_dgrad(L, backend, M, N, K):
             Ad, Wd, bd, rd = A.cuda(), W.cuda(), bias.cuda(), res.cuda()
             Cd = torch.empty(M, N, device="cuda")
             Ca = torch.empty(M, N, device="cuda") if act else None
-            check(lib.mmx_linear(ptr(Ad), K, ptr(Wd), K, ptr(bd), ptr(rd), N, ptr(Cd), N, ptr(Ca), act, M, N, K, st()))
+            pk = _pack(lib, check, ptr, st, Wd) if backend == 2 else None
+            check(lib.mmx_linear_packed(ptr(Ad), K, ptr(Wd), K, ptr(pk), ptr(bd), ptr(rd), N, ptr(Cd), N, ptr(Ca), act, M, N, K,
+                                        st()))
             ref = (A.double() @ W.double().t() + bias.double() + res.double())
             assert rel_err(Cd, ref) < tol
             if act:
@@ -53,10 +64,11 @@ def test_linear_and_dgrad(L, backend, M, N, K):
         pre = torch.randn(M, K, generator=gen)
         Wt = W.t().contiguous()
         dYd, Wtd, pred = dY.cuda(), Wt.cuda(), pre.cuda()      # keep device tensors alive across the call
+        pkt = _pack(lib, check, ptr, st, Wtd) if backend == 2 else None
         for act in (0, 1, 2, 3):
             dX = torch.empty(M, K, device="cuda")
-            check(lib.mmx_linear_dgrad(ptr(dYd), N, ptr(Wtd), N, ptr(pred) if act else None, K, act,
-                                       ptr(dX), K, M, N, K, st()))
+            check(lib.mmx_linear_dgrad_packed(ptr(dYd), N, ptr(Wtd), N, ptr(pkt), ptr(pred) if act else None, K, act,
+                                              ptr(dX), K, M, N, K, st()))
             p = pre.double().requires_grad_(True)
             y = ACTS[act](p) @ W.double().t()
             y.backward(dY.double())
@@ -64,16 +76,46 @@ def test_linear_and_dgrad(L, backend, M, N, K):
             ref = p.grad if act else base
             assert rel_err(dX, ref, base=base) < tol
     finally:
-        lib.mmx_set_gemm_backend(1)
+        lib.mmx_set_gemm_backend(2)
 
 
+def test_f16x3_range_and_tiny_operands(L):
+    """fp16x3 backend: operands spanning fp16's useful window (rows of A scaled from 1e-4 to 1e3) keep the fp32-faithful
+    error, an operand above 65504 yields a non-finite result (loud), and gradient-sized operands (1e-7) keep an ABSOLUTE
+    error of ~2^-35 |W| K (documented limit: scale such streams by a power of two)."""
+    lib, check, ptr, st = L["lib"], L["check"], L["ptr"], L["st"]
+    if lib.mmx_set_gemm_backend(2) != 2:
+        pytest.skip("tcgen05 backend not available")
+    M, N, K = 256, 256, 512
+    gen = torch.Generator().manual_seed(11)
+    A = torch.randn(M, K, generator=gen) * torch.logspace(-4, 3, M).unsqueeze(1)
+    W = torch.randn(N, K, generator=gen) / math.sqrt(K)
+    Ad, Wd = A.cuda(), W.cuda()
+    pk = _pack(lib, check, ptr, st, Wd)
+    Cd = torch.empty(M, N, device="cuda")
+    check(lib.mmx_linear_packed(ptr(Ad), K, ptr(Wd), K, ptr(pk), None, None, 0, ptr(Cd), N, None, 0, M, N, K, st()))
+    ref = A.double() @ W.double().t()
+    row_err = (Cd.cpu().double() - ref).abs().amax(1) / ref.abs().amax(1)
+    assert row_err.max().item() < 2e-5, row_err.max().item()           # every row, whatever its magnitude
+    A2 = A.clone(); A2[3, 5] = 7.0e4                                      # above fp16's largest finite value
+    A2d = A2.cuda()
+    check(lib.mmx_linear_packed(ptr(A2d), K, ptr(Wd), K, ptr(pk), None, None, 0, ptr(Cd), N, None, 0, M, N, K, st()))
+    assert not torch.isfinite(Cd[3]).all() and torch.isfinite(Cd[4]).all()
+    A3 = (torch.randn(M, K, generator=gen) * 1e-7)
+    A3d = A3.cuda()
+    check(lib.mmx_linear_packed(ptr(A3d), K, ptr(Wd), K, ptr(pk), None, None, 0, ptr(Cd), N, None, 0, M, N, K, st()))
+    ref3 = A3.double() @ W.double().t()
+    assert (Cd.cpu().double() - ref3).abs().max().item() < 2.0 ** -35 * K * W.abs().max().item()
+
+
+@pytest.mark.parametrize("backend", [1, 2])
 @pytest.mark.parametrize("M,N,K", [(3200, 768, 768), (3200, 2304, 768), (300, 260, 200), (129, 1000, 3072), (1, 132, 68)])
-def test_tile_width_never_changes_a_bit(L, M, N, K):
+def test_tile_width_never_changes_a_bit(L, backend, M, N, K):
     """The tcgen05 kernel picks its tile width (128 / 144 / 160 columns) from the tile count; each output element
     still sums its K products in the same order, so all three widths must agree bit for bit (batch invariance and
     sharded == single-GPU rest on this) and match fp64 to the 3xTF32 tolerance."""
     lib, check, ptr, st = L["lib"], L["check"], L["ptr"], L["st"]
-    if lib.mmx_set_gemm_backend(1) != 1:
+    if lib.mmx_set_gemm_backend(backend) != backend:
         pytest.skip("tcgen05 backend not available")
     try:
         gen = torch.Generator().manual_seed(7 * M + N + K)
@@ -81,12 +123,14 @@ def test_tile_width_never_changes_a_bit(L, M, N, K):
         W = torch.randn(N, K, generator=gen) / math.sqrt(K)
         bias, res = torch.randn(N, generator=gen), torch.randn(M, N, generator=gen)
         Ad, Wd, bd, rd = A.cuda(), W.cuda(), bias.cuda(), res.cuda()
+        pk = _pack(lib, check, ptr, st, Wd) if backend == 2 else None
         outs = {}
         for bn in (128, 144, 160, 0):
             assert lib.mmx_set_gemm_tile_n(bn) == bn
             Cd = torch.full((M, N), float("nan"), device="cuda")
             Ca = torch.full((M, N), float("nan"), device="cuda")
-            check(lib.mmx_linear(ptr(Ad), K, ptr(Wd), K, ptr(bd), ptr(rd), N, ptr(Cd), N, ptr(Ca), 2, M, N, K, st()))
+            check(lib.mmx_linear_packed(ptr(Ad), K, ptr(Wd), K, ptr(pk), ptr(bd), ptr(rd), N, ptr(Cd), N, ptr(Ca), 2, M, N, K,
+                                        st()))
             outs[bn] = (Cd.cpu(), Ca.cpu())
         ref = A.double() @ W.double().t() + bias.double() + res.double()
         assert rel_err(outs[128][0], ref) < 2e-5
@@ -95,6 +139,7 @@ def test_tile_width_never_changes_a_bit(L, M, N, K):
             assert torch.equal(outs[bn][1], outs[128][1]), bn
     finally:
         lib.mmx_set_gemm_tile_n(0)
+        lib.mmx_set_gemm_backend(2)
 
 
 @pytest.mark.parametrize("rows,D", [(3200, 768), (77, 512), (5, 32), (3, 1024), (9, 100)])

@@ -52,6 +52,12 @@ _SIGS = {
                              c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_linear_dgrad": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, C.c_int, c_float_p, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_pack_weight_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mmx_pack_weight": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mmx_linear_packed": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, C.c_void_p, c_float_p, c_float_p, C.c_int, c_float_p,
+                                    C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_linear_dgrad_packed": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, C.c_void_p, c_float_p, C.c_int, C.c_int,
+                                          c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_add": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, C.c_float, c_float_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     "mmx_gather_rows": (C.c_int, [c_float_p, C.c_int, c_int_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_scatter_add_rows": (C.c_int, [c_float_p, C.c_int, c_int_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -69,6 +75,10 @@ _SIGS = {
                                     c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
                                     c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                     C.c_void_p]),
+    "mmx_attention_bwd_scaled": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int,
+                                           c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
+                                           c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                           c_float_p, C.c_void_p]),
     "mmx_clip_create": (C.c_int, [C.POINTER(ClipConfigC), C.c_int, C.POINTER(C.c_void_p)]),
     "mmx_clip_destroy": (None, [C.c_void_p]),
     "mmx_clip_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_float_p, C.c_size_t]),

@@ -295,7 +295,7 @@ template <int HD, int TQ>
 __global__ void __launch_bounds__(TQ * 4) attention_bwd_q_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
     const float* __restrict__ A, float* __restrict__ dA, int ldA, float* __restrict__ delta, float* __restrict__ dQ,
-    int lddq, int H, int T, int S, float scale, Ragged rg) {
+    int lddq, int H, int T, int S, float scale, Ragged rg, const float* __restrict__ gscale) {
   constexpr int LDH = AttnSmem<HD>::LDX, ATT_THREADS = TQ * 4, ATT_WARPS = TQ / 8, MB = TQ / 16;
   extern __shared__ float smem[];
   const int S_pad = score_ld(S);
@@ -314,6 +314,9 @@ __global__ void __launch_bounds__(TQ * 4) attention_bwd_q_kernel(
     }
     return;
   }
+  // The gradient stream of sample b may carry a power-of-two factor gscale[b] (fp16x3 GEMM range, see gemm_f16x3.cu);
+  // the staged dA is divided by it (exact), everything that continues the backward (delta, dS, dQ) stays scaled.
+  const float ginv = gscale ? 1.f / gscale[b] : 1.f;
   load_rows_async<HD, TQ>(dO, lddo, qrow0 * lddo + h * HD, i0, T, sX, LDH);
   load_rows_async<HD, TKEY>(V, ldv, krow0 * ldv + h * HD, 0, S, sKV, LDH);
   cp_async_commit();
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(TQ * 4) attention_bwd_q_kernel(
     float dl = 0.f;
     for (int j = lane; j < ldA; j += 32) {
       const float g = (j < S) ? row[j] : 0.f;
-      dA[goff + j] = g;                       // the hooked gradient, unmasked (autograd of bmm(A, v))
+      dA[goff + j] = g * ginv;                // the hooked gradient, unmasked (autograd of bmm(A, v)), in TRUE units
       if (j < S) dl = fmaf(g, A[goff + j], dl);
     }
     dl = warp_sum(dl);
@@ -357,7 +360,7 @@ template <int HD>
 __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ Q, int ldq, const float* __restrict__ A,
     const float* __restrict__ dA, int ldA, const float* __restrict__ delta, float* __restrict__ dK, int lddk,
-    float* __restrict__ dV, int lddv, int H, int T, int S, float scale, Ragged rg) {
+    float* __restrict__ dV, int lddv, int H, int T, int S, float scale, Ragged rg, const float* __restrict__ gscale) {
   constexpr int LDH = HD + 8, LDK = KV_KEYS + 8, NT = HD / 16;   // both are [k][n]-indexed operands: stride = 8 (mod 16)
   extern __shared__ float smem[];
   float* sdO = smem;
@@ -371,6 +374,7 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
   long long qrow0 = (long long)b * T, krow0 = (long long)b * S;
   if (rg.lens) { T = S = rg.lens[b]; qrow0 = krow0 = rg.offs[b]; }
   if (j0 >= S) return;
+  const float gs = gscale ? gscale[b] : 1.f;           // staged dA is in true units, delta / dO / the outputs are scaled
   float accV[NT][4] = {}, crsV[NT][4] = {}, accK[NT][4] = {}, crsK[NT][4] = {};
   const long long plane = ((long long)b * H + h) * Tm;
   for (int i0 = 0; i0 < T; i0 += KV_ROWS) {
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
         a = *reinterpret_cast<const float4*>(A + off);
         const float4 ga = *reinterpret_cast<const float4*>(dA + off);
         const float dl = delta[plane + i0 + r];
-        ds = make_float4(a.x * (ga.x - dl), a.y * (ga.y - dl), a.z * (ga.z - dl), a.w * (ga.w - dl));
+        ds = make_float4(a.x * (ga.x * gs - dl), a.y * (ga.y * gs - dl), a.z * (ga.z * gs - dl), a.w * (ga.w * gs - dl));
       }
       *reinterpret_cast<float4*>(sA + r * LDK + c) = a;
       *reinterpret_cast<float4*>(sS + r * LDK + c) = ds;
@@ -455,12 +459,12 @@ static int launch_fwd(const float* Q, int ldq, const float* K, int ldk, const fl
 template <int HD, int TQ>
 static int launch_bwd_q_tq(const float* dO, int lddo, const float* K, int ldk, const float* V, int ldv, const float* A,
                            float* dA, int ldA, float* delta, float* dQ, int lddq, int B, int H, int T, int S, float scale,
-                           Ragged rg, cudaStream_t st) {
+                           Ragged rg, const float* gscale, cudaStream_t st) {
   const size_t smem = AttnSmem<HD>::bytes(S, TQ);
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<HD, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, TQ), H, B);
   attention_bwd_q_kernel<HD, TQ><<<grid, TQ * 4, smem, st>>>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, H, T, S,
-                                                            scale, rg);
+                                                            scale, rg, gscale);
   MMX_LAUNCH_CHECK();
   return 0;
 }
@@ -468,19 +472,19 @@ static int launch_bwd_q_tq(const float* dO, int lddo, const float* K, int ldk, c
 template <int HD>
 static int launch_bwd(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                       const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, float* dK, int lddk, float* dV,
-                      int lddv, int B, int H, int T, int S, float scale, Ragged rg, cudaStream_t st) {
+                      int lddv, int B, int H, int T, int S, float scale, Ragged rg, const float* gscale, cudaStream_t st) {
   if (AttnSmem<HD>::bytes(S, 64) <= ATT_SMEM_MAX) {
-    MMX_TRY((launch_bwd_q_tq<HD, 64>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, st)));
+    MMX_TRY((launch_bwd_q_tq<HD, 64>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, gscale, st)));
   } else {
     MMX_REQUIRE(AttnSmem<HD>::bytes(S, 32) <= ATT_SMEM_MAX, "sequence too long for the single-pass attention kernel");
-    MMX_TRY((launch_bwd_q_tq<HD, 32>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, st)));
+    MMX_TRY((launch_bwd_q_tq<HD, 32>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, gscale, st)));
   }
   if (dQ == nullptr) return 0;
   const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 8) + 2 * KV_ROWS * (KV_KEYS + 8));
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   dim3 grid2(cdiv(S, KV_KEYS), H, B);
   attention_bwd_kv_kernel<HD><<<grid2, KV_THREADS, smem2, st>>>(dO, lddo, Q, ldq, A, dA, ldA, delta, dK, lddk, dV, lddv, H,
-                                                                T, S, scale, rg);
+                                                                T, S, scale, rg, gscale);
   MMX_LAUNCH_CHECK();
   return 0;
 }
@@ -507,7 +511,7 @@ int attention_fwd(const float* Q, int ldq, const float* K, int ldk, const float*
 int attention_bwd(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                   const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, float* dK, int lddk, float* dV,
                   int lddv, int B, int H, int T, int S, int hd, float scale, int flags, cudaStream_t st, const int* offs,
-                  const int* lens) {
+                  const int* lens, const float* gscale) {
   Ragged rg;
   rg.offs = offs; rg.lens = lens;
   MMX_REQUIRE(lens == nullptr || (T == S && offs != nullptr), "ragged attention: self-attention only");
@@ -521,9 +525,9 @@ int attention_bwd(const float* dO, int lddo, const float* Q, int ldq, const floa
   (void)flags;  // the mask is already folded into A (masked entries are exactly 0, so dS vanishes there)
   if (B == 0 || T == 0) return 0;
   switch (hd) {
-    case 16: return launch_bwd<16>(dO, lddo, Q, ldq, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, scale, rg, st);
-    case 32: return launch_bwd<32>(dO, lddo, Q, ldq, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, scale, rg, st);
-    case 64: return launch_bwd<64>(dO, lddo, Q, ldq, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, scale, rg, st);
+    case 16: return launch_bwd<16>(dO, lddo, Q, ldq, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, scale, rg, gscale, st);
+    case 32: return launch_bwd<32>(dO, lddo, Q, ldq, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, scale, rg, gscale, st);
+    case 64: return launch_bwd<64>(dO, lddo, Q, ldq, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, scale, rg, gscale, st);
     default: MMX_REQUIRE(false, "head_dim must be 16, 32 or 64");
   }
   return 0;
@@ -543,6 +547,13 @@ int mmx_attention_bwd(const float* dO, int lddo, const float* Q, int ldq, const 
                       const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, float* dK, int lddk, float* dV,
                       int lddv, int B, int H, int T, int S, int hd, float scale, int flags, void* stream) {
   return attention_bwd(dO, lddo, Q, ldq, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, hd, scale,
-                       flags, (cudaStream_t)stream, nullptr, nullptr);
+                       flags, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+}
+int mmx_attention_bwd_scaled(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk, const float* V,
+                             int ldv, const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, float* dK,
+                             int lddk, float* dV, int lddv, int B, int H, int T, int S, int hd, float scale, int flags,
+                             const float* gscale, void* stream) {
+  return attention_bwd(dO, lddo, Q, ldq, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, hd, scale,
+                       flags, (cudaStream_t)stream, nullptr, nullptr, gscale);
 }
 }

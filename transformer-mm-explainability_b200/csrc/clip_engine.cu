@@ -30,7 +30,7 @@ int attention_fwd(const float*, int, const float*, int, const float*, int, const
                   int, int, float, int, cudaStream_t, const int* offs, const int* lens);
 int attention_bwd(const float*, int, const float*, int, const float*, int, const float*, int, const float*, float*, int, float*,
                   float*, int, float*, int, float*, int, int, int, int, int, int, float, int, cudaStream_t, const int* offs,
-                  const int* lens);
+                  const int* lens, const float* gscale);
 int text_embed_packed(const int*, const float*, const float*, float*, int*, int*, int*, int*, int, int, int, int, cudaStream_t);
 int avg_heads(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int bmm_add(const float*, int, long long, int, const float*, int, long long, const float*, int, long long, float*, int, long long,
@@ -40,7 +40,7 @@ int vision_tokens_lnpre(const float*, int, const float*, const float*, const flo
                         cudaStream_t);
 int text_embed(const int*, const float*, const float*, float*, int*, int, int, int, int, cudaStream_t);
 int cls_rows(int*, int, int, cudaStream_t);
-int clip_head(const float*, const float*, float, float*, float*, float*, float*, float*, int, int, cudaStream_t);
+int clip_head(const float*, const float*, float, float*, float*, float*, float*, float*, float*, float*, int, int, cudaStream_t);
 int scale_inplace(float*, long long, float, cudaStream_t);
 int set_eye(float*, int, int, int, cudaStream_t);
 int slice_out(const float*, long long, int, int, int, float*, int, int, int, cudaStream_t);
@@ -69,6 +69,7 @@ static int transpose(const float* in, float* out, int rows, int cols, cudaStream
 struct Mat {
   float* w = nullptr;
   int N = 0, K = 0;
+  void* packed = nullptr;   // fp16 hi / lo planes for the fp16x3 backend (built by finalize)
 };
 
 struct LayerW {
@@ -79,7 +80,7 @@ struct LayerW {
 };
 
 static inline int mm(const float* A, int lda, const Mat& B, float* C, int ldc, int M, const GemmEpilogue& ep, cudaStream_t st) {
-  return gemm_nt(A, lda, B.w, B.K, C, ldc, M, B.N, B.K, ep, st);
+  return gemm_nt_b(A, lda, packed_operand(B.w, B.K, B.packed, B.N, B.K), C, ldc, M, B.N, B.K, ep, st);
 }
 
 struct Tower {
@@ -100,10 +101,12 @@ struct Tower {
   // ragged text batches: packed rows, sample b owns rows offs[b] .. offs[b] + lens[b] - 1; *total = sum(lens)
   bool ragged = false;
   int *offs = nullptr, *lens = nullptr, *total = nullptr;
+  int rows_host = -1;       // sum(lens) read back for this chunk (-1: unknown, the GEMMs read *total on the device)
   float *pool_ln = nullptr, *pool_mean = nullptr, *pool_rstd = nullptr, *dpool = nullptr;  // [Bm,D], [Bm]
   float *lnf_g = nullptr, *lnf_b = nullptr;  // ln_post / ln_final
   Mat proj, projT;                           // [D,E] (as stored: the dgrad operand), [E,D] (forward operand)
   float *feat = nullptr, *featn = nullptr, *dfeat = nullptr;  // [Bm,E]
+  float* gscale = nullptr;  // [Bm] power-of-two factor carried by this tower's gradient stream (per sample)
   cudaStream_t st = nullptr;
   long long M(int B) const { return (long long)B * S; }
 };
@@ -133,7 +136,8 @@ struct mmx_clip {
   float* d_images = nullptr; int32_t* d_tokens = nullptr; float *d_Rtext = nullptr, *d_Rimage = nullptr;
   float *logits = nullptr, *diag = nullptr;
   cudaStream_t main = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_v = nullptr, ev_t = nullptr, ev_head = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_v = nullptr, ev_t = nullptr, ev_head = nullptr, ev_rows = nullptr;
+  int* rows_pinned = nullptr;   // host copy of the text tower's packed row count (ragged batches)
   int lastB = 0, last_start_v = 0, last_start_t = 0;
   size_t bytes = 0;
 };
@@ -216,6 +220,7 @@ int alloc_tower(mmx_clip* h, Tower& T, const std::string& prefix, int Bm, int E)
   MMX_TRY(dallocT(h, &T.feat, (size_t)Bm * E));
   MMX_TRY(dallocT(h, &T.featn, (size_t)Bm * E));
   MMX_TRY(dallocT(h, &T.dfeat, (size_t)Bm * E));
+  MMX_TRY(dallocT(h, &T.gscale, (size_t)Bm));
   MMX_CHECK_CUDA(cudaStreamCreateWithFlags(&T.st, cudaStreamNonBlocking));
   return 0;
 }
@@ -230,6 +235,10 @@ int tower_forward(Tower& T, int B) {
   const int* md = T.ragged ? T.total : nullptr;      // device row count; M = B*S is then only the upper bound
   const int* offs = T.ragged ? T.offs : nullptr;
   const int* lens = T.ragged ? T.lens : nullptr;
+  // GEMM row count: exact on the host when the packed row count was read back (tile width / grid chosen for the real
+  // size), else the upper bound with the device-side count
+  const int Mg = (T.ragged && T.rows_host >= 0) ? T.rows_host : M;
+  const int* mg = (T.ragged && T.rows_host >= 0) ? nullptr : md;
   for (int l = 0; l < T.L; ++l) {
     const LayerW& w = T.w[l];
     float* x_in = T.x + l * MD;
@@ -239,17 +248,17 @@ int tower_forward(Tower& T, int B) {
     float* f = T.f + l * MD * 4;
     float* stt = T.stats + (size_t)l * 4 * M;
     MMX_TRY(layernorm_fwd(x_in, D, nullptr, w.ln1_g, w.ln1_b, T.h, D, stt, stt + M, M, D, 1e-5f, st, md));
-    GemmEpilogue e1; e1.bias = w.bqkv; e1.m_dev = md;
-    MMX_TRY(mm(T.h, D, w.Wqkv, qkv, 3 * D, M, e1, st));
+    GemmEpilogue e1; e1.bias = w.bqkv; e1.m_dev = mg;
+    MMX_TRY(mm(T.h, D, w.Wqkv, qkv, 3 * D, Mg, e1, st));
     MMX_TRY(attention_fwd(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, nullptr, T.A + l * plane, T.ld, T.o, D, B, T.H, T.S,
                           T.S, T.hd, scale, T.causal ? MMX_ATTN_CAUSAL : 0, st, offs, lens));
-    GemmEpilogue e2; e2.bias = w.bo; e2.residual = x_in; e2.ldres = D; e2.m_dev = md;
-    MMX_TRY(mm(T.o, D, w.Wo, x_mid, D, M, e2, st));
+    GemmEpilogue e2; e2.bias = w.bo; e2.residual = x_in; e2.ldres = D; e2.m_dev = mg;
+    MMX_TRY(mm(T.o, D, w.Wo, x_mid, D, Mg, e2, st));
     MMX_TRY(layernorm_fwd(x_mid, D, nullptr, w.ln2_g, w.ln2_b, T.h, D, stt + 2 * M, stt + 3 * M, M, D, 1e-5f, st, md));
-    GemmEpilogue e3; e3.bias = w.bfc; e3.C_act = T.g; e3.act = T.act; e3.m_dev = md;
-    MMX_TRY(mm(T.h, D, w.Wfc, f, 4 * D, M, e3, st));
-    GemmEpilogue e4; e4.bias = w.bproj; e4.residual = x_mid; e4.ldres = D; e4.m_dev = md;
-    MMX_TRY(mm(T.g, 4 * D, w.Wproj, x_out, D, M, e4, st));
+    GemmEpilogue e3; e3.bias = w.bfc; e3.C_act = T.g; e3.act = T.act; e3.m_dev = mg;
+    MMX_TRY(mm(T.h, D, w.Wfc, f, 4 * D, Mg, e3, st));
+    GemmEpilogue e4; e4.bias = w.bproj; e4.residual = x_mid; e4.ldres = D; e4.m_dev = mg;
+    MMX_TRY(mm(T.g, 4 * D, w.Wproj, x_out, D, Mg, e4, st));
   }
   return 0;
 }
@@ -281,6 +290,8 @@ int tower_backward(Tower& T, int B, int E, int stop) {
   const int* md = T.ragged ? T.total : nullptr;
   const int* offs = T.ragged ? T.offs : nullptr;
   const int* lens = T.ragged ? T.lens : nullptr;
+  const int Mg = (T.ragged && T.rows_host >= 0) ? T.rows_host : M;
+  const int* mg = (T.ragged && T.rows_host >= 0) ? nullptr : md;
   for (int l = T.L - 1; l >= stop; --l) {
     const LayerW& w = T.w[l];
     const float* x_in = T.x + l * MD;
@@ -288,18 +299,18 @@ int tower_backward(Tower& T, int B, int E, int stop) {
     const float* qkv = T.qkv + l * MD * 3;
     const float* f = T.f + l * MD * 4;
     const float* stt = T.stats + (size_t)l * 4 * M;
-    GemmEpilogue e1; e1.pre = f; e1.ldpre = 4 * D; e1.act = T.act; e1.m_dev = md;
-    MMX_TRY(mm(dx_out, D, w.WprojT, T.g, 4 * D, M, e1, st));                        // df = (dx W_proj) . act'(f)
-    GemmEpilogue e2; e2.m_dev = md;
-    MMX_TRY(mm(T.g, 4 * D, w.WfcT, T.h, D, M, e2, st));                             // dh2 = df W_fc
+    GemmEpilogue e1; e1.pre = f; e1.ldpre = 4 * D; e1.act = T.act; e1.m_dev = mg;
+    MMX_TRY(mm(dx_out, D, w.WprojT, T.g, 4 * D, Mg, e1, st));                        // df = (dx W_proj) . act'(f)
+    GemmEpilogue e2; e2.m_dev = mg;
+    MMX_TRY(mm(T.g, 4 * D, w.WfcT, T.h, D, Mg, e2, st));                             // dh2 = df W_fc
     MMX_TRY(layernorm_bwd(T.h, D, x_mid, D, nullptr, w.ln2_g, stt + 2 * M, stt + 3 * M, dx_out, D, dx_mid, D, M, D, st, md));
-    MMX_TRY(mm(dx_mid, D, w.WoT, T.o, D, M, e2, st));                               // d(attn out) = dx_mid W_o
+    MMX_TRY(mm(dx_mid, D, w.WoT, T.o, D, Mg, e2, st));                               // d(attn out) = dx_mid W_o
     const bool last = (l == stop);
     MMX_TRY(attention_bwd(T.o, D, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, T.A + l * plane, T.dA + l * plane, T.ld,
                           T.delta, last ? nullptr : T.dqkv, 3 * D, last ? nullptr : T.dqkv + D, 3 * D,
-                          last ? nullptr : T.dqkv + 2 * D, 3 * D, B, T.H, T.S, T.S, T.hd, scale, 0, st, offs, lens));
+                          last ? nullptr : T.dqkv + 2 * D, 3 * D, B, T.H, T.S, T.S, T.hd, scale, 0, st, offs, lens, T.gscale));
     if (last) break;
-    MMX_TRY(mm(T.dqkv, 3 * D, w.WqkvT, T.h, D, M, e2, st));                          // dh1 = dqkv W_qkv
+    MMX_TRY(mm(T.dqkv, 3 * D, w.WqkvT, T.h, D, Mg, e2, st));                          // dh1 = dqkv W_qkv
     MMX_TRY(layernorm_bwd(T.h, D, x_in, D, nullptr, w.ln1_g, stt, stt + M, dx_mid, D, dx_out, D, M, D, st, md));
   }
   return 0;
@@ -333,6 +344,16 @@ int run_chunk(mmx_clip* h, const float* images, int n_images, const int32_t* tok
   MMX_CHECK_CUDA(cudaEventRecord(h->ev_fork, caller));
   MMX_CHECK_CUDA(cudaStreamWaitEvent(V.st, h->ev_fork, 0));
   MMX_CHECK_CUDA(cudaStreamWaitEvent(Tx.st, h->ev_fork, 0));
+  // ---- text embedding first: it yields the packed row count of the ragged text batch, which is copied to the host
+  // while the vision tower's launches are being enqueued (no stall), so the text GEMMs get exact sizes
+  if (Tx.ragged) {
+    MMX_TRY(text_embed_packed(tokens, h->tok_emb, h->pos_t, Tx.x, Tx.offs, Tx.lens, Tx.rows, Tx.total, B, Tx.S, Tx.D,
+                              c.vocab_size, Tx.st));
+    MMX_CHECK_CUDA(cudaMemcpyAsync(h->rows_pinned, Tx.total, sizeof(int), cudaMemcpyDeviceToHost, Tx.st));
+    MMX_CHECK_CUDA(cudaEventRecord(h->ev_rows, Tx.st));
+  } else {
+    MMX_TRY(text_embed(tokens, h->tok_emb, h->pos_t, Tx.x, Tx.rows, B, Tx.S, Tx.D, c.vocab_size, Tx.st));
+  }
   // ---- vision tower
   {
     NvtxRange r("vision/forward");
@@ -348,18 +369,20 @@ int run_chunk(mmx_clip* h, const float* images, int n_images, const int32_t* tok
   // ---- text tower
   {
     NvtxRange r("text/forward");
-    if (Tx.ragged)
-      MMX_TRY(text_embed_packed(tokens, h->tok_emb, h->pos_t, Tx.x, Tx.offs, Tx.lens, Tx.rows, Tx.total, B, Tx.S, Tx.D,
-                                c.vocab_size, Tx.st));
-    else
-      MMX_TRY(text_embed(tokens, h->tok_emb, h->pos_t, Tx.x, Tx.rows, B, Tx.S, Tx.D, c.vocab_size, Tx.st));
+    Tx.rows_host = -1;
+    if (Tx.ragged) {
+      MMX_CHECK_CUDA(cudaEventSynchronize(h->ev_rows));
+      Tx.rows_host = *h->rows_pinned;
+      MMX_REQUIRE(Tx.rows_host >= 0 && Tx.rows_host <= B * Tx.S, "packed text row count out of range");
+    }
     MMX_TRY(tower_forward(Tx, B));
     MMX_TRY(tower_pool(Tx, B, E));
   }
   // ---- head on the vision stream after the text features landed
   MMX_CHECK_CUDA(cudaEventRecord(h->ev_t, Tx.st));
   MMX_CHECK_CUDA(cudaStreamWaitEvent(V.st, h->ev_t, 0));
-  MMX_TRY(clip_head(V.feat, Tx.feat, expf(h->logit_scale), V.featn, Tx.featn, V.dfeat, Tx.dfeat, h->diag, B, E, V.st));
+  MMX_TRY(clip_head(V.feat, Tx.feat, expf(h->logit_scale), V.featn, Tx.featn, V.dfeat, Tx.dfeat, h->diag, V.gscale, Tx.gscale, B,
+                    E, V.st));
   MMX_CHECK_CUDA(cudaEventRecord(h->ev_head, V.st));
   MMX_CHECK_CUDA(cudaStreamWaitEvent(Tx.st, h->ev_head, 0));
   {
@@ -470,7 +493,9 @@ int mmx_clip_create(const mmx_clip_config* cfg, int max_batch, mmx_clip** out) {
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_v, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_t, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_rows, cudaEventDisableTiming) != cudaSuccess ||
+      cudaHostAlloc((void**)&h->rows_pinned, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
     set_error("stream/event creation failed");
     return fail(1);
   }
@@ -485,7 +510,8 @@ void mmx_clip_destroy(mmx_clip* h) {
   if (h->v.st) cudaStreamDestroy(h->v.st);
   if (h->t.st) cudaStreamDestroy(h->t.st);
   if (h->main) cudaStreamDestroy(h->main);
-  for (cudaEvent_t e : {h->ev_fork, h->ev_v, h->ev_t, h->ev_head}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev_fork, h->ev_v, h->ev_t, h->ev_head, h->ev_rows}) if (e) cudaEventDestroy(e);
+  if (h->rows_pinned) cudaFreeHost(h->rows_pinned);
   delete h;
 }
 
@@ -518,6 +544,20 @@ int mmx_clip_finalize(mmx_clip* h) {
       MMX_TRY(transpose(w.Wproj.w, w.WprojT.w, D, 4 * D, st));  // [D,4D] -> [4D,D]
     }
     MMX_TRY(transpose(T->proj.w, T->projT.w, D, h->E, st));     // [D,E] -> [E,D]
+  }
+  // fp16 hi / lo planes of every static GEMM operand (the fp16x3 backend; 4 bytes per element like the fp32 copy)
+  if (gemm_tc_available()) {
+    std::vector<Mat*> mats{&h->conv_w};
+    for (Tower* T : {&h->v, &h->t}) {
+      for (LayerW& w : T->w)
+        for (Mat* m : {&w.Wqkv, &w.Wo, &w.Wfc, &w.Wproj, &w.WqkvT, &w.WoT, &w.WfcT, &w.WprojT}) mats.push_back(m);
+      mats.push_back(&T->proj);
+      mats.push_back(&T->projT);
+    }
+    for (Mat* m : mats) {
+      if (!m->packed) MMX_TRY(dalloc(h, &m->packed, pack_f16x3_bytes(m->N, m->K)));
+      MMX_TRY(pack_f16x3(m->w, m->K, m->N, m->K, m->packed, st));
+    }
   }
   MMX_CHECK_CUDA(cudaStreamSynchronize(st));
   h->finalized = true;

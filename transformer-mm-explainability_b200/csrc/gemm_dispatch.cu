@@ -29,30 +29,26 @@ bool gemm_tc_shape_ok(const float* A, int lda, const float* Bt, int ldb, float* 
                       const GemmEpilogue& ep);
 int gemm_nt_tc(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
                const GemmEpilogue& ep, cudaStream_t st);
-// gemm_tcgen05_2cta.cu
-int gemm_nt_tc2(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
-                const GemmEpilogue& ep, cudaStream_t st);
 
 void gemm_tc_set_trace(long long* buf);
 
 int gemm_backend() {
   int b = g_backend.load();
   if (b < 0) {
-    b = gemm_tc_available() ? 1 : 0;
+    b = gemm_tc_available() ? 2 : 0;
     const char* env = getenv("MMX_GEMM_BACKEND");
-    if (env && b) b = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));
+    if (env && b) b = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));   // 0 FFMA, 1 tf32x3, 2 fp16x3 (packed weights)
     g_backend.store(b);
   }
   return b;
 }
 
-static int gemm_nt_impl(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
+static int gemm_nt_impl(const float* A, int lda, const BOperand& B, float* C, int ldc, int M, int N, int K,
                         const GemmEpilogue& ep, cudaStream_t st) {
   const int be = gemm_backend();
-  if (be >= 1 && gemm_tc_shape_ok(A, lda, Bt, ldb, C, ldc, N, K, ep))
-    return be == 2 ? gemm_nt_tc2(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st)
-                   : gemm_nt_tc(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
-  return gemm_nt_simt(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
+  if (be == 2 && B.hi && gemm_f16x3_shape_ok(A, lda, B, C, ldc, N, K, ep)) return gemm_nt_f16x3(A, lda, B, C, ldc, M, N, K, ep, st);
+  if (be >= 1 && gemm_tc_shape_ok(A, lda, B.w, B.ldw, C, ldc, N, K, ep)) return gemm_nt_tc(A, lda, B.w, B.ldw, C, ldc, M, N, K, ep, st);
+  return gemm_nt_simt(A, lda, B.w, B.ldw, C, ldc, M, N, K, ep, st);
 }
 
 int gemm_nt_tc_rule(const float* A, int lda, const float* Bt, int ldb, const float* residual, int ldres, float* C, int ldc,
@@ -79,8 +75,15 @@ static std::atomic<int> g_prof_on{0};
 
 int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
             const GemmEpilogue& ep, cudaStream_t st) {
+  BOperand B;
+  B.w = Bt; B.ldw = ldb;
+  return gemm_nt_b(A, lda, B, C, ldc, M, N, K, ep, st);
+}
+
+int gemm_nt_b(const float* A, int lda, const BOperand& Bop, float* C, int ldc, int M, int N, int K, const GemmEpilogue& ep,
+              cudaStream_t st) {
   if (!g_prof_on.load(std::memory_order_relaxed) || M == 0 || N == 0)
-    return gemm_nt_impl(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
+    return gemm_nt_impl(A, lda, Bop, C, ldc, M, N, K, ep, st);
   ProfRec r;
   {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -93,7 +96,7 @@ int gemm_nt(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc
   r.m_dev = ep.m_dev;
   r.M = M;
   MMX_CHECK_CUDA(cudaEventRecord(r.s, st));
-  MMX_TRY(gemm_nt_impl(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st));
+  MMX_TRY(gemm_nt_impl(A, lda, Bop, C, ldc, M, N, K, ep, st));
   MMX_CHECK_CUDA(cudaEventRecord(r.e, st));
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back(r);
@@ -156,17 +159,31 @@ int mmx_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
   return 0;
 }
 
-int mmx_linear(const float* A, int lda, const float* W, int ldw, const float* bias, const float* residual, int ldres, float* C,
-               int ldc, float* C_act, int act, int M, int N, int K, void* stream) {
+size_t mmx_pack_weight_bytes(int N, int K) { return (N > 0 && K > 0) ? pack_f16x3_bytes(N, K) : 0; }
+int mmx_pack_weight(const float* W, int ldw, int N, int K, void* packed, void* stream) {
+  MMX_REQUIRE(W && packed && N > 0 && K > 0 && ldw >= K, "bad arguments");
+  return pack_f16x3(W, ldw, N, K, packed, (cudaStream_t)stream);
+}
+int mmx_linear_packed(const float* A, int lda, const float* W, int ldw, const void* packed, const float* bias,
+                      const float* residual, int ldres, float* C, int ldc, float* C_act, int act, int M, int N, int K,
+                      void* stream) {
   GemmEpilogue ep;
   ep.bias = bias; ep.residual = residual; ep.ldres = ldres; ep.C_act = C_act; ep.act = act;
-  return gemm_nt(A, lda, W, ldw, C, ldc, M, N, K, ep, (cudaStream_t)stream);
+  return gemm_nt_b(A, lda, packed_operand(W, ldw, packed, N, K), C, ldc, M, N, K, ep, (cudaStream_t)stream);
 }
-int mmx_linear_dgrad(const float* dY, int lddy, const float* Wt, int ldwt, const float* pre, int ldpre, int act, float* dX,
-                     int lddx, int M, int N, int K, void* stream) {
+int mmx_linear(const float* A, int lda, const float* W, int ldw, const float* bias, const float* residual, int ldres, float* C,
+               int ldc, float* C_act, int act, int M, int N, int K, void* stream) {
+  return mmx_linear_packed(A, lda, W, ldw, nullptr, bias, residual, ldres, C, ldc, C_act, act, M, N, K, stream);
+}
+int mmx_linear_dgrad_packed(const float* dY, int lddy, const float* Wt, int ldwt, const void* packed_t, const float* pre,
+                            int ldpre, int act, float* dX, int lddx, int M, int N, int K, void* stream) {
   GemmEpilogue ep;
   ep.pre = pre; ep.ldpre = ldpre; ep.act = act;
   // dX[M,K] = dY[M,N] * Wt[K,N]^T : an NT GEMM with "N" = K and reduction over N
-  return gemm_nt(dY, lddy, Wt, ldwt, dX, lddx, M, K, N, ep, (cudaStream_t)stream);
+  return gemm_nt_b(dY, lddy, packed_operand(Wt, ldwt, packed_t, K, N), dX, lddx, M, K, N, ep, (cudaStream_t)stream);
+}
+int mmx_linear_dgrad(const float* dY, int lddy, const float* Wt, int ldwt, const float* pre, int ldpre, int act, float* dX,
+                     int lddx, int M, int N, int K, void* stream) {
+  return mmx_linear_dgrad_packed(dY, lddy, Wt, ldwt, nullptr, pre, ldpre, act, dX, lddx, M, N, K, stream);
 }
 }

@@ -1,0 +1,409 @@
+// tcgen05 GEMM with fp32-faithful numerics from THREE fp16 tensor-core passes:  C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).
+//
+// Each fp32 operand x is represented as  x = hi + lo' / 2048,  hi = fp16_rn(x),  lo' = fp16_rn((x - hi) * 2048)
+// (22 significand bits, like the tf32 hi/lo split of gemm_tcgen05.cu; the 2^11 factor keeps lo' in fp16's normal
+// range), and   A W^T = A_hi W_hi^T + (A_lo' W_hi^T + A_hi W_lo'^T) / 2048.   fp16 x fp16 products are exact in the
+// fp32 accumulator; the two cross products have their own TMEM accumulator (the tensor core adds with truncation, so
+// keeping the 2^-11-smaller terms apart keeps their truncation error 2^-11 smaller) and are folded in once, with RN,
+// in the epilogue.  kind::f16 runs at twice the kind::tf32 rate and one instruction covers K = 16 instead of 8, so
+// against the tf32x3 kernel this halves the tensor time, the MMA issue count and the per-K-slab barrier round trips.
+//
+// Range.  fp16 spans 2^-24 .. 65504: a value above 65504 becomes inf (and the result NaN - loud, never silently wrong);
+// values below 2^-14 keep an ABSOLUTE precision of 2^-35, so tensors whose typical magnitude is above ~1e-5 lose
+// nothing.  Forward activations and weights of the models on this path sit in 1e-3 .. 1e2.  Gradients do not, which is
+// why the CLIP engine normalises the seed gradient of every sample to a power of two near 1 and undoes the factor when
+// dA is staged (clip_engine.cu / attention.cu) - an exact operation, and a per-sample one, so batch invariance holds.
+//
+// Operand movement (what bounds a 3-pass GEMM, see profiles/gemm_ablation_r1.md): the weights are static, so their
+// hi / lo planes are built ONCE (pack_f16x3, 4 bytes per element like the fp32 original) and arrive by TMA ready for
+// the MMAs - no in-kernel B split, no extra shared-memory pass.  A (activations / gradients, produced as fp32 by the
+// previous kernel) crosses L2 once as raw fp32, is split in registers and written to TMEM (tcgen05.st, packed fp16
+// pairs), and the MMAs take it from there (.ts form).
+//
+// Structure (one CTA per SM, persistent over 128 x BN tiles, 3-stage ring of 128 x 64 K-slabs):
+//   warp 0      TMA producer: A raw fp32 (two 32-wide swizzle-128B boxes), W_hi, W_lo fp16 (64-wide boxes)
+//   warps 12-15 splitters: one A row per thread -> hi / lo' fp16 pairs -> 32 + 32 TMEM columns of the stage
+//   warp 1      MMA issuer: 12 tcgen05.mma.kind::f16 per slab (4 k-steps x 3 products), tcgen05.commit
+//   warp 2      TMEM allocator (512 columns: BN main + BN cross accumulators + 3 x 64 columns of A)
+//   warps 4-11  epilogue: tcgen05.ld main + cross/2048 -> registers, TMEM released, bias / act' / residual / act
+#include "gemm.cuh"
+#include "tcgen05_ptx.cuh"
+#include <cuda_fp16.h>
+#include <cudaTypedefs.h>
+#include <cstdlib>
+
+namespace mmx {
+namespace hx {
+
+using namespace ::mmx::tcp;
+
+constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr int SPLIT_WARPS = 4, EPI_WARP0 = 4, EPI_WARPS = 8, SPLIT_WARP0 = 12;
+constexpr int THREADS = (12 + SPLIT_WARPS) * 32;
+constexpr int A_SUB = BM * 32 * 4;             // one 128 x 32 fp32 swizzle-128B box: 16 KB
+constexpr int A_BYTES = 2 * A_SUB;             // raw A slab 128 x 64 fp32
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+template <int BN> struct Cfg {
+  static_assert(BN % 16 == 0 && BN >= 128 && BN <= 160, "UMMA N for M=128: multiple of 16; TMEM budget caps it at 160");
+  static constexpr int B_BYTES = BN * BK * 2;           // per plane (hi / lo): 16-20 KB, a multiple of 1024
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t TM_MAIN = 0, TM_CROSS = (BN + 31) / 32 * 32, TM_A = 2 * TM_CROSS;   // A ring: hi at +64s, lo at +32
+  static_assert(TM_A + 64 * STAGES <= 512, "TMEM has 512 columns");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory per CTA");
+  static constexpr int CW = BN / 2;                     // accumulator columns per epilogue warp
+};
+
+struct Params {
+  int M, N, K, ldc;
+  float* C;
+  GemmEpilogue ep;
+};
+
+__device__ __forceinline__ void tmem_st16v(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+// (x0, x1) -> packed fp16 pair hi (x0 in the low half: element k of a K-major operand sits below element k+1) and the
+// packed pair of the scaled residuals
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                const __grid_constant__ CUtensorMap mapBhi,
+                                                                const __grid_constant__ CUtensorMap mapBlo, Params p) {
+  using cfg = Cfg<BN>;
+  constexpr int B_BYTES = cfg::B_BYTES, STAGE_BYTES = cfg::STAGE_BYTES, CW = cfg::CW;
+  constexpr uint32_t TM_MAIN = cfg::TM_MAIN, TM_CROSS = cfg::TM_CROSS, TM_A = cfg::TM_A;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle-128B tiles need 1024 B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers (8 B each): full_tma[S], split_done[S], empty[S], tmem_full, tmem_empty, then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (3 * STAGES), tempty_bar = bar_base + 8u * (3 * STAGES + 1);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(split_bar(s), SPLIT_WARPS); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), A_BYTES + 2 * B_BYTES);
+          tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sa + A_SUB, &mapA, full_bar(stage), kb * BK + 32, m0);
+          tma_load_2d(sa + A_BYTES, &mapBhi, full_bar(stage), kb * BK, n0);
+          tma_load_2d(sa + A_BYTES + B_BYTES, &mapBlo, full_bar(stage), kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+    // instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    const uint32_t d_main = tmem_base + TM_MAIN, d_cross = tmem_base + TM_CROSS;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      mbar_wait(tempty_bar, (uint32_t)(it & 1) ^ 1);               // epilogue drained the accumulators
+      tc_fence_after();
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(split_bar(stage), phase);                       // A hi/lo in TMEM (the splitters waited for the TMA: W landed too)
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint64_t b_hi = make_desc(sa + A_BYTES), b_lo = make_desc(sa + A_BYTES + B_BYTES);
+        const uint32_t a_hi = tmem_base + TM_A + 64u * stage, a_lo = a_hi + 32u;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {                     // UMMA_K = 16 (f16): +32 B in smem (+2 in the descriptor), +8 TMEM columns
+            const uint64_t adv = (uint64_t)(2 * k);
+            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_f16_ts(d_cross, a_lo + 8u * k, b_hi + adv, idesc, first);
+            umma_f16_ts(d_cross, a_hi + 8u * k, b_lo + adv, idesc, 1u);
+            umma_f16_ts(d_main, a_hi + 8u * k, b_hi + adv, idesc, first);
+          }
+          umma_commit(empty_bar(stage));                          // frees the stage (smem + TMEM A slab) when these MMAs retire
+          if (kb == nk - 1) umma_commit(tfull_bar);               // accumulators complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= SPLIT_WARP0) {
+    // ------------------------------------------------------------------ splitter: A slab (smem, raw fp32) -> hi / lo' fp16 -> TMEM
+    const int q = warp & 3;                                     // TMEM lane quarter this warp may write
+    const int row = q * 32 + lane;                              // tile row handled by this thread
+    const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        const uint8_t* a_raw = smem_gen + stage * STAGE_BYTES + row_off;
+        const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * stage;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                             // the two 32-wide boxes of the slab: k = 32j .. 32j+31 -> columns 16j .. 16j+15
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                           // 16-byte chunk c of the row = k 4c .. 4c+3 (swizzled position c ^ (row & 7))
+            const float4 x = *reinterpret_cast<const float4*>(a_raw + j * A_SUB + (((uint32_t)c ^ sw) << 4));
+            split2(x.x, x.y, hi[2 * c], lo[2 * c]);
+            split2(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
+          }
+          tmem_st16v(t_hi + 16u * j, hi);
+          tmem_st16v(t_hi + 32u + 16u * j, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
+    const int q = warp & 3;                                     // TMEM lane quarter this warp may read
+    const int ch = (warp - EPI_WARP0) >> 2;                     // column half: CW of the BN accumulator columns
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      mbar_wait(tfull_bar, (uint32_t)(it & 1));
+      tc_fence_after();
+      // drain main + cross accumulators into registers (one RN fma each), then hand TMEM back before any global traffic
+      uint32_t acc[CW];
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CW);
+#pragma unroll
+      for (int c = 0; c + 16 <= CW; c += 16) {
+        uint32_t x[16];
+        tmem_ld16_nowait(trow + TM_MAIN + c, acc + c);
+        tmem_ld16_nowait(trow + TM_CROSS + c, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c + j] = __float_as_uint(fmaf(__uint_as_float(x[j]), LO_INV, __uint_as_float(acc[c + j])));
+      }
+      if constexpr (CW % 16 == 8) {
+        constexpr int c = CW - 8;
+        uint32_t x[8];
+        tmem_ld8_nowait(trow + TM_MAIN + c, acc + c);
+        tmem_ld8_nowait(trow + TM_CROSS + c, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c + j] = __float_as_uint(fmaf(__uint_as_float(x[j]), LO_INV, __uint_as_float(acc[c + j])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);                  // next tile's MMAs may start
+      const int m = m0 + q * 32 + lane;
+      if (m < p.M) {
+        float* crow = p.C + (long long)m * p.ldc;
+        const float* prow = p.ep.pre ? p.ep.pre + (long long)m * p.ep.ldpre : nullptr;
+        const float* rrow = p.ep.residual ? p.ep.residual + (long long)m * p.ep.ldres : nullptr;
+        float* arow = p.ep.C_act ? p.ep.C_act + (long long)m * p.ldc : nullptr;
+        const int nbase = n0 + ch * CW;
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          const int n = nbase + j;
+          if (n >= p.N) break;                                  // N % 4 == 0 is required by the host wrapper
+          float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                 __uint_as_float(acc[j + 3]));
+          if (p.ep.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          if (prow) {
+            const float4 f = *reinterpret_cast<const float4*>(prow + n);
+            v.x *= act_bwd(f.x, p.ep.act); v.y *= act_bwd(f.y, p.ep.act);
+            v.z *= act_bwd(f.z, p.ep.act); v.w *= act_bwd(f.w, p.ep.act);
+          }
+          if (rrow) {
+            const float4 b = *reinterpret_cast<const float4*>(rrow + n);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          *reinterpret_cast<float4*>(crow + n) = v;
+          if (arow) {
+            float4 a = make_float4(act_fwd(v.x, p.ep.act), act_fwd(v.y, p.ep.act), act_fwd(v.z, p.ep.act),
+                                   act_fwd(v.w, p.ep.act));
+            *reinterpret_cast<float4*>(arow + n) = a;
+          }
+        }
+      }
+    }
+  }
+  // ---------------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// fp32 [N,K] (row stride ldw) -> hi / lo' fp16 planes [N, ldp], pad columns K .. ldp-1 zero
+__global__ void __launch_bounds__(256) pack_f16x3_kernel(const float* __restrict__ W, int ldw, __half* __restrict__ hi,
+                                                         __half* __restrict__ lo, int ldp, int N, int K) {
+  const long long total = (long long)N * ldp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ldp), k = (int)(i % ldp);
+    float x = 0.f;
+    if (k < K) x = W[(long long)n * ldw + k];
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn((x - __half2float(h)) * LO_SCALE);
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, int rows, int K, int ld, int box_k,
+                    int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return 1;
+  }
+  return 0;
+}
+
+static int ensure_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available");
+    return 1;
+  }
+  g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  return 0;
+}
+
+// Tile width for this launch: the BN whose tile count costs the fewest SM-waves x BN (ties go to the narrower tile).
+// A ragged launch carries the host's upper bound of the row count; the choice never changes a result bit.
+static int pick_bn(int M, int N) {
+  const int forced = gemm_tc_tile_n(-1);
+  if (forced) return forced;
+  const int sms = sm_count(), tiles_m = cdiv(M, BM);
+  int best = 128;
+  long long best_cost = 1ll << 60;
+  for (int bn : {128, 144, 160}) {
+    const long long cost = (long long)cdiv(tiles_m * cdiv(N, bn), sms) * bn;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int BN>
+static int launch_bn(const float* A, int lda, const BOperand& B, int M, int N, int K, const Params& p, cudaStream_t st) {
+  using cfg = Cfg<BN>;
+  CUtensorMap mapA, mapBhi, mapBlo;
+  MMX_TRY(make_map(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, 32, BM));
+  MMX_TRY(make_map(&mapBhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.hi, N, K, B.ldp, BK, BN));
+  MMX_TRY(make_map(&mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.lo, N, K, B.ldp, BK, BN));
+  // per device: the attribute belongs to the (function, device) pair
+  MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_f16x3_kernel<BN><<<grid, THREADS, cfg::SMEM_BYTES, st>>>(mapA, mapBhi, mapBlo, p);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace hx
+
+int pack_f16x3_ld(int K) { return round_up(K, 8); }
+size_t pack_f16x3_bytes(int N, int K) { return (size_t)2 * N * pack_f16x3_ld(K) * sizeof(uint16_t); }
+
+int pack_f16x3(const float* W, int ldw, int N, int K, void* packed, cudaStream_t st) {
+  if (N == 0 || K == 0) return 0;
+  MMX_REQUIRE(aligned16(packed), "packed operand must be 16-byte aligned");
+  const int ldp = pack_f16x3_ld(K);
+  __half* hi = reinterpret_cast<__half*>(packed);
+  __half* lo = hi + (size_t)N * ldp;
+  const long long total = (long long)N * ldp;
+  const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  hx::pack_f16x3_kernel<<<grid, 256, 0, st>>>(W, ldw, hi, lo, ldp, N, K);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+BOperand packed_operand(const float* W, int ldw, const void* packed, int N, int K) {
+  BOperand B;
+  B.w = W; B.ldw = ldw;
+  if (packed) {
+    B.ldp = pack_f16x3_ld(K);
+    B.hi = reinterpret_cast<const uint16_t*>(packed);
+    B.lo = B.hi + (size_t)N * B.ldp;
+  }
+  return B;
+}
+
+// Which problems go to this kernel.  Independent of M (a sample alone and inside a batch take the same arithmetic path).
+bool gemm_f16x3_shape_ok(const float* A, int lda, const BOperand& B, float* C, int ldc, int N, int K, const GemmEpilogue& ep) {
+  if (!gemm_tc_available() || !B.hi || !B.lo) return false;
+  if (N < 128 || K < 64 || (N % 4) || (lda % 4) || (B.ldp % 8) || (ldc % 4)) return false;   // K itself is free: TMA zero-fills the tail
+  if (!aligned16(A) || !aligned16(B.hi) || !aligned16(B.lo) || !aligned16(C)) return false;
+  if ((ep.bias && !aligned16(ep.bias)) || (ep.pre && (!aligned16(ep.pre) || ep.ldpre % 4)) ||
+      (ep.residual && (!aligned16(ep.residual) || ep.ldres % 4)) || (ep.C_act && !aligned16(ep.C_act)))
+    return false;
+  return true;
+}
+
+int gemm_nt_f16x3(const float* A, int lda, const BOperand& B, float* C, int ldc, int M, int N, int K, const GemmEpilogue& ep,
+                  cudaStream_t st) {
+  if (M == 0 || N == 0) return 0;
+  MMX_TRY(hx::ensure_encode());
+  hx::Params p{M, N, K, ldc, C, ep};
+  switch (hx::pick_bn(M, N)) {
+    case 144: return hx::launch_bn<144>(A, lda, B, M, N, K, p, st);
+    case 160: return hx::launch_bn<160>(A, lda, B, M, N, K, p, st);
+    default: return hx::launch_bn<128>(A, lda, B, M, N, K, p, st);
+  }
+}
+
+}  // namespace mmx

@@ -1,6 +1,7 @@
 // Row-wise kernels around the GEMMs: LayerNorm forward/backward (one warp per row), CLIP token assembly
 // (patch im2col, class/positional embedding, token embedding) and the logit head with its analytic backward.
 #include "mmx_common.cuh"
+#include <math_constants.h>
 #include <initializer_list>
 
 namespace mmx {
@@ -332,7 +333,8 @@ __global__ void cls_rows_kernel(int* __restrict__ rows, int B, int S) {
 __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict__ fi, const float* __restrict__ ft,
                                                         float logit_scale_exp, float* __restrict__ fin,
                                                         float* __restrict__ ftn, float* __restrict__ dfi,
-                                                        float* __restrict__ dft, float* __restrict__ diag, int B, int E) {
+                                                        float* __restrict__ dft, float* __restrict__ diag,
+                                                        float* __restrict__ gs_i, float* __restrict__ gs_t, int B, int E) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* a = fi + (long long)b * E;
@@ -343,12 +345,26 @@ __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict_
   float c = 0.f;
   for (int i = lane; i < E; i += 32) c = fmaf(a[i] / na, t[i] / nt, c);
   c = warp_sum(c);
+  float mi = 0.f, mt = 0.f;
   for (int i = lane; i < E; i += 32) {
     const float an = a[i] / na, tn = t[i] / nt;
     fin[(long long)b * E + i] = an;
     ftn[(long long)b * E + i] = tn;
-    dfi[(long long)b * E + i] = logit_scale_exp / na * (tn - c * an);
-    dft[(long long)b * E + i] = logit_scale_exp / nt * (an - c * tn);
+    const float gi = logit_scale_exp / na * (tn - c * an), gt = logit_scale_exp / nt * (an - c * tn);
+    dfi[(long long)b * E + i] = gi;
+    dft[(long long)b * E + i] = gt;
+    mi = fmaxf(mi, fabsf(gi)); mt = fmaxf(mt, fabsf(gt));
+  }
+  if (gs_i) {
+    // Per-sample power-of-two normalisation of the seed gradient (max |d feat| -> [16, 32)): the fp16x3 GEMMs of the
+    // dgrad sweep then see magnitudes inside fp16's range whatever the model's logit scale / feature norm is; the
+    // attention backward divides the staged dA by the same factor.  Exact (powers of two) and per sample.
+    mi = warp_max(mi); mt = warp_max(mt);
+    const float si = (mi > 0.f && mi < CUDART_INF_F) ? exp2f(4.f - (float)ilogbf(mi)) : 1.f;
+    const float st2 = (mt > 0.f && mt < CUDART_INF_F) ? exp2f(4.f - (float)ilogbf(mt)) : 1.f;
+    __syncwarp();
+    for (int i = lane; i < E; i += 32) { dfi[(long long)b * E + i] *= si; dft[(long long)b * E + i] *= st2; }
+    if (lane == 0) { gs_i[b] = si; gs_t[b] = st2; }
   }
   if (lane == 0 && diag) diag[b] = logit_scale_exp * c;
 }
@@ -451,9 +467,9 @@ int cls_rows(int* rows, int B, int S, cudaStream_t st) {
   MMX_LAUNCH_CHECK();
   return 0;
 }
-int clip_head(const float* fi, const float* ft, float lse, float* fin, float* ftn, float* dfi, float* dft, float* diag, int B,
-              int E, cudaStream_t st) {
-  clip_head_kernel<<<cdiv(B, 8), 256, 0, st>>>(fi, ft, lse, fin, ftn, dfi, dft, diag, B, E);
+int clip_head(const float* fi, const float* ft, float lse, float* fin, float* ftn, float* dfi, float* dft, float* diag,
+              float* gs_i, float* gs_t, int B, int E, cudaStream_t st) {
+  clip_head_kernel<<<cdiv(B, 8), 256, 0, st>>>(fi, ft, lse, fin, ftn, dfi, dft, diag, gs_i, gs_t, B, E);
   MMX_LAUNCH_CHECK();
   return 0;
 }

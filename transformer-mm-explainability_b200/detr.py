@@ -125,7 +125,7 @@ class DetrEngine:
                 cls = torch.as_tensor(index, device=dev).reshape(B).long()
             one_hot = torch.zeros_like(logits.v)
             one_hot[rows, cls] = 1.0
-            logits.g = one_hot
+            tape.seed(logits, one_hot, B)
             tape.backward()
             self._shape = (B, S, Q)
         return {"pred_logits": self.pred_logits}

@@ -159,7 +159,7 @@ class LxmertEngine:
             idx = logits.v.argmax(-1) if index is None else torch.as_tensor(index, device=dev).reshape(B).long()
             one_hot = torch.zeros_like(logits.v)
             one_hot[torch.arange(B, device=dev), idx] = 1.0                     # ExplanationGenerator.py:152-160
-            logits.g = one_hot
+            tape.seed(logits, one_hot, B)
             tape.backward()
             self._shape = (B, T, I)
         return self.question_answering_score

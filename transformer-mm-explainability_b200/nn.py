@@ -43,21 +43,46 @@ class Var:
         return self.v.shape[1]
 
 
+def pack_weight(w: torch.Tensor) -> Optional[torch.Tensor]:
+    """fp16 hi / lo planes of a static [N, K] GEMM operand for the fp16x3 tensor-core backend (``mmx_pack_weight``);
+    None when the matrix is below the tensor-core kernel's minimum tile (N < 128 or K < 64: the fp32 path runs)."""
+    N, K = w.shape
+    if N < 128 or K < 64:
+        return None
+    l = lib()
+    buf = torch.empty(l.mmx_pack_weight_bytes(N, K), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        check(l.mmx_pack_weight(ptr(w), w.stride(0), N, K, ptr(buf), current_stream()))
+    return buf
+
+
 class Weight:
-    """Linear weight [out, in] plus its transpose (the K-major operand of the dgrad GEMM) and optional bias."""
+    """Linear weight [out, in] plus its transpose (the K-major operand of the dgrad GEMM), their packed fp16x3 copies
+    and the optional bias."""
 
     def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], device):
         self.w = _f32(w, device)
         self.wt = self.w.t().contiguous()
         self.b = _f32(b, device) if b is not None else None
         self.out_features, self.in_features = self.w.shape
+        self.pw, self.pwt = pack_weight(self.w), pack_weight(self.wt)
 
 
 class Tape:
+    # Power-of-two factor the seed gradient is multiplied by (and every staged dA divided by, exactly): keeps the
+    # operands of the fp16x3 dgrad GEMMs well inside fp16's exponent range (csrc/gemm_f16x3.cu).
+    GRAD_SCALE = 256.0
+
     def __init__(self, device):
         self.device = torch.device(device)
         self.ops: List[Callable[[], None]] = []
         self.lib = lib()
+        self.gscale: Optional[torch.Tensor] = None
+
+    def seed(self, var: "Var", one_hot: torch.Tensor, B: int):
+        """var.g = GRAD_SCALE * one_hot; the attention backwards stage dA / GRAD_SCALE (the true gradient)."""
+        var.g = one_hot * self.GRAD_SCALE
+        self.gscale = torch.full((B,), self.GRAD_SCALE, device=self.device, dtype=torch.float32)
 
     # ------------------------------------------------------------------ helpers
     def new(self, rows, cols) -> torch.Tensor:
@@ -82,8 +107,8 @@ class Tape:
         assert K == W.in_features, (K, W.in_features)
         pre = self.new(M, N)
         out = self.new(M, N) if act else None
-        check(self.lib.mmx_linear(ptr(x.v), x.v.stride(0), ptr(W.w), K, ptr(W.b), None, 0, ptr(pre), N, ptr(out), act, M, N, K,
-                                  current_stream()))
+        check(self.lib.mmx_linear_packed(ptr(x.v), x.v.stride(0), ptr(W.w), K, ptr(W.pw), ptr(W.b), None, 0, ptr(pre), N,
+                                         ptr(out), act, M, N, K, current_stream()))
         y = Var(out if act else pre)
 
         def bwd():
@@ -95,8 +120,8 @@ class Tape:
                 check(self.lib.mmx_act_bwd(ptr(dy), dy.stride(0), ptr(pre), N, act, ptr(dpre), N, M, N, current_stream()))
                 dy = dpre
             dx = self.new(M, K)
-            check(self.lib.mmx_linear_dgrad(ptr(dy), dy.stride(0), ptr(W.wt), N, None, 0, 0, ptr(dx), K, M, N, K,
-                                            current_stream()))
+            check(self.lib.mmx_linear_dgrad_packed(ptr(dy), dy.stride(0), ptr(W.wt), N, ptr(W.pwt), None, 0, 0, ptr(dx), K,
+                                                   M, N, K, current_stream()))
             self.accumulate(x, dx)
         self.ops.append(bwd)
         return y
@@ -187,9 +212,10 @@ class Tape:
             dA = torch.empty_like(A)
             delta = torch.empty(B, H, T, device=self.device, dtype=torch.float32)
             dq, dk, dv = self.new(B * T, Dm), self.new(B * S, Dm), self.new(B * S, Dm)
-            check(self.lib.mmx_attention_bwd(ptr(y.g), y.g.stride(0), ptr(q.v), q.v.stride(0), ptr(k.v), k.v.stride(0), ptr(v.v),
-                                             v.v.stride(0), ptr(A), ptr(dA), ldA, ptr(delta), ptr(dq), Dm, ptr(dk), Dm, ptr(dv),
-                                             Dm, B, H, T, S, hd, C.c_float(scale), flags, current_stream()))
+            check(self.lib.mmx_attention_bwd_scaled(ptr(y.g), y.g.stride(0), ptr(q.v), q.v.stride(0), ptr(k.v), k.v.stride(0),
+                                                    ptr(v.v), v.v.stride(0), ptr(A), ptr(dA), ldA, ptr(delta), ptr(dq), Dm,
+                                                    ptr(dk), Dm, ptr(dv), Dm, B, H, T, S, hd, C.c_float(scale), flags,
+                                                    ptr(self.gscale), current_stream()))
             if record is not None:
                 record.dA = dA
             self.accumulate(q, dq)

@@ -111,7 +111,7 @@ class VisualBertEngine:
                 idx = scores.v.argmax(-1) if index is None else torch.as_tensor(index, device=dev).reshape(-1).expand(B).long()
                 one_hot = torch.zeros_like(scores.v)
                 one_hot[torch.arange(B, device=dev), idx] = 1.0
-                scores.g = one_hot
+                tape.seed(scores, one_hot, B)
                 tape.backward()
         return self.scores
 

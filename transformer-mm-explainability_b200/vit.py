@@ -85,7 +85,7 @@ class ViTEngine:
             idx = logits.v.argmax(-1) if index is None else torch.as_tensor(index, device=self.device).reshape(B)
             one_hot = torch.zeros_like(logits.v)
             one_hot[torch.arange(B, device=self.device), idx.long()] = 1.0      # ipynb:1186-1190
-            logits.g = one_hot
+            tape.seed(logits, one_hot, B)
             tape.backward()
         return self.logits
 
