@@ -37,6 +37,10 @@ uint64_t mmx_launch_count(void);
  * All three are fp32-faithful (<= 2e-5 of max|C| against fp64).  Env MMX_GEMM_BACKEND overrides the default.
  * Returns the backend in effect. */
 int mmx_set_gemm_backend(int backend);
+/* The backend in effect.  The LRP sweeps (use_lrp=True) switch to backend 0 for their forward, backward and relprop and
+ * restore this value afterwards: relprop divides by activations and sums that nearly cancel, which amplifies the 1e-6
+ * rounding of the tensor-core splits by several orders of magnitude (measured: tests/test_lrp_gpu.py). */
+int mmx_get_gemm_backend(void);
 /* Tile width of the tcgen05 backend: 0 = automatic (the width in {128, 144, 160} whose tile count best fills whole
  * waves of SMs), or one of 128 / 144 / 160 to force it (profiling and the bit-equality test: the width never changes a
  * result bit).  Env MMX_TC_BN sets the initial value.  Returns the value in effect. */
@@ -140,6 +144,8 @@ int mmx_bmm_add(const float* A, int lda, long long strideA, int transA, const fl
 #define MMX_ACT_GELU       2   /* exact erf GELU (timm ViT, LXMERT) */
 #define MMX_ACT_RELU       3   /* DETR FFN, DETR/models/transformer.py:239 */
 #define MMX_ACT_TANH       4   /* LXMERT pooler, lxmert/lxmert/src/lxmert_lrp.py:868-884 */
+#define MMX_ACT_MUL        5   /* not an activation: the `pre` operand of a GEMM epilogue multiplies the product itself
+                                  (C = (A W^T) (.) pre), the `x * (S W)` step of Linear.relprop, DETR/modules/layers.py:421-423 */
 
 /* C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (+ residual[M,N]);  if act != NONE and C_act != NULL also writes
  * C_act = act(C).  F.linear of CLIP/clip/auxilary.py:77,255 and CLIP/clip/model.py:175-177. */
@@ -166,6 +172,13 @@ int mmx_linear_packed(const float* A, int lda, const float* W, int ldw, const vo
                       void* stream);
 int mmx_linear_dgrad_packed(const float* dY, int lddy, const float* Wt, int ldwt, const void* packed_t, const float* pre,
                             int ldpre, int act, float* dX, int lddx, int M, int N, int K, void* stream);
+
+/* The general form behind the four entry points above:  C = ((A[M,K] * Bt[N,K]^T + bias) (.) act'(pre)) + residual, and
+ * C_act = act(C) when given.  bias / pre / residual / C_act / packed may be NULL.  With act = MMX_ACT_MUL the product is
+ * multiplied by `pre` itself. */
+int mmx_gemm_nt(const float* A, int lda, const float* Bt, int ldb, const void* packed, const float* bias, const float* pre,
+                int ldpre, const float* residual, int ldres, float* C, int ldc, float* C_act, int act, int M, int N, int K,
+                void* stream);
 
 /* Small glue kernels for the host-side generators (DETR / LXMERT / ViT orchestration; row-major [rows, cols] with
  * row strides in elements).  They replace elementwise torch ops of the reference models (positional-embedding adds
@@ -249,6 +262,10 @@ int mmx_clip_interpret_device(mmx_clip* h, const float* images, int n_images, co
 int mmx_clip_interpret_host(mmx_clip* h, const float* images, int n_images, const int32_t* tokens, int B,
                             int start_layer, int start_layer_text, float* R_text, float* R_image);
 
+/* Measurement aid: serial != 0 puts both towers on ONE stream (results unchanged), so that per-launch CUDA-event times do
+ * not overlap and the time of a kernel family is a true share of the step; 0 restores the two concurrent tower streams. */
+int mmx_clip_set_serial(mmx_clip* h, int serial);
+
 /* Test taps: device pointers into the engine workspace after the last interpret (valid for batch <= max_batch,
  * first micro-batch).  what: "A" / "dA" / "Abar" (tower 0 = vision, 1 = text, layer index), "logits" ([B,B]).
  * Writes the pointer, the dims (up to 4) and the row stride of the last dim. */
@@ -262,6 +279,54 @@ int mmx_attention_bwd_scaled(const float* dO, int lddo, const float* Q, int ldq,
                              const float* V, int ldv, const float* A, float* dA, int ldA, float* delta,
                              float* dQ, int lddq, float* dK, int lddk, float* dV, int lddv,
                              int B, int H, int T, int S, int hd, float scale, int flags, const float* gscale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LRP (`relprop`) primitives: the second sweep behind use_lrp=True / generate_transformer_att / generate_partial_lrp
+ * (SURVEY.md §8f-4).  The reference runs it through autograd (gradient x input per layer, DETR/modules/layers.py:38-66);
+ * these are the same rules as direct kernels.  Matrices are row-major [B * rows_per_sample, cols] with row strides in
+ * elements; one "sample" is what the reference treats as the whole tensor (it runs relprop with batch 1).
+ * Whole-sample sums are carried as `partials`: mmx_lrp_partials_len() * k doubles per sample (k = 2: sum and abs-sum,
+ * k = 3 inside mmx_lrp_add), reduced in a fixed order by the consumer, so results are deterministic.
+ * ------------------------------------------------------------------------------------------------------- */
+/* P = clamp(X, min=0), N = clamp(X, max=0): the positive / negative parts of Linear.relprop (layers.py:411-414) */
+int mmx_lrp_split(const float* X, int ldx, float* P, float* N, int ld, long long rows, int cols, void* stream);
+/* S = safe_divide(R, Z) (layers.py:11-14): R / (Z + 1e-9) (1e-9 when that is 0), and 0 where Z == 0 */
+int mmx_lrp_safe_divide(const float* R, int ldr, const float* Z, int ldz, float* S, int lds, long long rows, int cols,
+                        void* stream);
+int mmx_lrp_partials_len(void);
+/* partials[b][c] = {sum, sum of |x|} over chunk c of sample b (the `R.sum()`, `out.sum()`, `cam_v.min() == cam_v.max() == 0`
+ * reductions of layers.py:430-432,786-799) */
+int mmx_lrp_sums(const float* X, int ldx, int rows_per_sample, int cols, int B, double* partials, void* stream);
+/* X[b] *= safe_divide(sum(num[b]), sum(den[b])): the renormalisation that ends DETR's Linear.relprop (layers.py:430-432) */
+int mmx_lrp_renorm(float* X, int ldx, int rows_per_sample, int cols, int B, const double* num_partials,
+                   const double* den_partials, void* stream);
+/* Add.relprop (layers.py:194-221; lxmert/lxmert/src/layers.py Add): S = safe_divide(R, x0 + x1), a = x0 S, b = x1 S, each
+ * rescaled to its share |sum a| : |sum b| of sum R.  b may be NULL.  workspace: 3 * partials_len doubles per sample. */
+int mmx_lrp_add(const float* R, int ldr, const float* x0, int ld0, const float* x1, int ld1, float* a, int lda, float* b,
+                int ldb, int rows_per_sample, int cols, int B, double* workspace, void* stream);
+/* Clone.relprop (layers.py:252-270): out = X * sum_i safe_divide(R[i], X), i < n <= 8 (R: host array of device pointers).
+ * With n = 1 it is also IndexSelect.relprop on the selected rows (layers.py:230-249). */
+int mmx_lrp_clone(const float* X, int ldx, const float* const* R, const int* ldr, int n, float* out, int ldo, long long rows,
+                  int cols, void* stream);
+/* The all-zero-value case of MultiheadAttention.relprop (layers.py:786-799), decided per sample ON THE DEVICE: when the
+ * value relevance is all zero after its projection but was not before, cam_q and cam_k are rescaled to share sum(cam). */
+int mmx_lrp_zero_value_fix(float* cam_q, int ldq, int rows_q, float* cam_k, int ldk, int rows_k, int cols, int B,
+                           const double* v_pre, const double* v_post, const double* q_sums, const double* k_sums,
+                           const double* cam_sums, void* stream);
+/* RelPropSimple through attn @ v (layers.py:776-781; lxmert_lrp.py:431-437): with Sv = safe_divide(R_o, O),
+ * cam_A[b,h,i,j] = A (.) (Sv V^T) / 2 staged in A's [B,H,T,ldA] layout (pad columns zero) - this is `attn_cam` - and
+ * cam_V[b*S+j, h*hd+d] = V (.) (A^T Sv) / 2.  R_o, O: [B*T, H*hd]; V: [B*S, H*hd]. */
+int mmx_lrp_attn_pv(const float* R_o, int ldr, const float* O, int ldo, const float* A, int ldA, const float* V, int ldv,
+                    float* cam_A, float* cam_V, int ldcv, int B, int H, int T, int S, int hd, void* stream);
+/* RelPropSimple through q @ k^T (layers.py:783-785; lxmert_lrp.py:441-447): Z = zscale * Q K^T, S2 = safe_divide(cam1, Z),
+ * cam_Q = (zscale Q) (.) (S2 K) / 2, cam_K = K (.) (S2^T zscale Q) / 2.  zscale = hd^-1/2 where the reference scales q before
+ * the product (DETR), 1 where it divides the scores afterwards (LXMERT, VisualBERT). */
+int mmx_lrp_attn_qk(const float* cam1, int ldA, const float* Q, int ldq, const float* K, int ldk, float zscale, float* cam_Q,
+                    int ldcq, float* cam_K, int ldck, int B, int H, int T, int S, int hd, void* stream);
+/* scores = zscale * Q K^T and mask[b,h,i,j] = key_bias[b,j] in the [B,H,T,ldA] layout: the two inputs of the Add that
+ * VisualBERT's BertSelfAttention.relprop sends the relevance through (BERT_ours.py:352-395).  mask / key_bias may be NULL. */
+int mmx_lrp_attn_scores(const float* Q, int ldq, const float* K, int ldk, const float* key_bias, float zscale, float* scores,
+                        float* mask, int ldA, int B, int H, int T, int S, int hd, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ VIT_B32 = ClipConfig()
 VIT_L14_336 = ClipConfig(768, 336, 24, 1024, 14, 77, 49408, 768, 12, 12)
 TINY = ClipConfig(32, 32, 2, 64, 16, 8, 64, 32, 2, 2)           # golden-fixture size
 SMALL = ClipConfig(64, 64, 3, 128, 16, 16, 512, 64, 2, 3)        # 17 vision tokens (odd), 16 text tokens
+EXAMPLE = ClipConfig(32, 224, 3, 64, 32, 16, 100, 64, 2, 2)      # 7x7 patches at 224 px: the grid CLIP/example.py:42 hard-codes
 
 
 def init_state_dict(cfg: ClipConfig, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:

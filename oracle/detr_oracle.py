@@ -22,71 +22,9 @@ import torch.nn.functional as F
 from . import rules as R_
 
 
-@dataclass(frozen=True)
-class DetrConfig:
-    d_model: int = 256
-    nhead: int = 8
-    enc_layers: int = 6
-    dec_layers: int = 6
-    dim_ff: int = 2048
-    queries: int = 100
-    classes: int = 91          # logits have classes + 1 entries (last = no-object)
-
-
-DETR_R50 = DetrConfig()
-DETR_TINY = DetrConfig(64, 2, 2, 2, 96, 7, 5)
-
-
-def init_state_dict(cfg: DetrConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
-    g = torch.Generator().manual_seed(seed)
-    sd: Dict[str, torch.Tensor] = {}
-
-    def xavier(o, i):
-        b = (6.0 / (o + i)) ** 0.5
-        return (torch.rand(o, i, generator=g) * 2 - 1) * b
-
-    def vec(n, s=0.05):
-        return torch.randn(n, generator=g) * s
-
-    def mha(p):
-        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
-            sd[p + nm + ".weight"] = xavier(cfg.d_model, cfg.d_model)
-            sd[p + nm + ".bias"] = vec(cfg.d_model)
-
-    def ffn_norms(p, norms):
-        sd[p + "linear1.weight"] = xavier(cfg.dim_ff, cfg.d_model); sd[p + "linear1.bias"] = vec(cfg.dim_ff)
-        sd[p + "linear2.weight"] = xavier(cfg.d_model, cfg.dim_ff); sd[p + "linear2.bias"] = vec(cfg.d_model)
-        for n in norms:
-            sd[p + n + ".weight"] = 1 + vec(cfg.d_model, 0.1); sd[p + n + ".bias"] = vec(cfg.d_model)
-
-    for i in range(cfg.enc_layers):
-        p = f"transformer.encoder.layers.{i}."
-        mha(p + "self_attn."); ffn_norms(p, ("norm1", "norm2"))
-    for i in range(cfg.dec_layers):
-        p = f"transformer.decoder.layers.{i}."
-        mha(p + "self_attn."); mha(p + "multihead_attn."); ffn_norms(p, ("norm1", "norm2", "norm3"))
-    sd["transformer.decoder.norm.weight"] = 1 + vec(cfg.d_model, 0.1)
-    sd["transformer.decoder.norm.bias"] = vec(cfg.d_model)
-    sd["query_embed.weight"] = torch.randn(cfg.queries, cfg.d_model, generator=g)
-    sd["class_embed.weight"] = xavier(cfg.classes + 1, cfg.d_model)
-    sd["class_embed.bias"] = vec(cfg.classes + 1)
-    return sd
-
-
-def sine_position_embedding(B: int, h: int, w: int, d_model: int, temperature: float = 10000.0) -> torch.Tensor:
-    """PositionEmbeddingSine(normalize=True) for an all-valid mask (DETR/models/position_encoding.py:28-50)."""
-    npf = d_model // 2
-    ones = torch.ones(B, h, w)
-    y_embed, x_embed = ones.cumsum(1), ones.cumsum(2)
-    eps, scale = 1e-6, 2 * torch.pi
-    y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
-    x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
-    dim_t = torch.arange(npf, dtype=torch.float32)
-    dim_t = temperature ** (2 * (dim_t // 2) / npf)
-    pos_x, pos_y = x_embed[:, :, :, None] / dim_t, y_embed[:, :, :, None] / dim_t
-    pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
-    pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
-    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+# configs, random-init weights and synthetic inputs are shared with bench.py: they live in mmx_b200/synthetic.py
+from mmx_b200.synthetic import (DetrConfig, DETR_R50, DETR_TINY, detr_init_state_dict as init_state_dict,  # noqa: E402,F401
+                                detr_sine_position_embedding as sine_position_embedding, detr_synthetic_inputs as synthetic_inputs)
 
 
 def _mha(sd, p, query, key, value, H, stage: List[torch.Tensor]):
@@ -264,14 +202,6 @@ def generate_lrp_baseline(sd, cfg: DetrConfig, src, pos, target_index, method: s
                 R = (R - R.min()) / (R.max() - R.min())
             out.append(R[tq[b]])
     return torch.stack(out)
-
-
-def synthetic_inputs(cfg: DetrConfig, B: int, h: int, w: int, seed: int = 0):
-    g = torch.Generator().manual_seed(seed)
-    src = torch.randn(B, cfg.d_model, h, w, generator=g)
-    pos = sine_position_embedding(B, h, w, cfg.d_model)
-    tq = torch.randint(0, cfg.queries, (B,), generator=g)
-    return src, pos, tq
 
 
 def to_checkpoint_format(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -23,79 +23,9 @@ import torch.nn.functional as F
 from . import rules as R_
 
 
-@dataclass(frozen=True)
-class LxmertConfig:
-    hidden: int = 768
-    heads: int = 12
-    intermediate: int = 3072
-    l_layers: int = 9
-    x_layers: int = 5
-    r_layers: int = 5
-    vocab: int = 30522
-    max_pos: int = 512
-    feat_dim: int = 2048
-    pos_dim: int = 4
-    num_labels: int = 3129
-
-
-LXMERT_BASE = LxmertConfig()
-LXMERT_TINY = LxmertConfig(hidden=64, heads=2, intermediate=96, l_layers=2, x_layers=2, r_layers=2, vocab=50, max_pos=16,
-                           feat_dim=24, pos_dim=4, num_labels=11)
-
-
-def init_state_dict(cfg: LxmertConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
-    g = torch.Generator().manual_seed(seed)
-    sd: Dict[str, torch.Tensor] = {}
-    Hd = cfg.hidden
-
-    def lin(p, o, i, std=None):
-        sd[p + ".weight"] = torch.randn(o, i, generator=g) * (std if std else i ** -0.5)
-        sd[p + ".bias"] = torch.randn(o, generator=g) * 0.02
-
-    def ln(p, d):
-        sd[p + ".weight"] = 1 + 0.1 * torch.randn(d, generator=g)
-        sd[p + ".bias"] = 0.05 * torch.randn(d, generator=g)
-
-    def att(p):
-        for n in ("query", "key", "value"):
-            lin(p + n, Hd, Hd)
-
-    def att_out(p):
-        lin(p + "dense", Hd, Hd); ln(p + "LayerNorm", Hd)
-
-    def ffn(pi, po):
-        lin(pi + "dense", cfg.intermediate, Hd); lin(po + "dense", Hd, cfg.intermediate); ln(po + "LayerNorm", Hd)
-
-    e = "lxmert.embeddings."
-    sd[e + "word_embeddings.weight"] = torch.randn(cfg.vocab, Hd, generator=g) * 0.5
-    sd[e + "position_embeddings.weight"] = torch.randn(cfg.max_pos, Hd, generator=g) * 0.5
-    sd[e + "token_type_embeddings.weight"] = torch.randn(2, Hd, generator=g) * 0.5
-    ln(e + "LayerNorm", Hd)
-    v = "lxmert.encoder.visn_fc."
-    lin(v + "visn_fc", Hd, cfg.feat_dim); ln(v + "visn_layer_norm", Hd); lin(v + "box_fc", Hd, cfg.pos_dim); ln(v + "box_layer_norm", Hd)
-    for name, n in (("layer", cfg.l_layers), ("r_layers", cfg.r_layers)):
-        for i in range(n):
-            p = f"lxmert.encoder.{name}.{i}."
-            att(p + "attention.self."); att_out(p + "attention.output."); ffn(p + "intermediate.", p + "output.")
-    for i in range(cfg.x_layers):
-        p = f"lxmert.encoder.x_layers.{i}."
-        att(p + "visual_attention.att."); att_out(p + "visual_attention.output.")
-        for s in ("lang_self_att", "visn_self_att"):
-            att(p + s + ".self."); att_out(p + s + ".output.")
-        ffn(p + "lang_inter.", p + "lang_output."); ffn(p + "visn_inter.", p + "visn_output.")
-    lin("lxmert.pooler.dense", Hd, Hd)
-    lin("answer_head.logit_fc.0", 2 * Hd, Hd); ln("answer_head.logit_fc.2", 2 * Hd); lin("answer_head.logit_fc.3", cfg.num_labels, 2 * Hd)
-    return sd
-
-
-def synthetic_inputs(cfg: LxmertConfig, B: int, T: int, I: int, seed: int = 0):
-    g = torch.Generator().manual_seed(seed)
-    ids = torch.randint(3, cfg.vocab, (B, T), generator=g)
-    ids[:, 0] = 1
-    ids[:, -1] = 2
-    feats = torch.randn(B, I, cfg.feat_dim, generator=g)
-    boxes = torch.rand(B, I, cfg.pos_dim, generator=g)
-    return ids, feats, boxes
+# configs, random-init weights and synthetic inputs are shared with bench.py: they live in mmx_b200/synthetic.py
+from mmx_b200.synthetic import (LxmertConfig, LXMERT_BASE, LXMERT_TINY, lxmert_init_state_dict as init_state_dict,  # noqa: E402,F401
+                                lxmert_synthetic_inputs as synthetic_inputs)
 
 
 def _lnorm(sd, p, x):

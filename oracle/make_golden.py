@@ -56,6 +56,23 @@ def golden_clip(tag, cfg, batch, wseed, iseed):
     print("wrote", tag, {k: v.shape for k, v in out.items() if not k.startswith("sd.")})
 
 
+def golden_clip_example():
+    """CLIP/example.py:8-53 (the older interpret: one image, N texts, ``index``, all image blocks) run unmodified."""
+    cfg = co.EXAMPLE
+    sd = co.init_state_dict(cfg, seed=4)
+    images, tokens = co.synthetic_inputs(cfg, 3, seed=21)
+    model = rs.build_reference_clip(cfg, sd)
+    out = {"cfg": np.array(cfg.ref_args(), dtype=np.int64), "image": images[:1].numpy(), "tokens": tokens.numpy()}
+    for k, v in sd.items():
+        out["sd." + k] = v.numpy()
+    for index in (None, 0, 1, 2):
+        R, logits = rs.reference_example_interpret(images[:1], tokens, model, "cpu", index)
+        out[f"R.index{index}"] = R.numpy()
+        out["logits_per_image"] = logits.numpy()
+    np.savez_compressed(os.path.join(OUT, "clip_example.npz"), **out)
+    print("wrote clip_example", {k: v.shape for k, v in out.items() if not k.startswith("sd.")})
+
+
 def golden_rules():
     detr = _load_module("ref_detr_eg", "DETR/modules/ExplanationGenerator.py")
     lx = _load_module("ref_lxmert_eg", "lxmert/lxmert/src/ExplanationGenerator.py")
@@ -218,6 +235,9 @@ def main():
     if "--otsu" in argv:
         golden_otsu()
         return
+    if "--clip-example" in argv:
+        golden_clip_example()
+        return
     if "--only-new" in argv:
         golden_detr()
         golden_lxmert()
@@ -227,6 +247,7 @@ def main():
     golden_rules()
     golden_clip("tiny", co.TINY, 3, wseed=1, iseed=7)
     golden_clip("small", co.SMALL, 4, wseed=2, iseed=11)
+    golden_clip_example()
     golden_detr()
     golden_lxmert()
     golden_visualbert()

@@ -78,3 +78,36 @@ def reference_interpret(image, texts, model, device="cpu", start_layer=-1, start
     with cuda_is_identity():
         return ns["interpret"](image, texts, model, device, start_layer=start_layer,
                                start_layer_text=start_layer_text)
+
+
+def reference_example_interpret(image, text, model, device="cpu", index=None):
+    """Runs the older ``interpret`` of CLIP/example.py:8-53 (one image, N texts, all image blocks, ``R[0,0] = 0``) by
+    exec-ing the function source straight from the reference file.  The function plots and returns nothing; the relevance
+    vector is captured where the unmodified code hands it to ``torch.nn.functional.interpolate`` (:42-43).  matplotlib is
+    absent in this image and is stubbed (``plt.imshow`` / ``plt.show`` are no-ops); needs a 7x7 patch grid at 224 px
+    (hard-coded in :42-43).  Returns (image_relevance [49], logits_per_image [1,N])."""
+    _ensure_path()
+    import numpy as np
+    import torch
+    import cv2
+    with open(os.path.join(REFERENCE_ROOT, "CLIP", "example.py")) as f:
+        src = f.read()
+    start, end = src.index("def interpret("), src.index("def main(")
+    plt = types.SimpleNamespace(imshow=lambda *a, **k: None, show=lambda *a, **k: None)
+    ns = {"torch": torch, "np": np, "cv2": cv2, "plt": plt, "print": lambda *a, **k: None}
+    exec(compile(src[start:end], "CLIP/example.py:interpret", "exec"), ns)
+    captured = {}
+    orig = torch.nn.functional.interpolate
+
+    def spy(x, *a, **k):
+        captured["R"] = x.detach().clone().reshape(-1)
+        return orig(x, *a, **k)
+
+    torch.nn.functional.interpolate = spy
+    try:
+        with cuda_is_identity():
+            ns["interpret"](image, text, model, device, index)
+            logits, _ = model(image, text)
+    finally:
+        torch.nn.functional.interpolate = orig
+    return captured["R"], logits.detach()

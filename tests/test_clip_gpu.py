@@ -169,3 +169,73 @@ def test_vit_l14_336_vs_oracle(mmx):
     rt, ri = mmx.interpret(images.cuda(), tokens.cuda(), eng, "cuda:0", 0, 0)
     assert ri.shape == (2, 576) and rt.shape == (2, 77, 77)
     assert text_rel_err(rt, ot) < TOL and rel_err(ri, oi) < TOL
+
+
+class _RefLikeClip:
+    """Stands in for the reference ``CLIP`` nn.Module on the GPU box (the reference tree does not travel): what
+    ``interpret`` needs from it is ``state_dict()`` with the reference's key names (CLIP/clip/model.py:248-303)."""
+
+    def __init__(self, sd, text_heads):
+        import types
+        self._sd = dict(sd)
+        self.calls = 0
+        attn = types.SimpleNamespace(num_heads=text_heads)            # nn.MultiheadAttention.num_heads of the text blocks
+        self.transformer = types.SimpleNamespace(resblocks=[types.SimpleNamespace(attn=attn)])
+
+    def state_dict(self):
+        self.calls += 1
+        return self._sd
+
+
+def test_notebook_call_form_with_reference_module(mmx, golden_dir):
+    """The notebook cells call ``interpret(model=model, image=img, texts=text, device=device)`` with the reference module
+    (CLIP_explainability.ipynb cells 12-19): that exact call must work, build ONE engine per module, and give the goldens."""
+    g = np.load(os.path.join(golden_dir, "clip_small.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    model, device = _RefLikeClip(sd, int(g["cfg"][8])), "cuda"
+    img, text = torch.from_numpy(g["images"][:1]).to(device), torch.from_numpy(g["tokens"]).to(device)
+    interpret = mmx.interpret                                            # the only line a notebook changes: the import
+    R_text, R_image = interpret(model=model, image=img, texts=text, device=device)
+    assert text_rel_err(R_text, g["repeat.sl-1.R_text"]) < TOL and rel_err(R_image, g["repeat.sl-1.R_image"]) < TOL
+    R_text, R_image = interpret(model=model, image=img, texts=text, device=device, start_layer=0, start_layer_text=0)
+    assert text_rel_err(R_text, g["repeat.sl0.R_text"]) < TOL and rel_err(R_image, g["repeat.sl0.R_image"]) < TOL
+    assert model.calls == 1                                              # engine cached per module object
+    batch_size = text.shape[0]
+    assert R_text.shape == (batch_size, text.shape[1], text.shape[1]) and R_image[0].numel() == (img.shape[-1] // 16) ** 2
+
+
+@pytest.mark.parametrize("index", [None, 0, 1, 2])
+def test_example_py_interpret_golden(mmx, golden_dir, index):
+    """CLIP/example.py:8-53 (one image, N texts, ``index``) vs the relevance the unmodified function computes."""
+    g = np.load(os.path.join(golden_dir, "clip_example.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    model = _RefLikeClip(sd, int(g["cfg"][8]))
+    image, text = torch.from_numpy(g["image"]).cuda(), torch.from_numpy(g["tokens"]).cuda()
+    R, logits = mmx.interpret_example(model=model, image=image, text=text, device="cuda", index=index)
+    assert rel_err(logits, g["logits_per_image"]) < TOL
+    assert rel_err(R, g[f"R.index{index}"]) < TOL
+
+
+def test_shape_and_token_validation(mmx, golden_dir):
+    """The C ABI takes no sizes: wrong shapes / token ids must be refused before any pointer reaches it."""
+    g = np.load(os.path.join(golden_dir, "clip_tiny.npz"))
+    cfg = co.ClipConfig(*[int(v) for v in g["cfg"]])
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    eng = _engine(mmx, cfg, sd, 4)
+    images, tokens = torch.from_numpy(g["images"]), torch.from_numpy(g["tokens"])
+    bad = [(images[:, :, :16], tokens), (images, tokens[:, :-1]), (images[:2], tokens), (images[:, :2], tokens)]
+    for im, tk in bad:
+        with pytest.raises(mmx.MmxError):
+            eng.interpret(im.cuda(), tk.cuda())
+        with pytest.raises(mmx.MmxError):
+            eng.interpret_host(im, tk)
+    oob = tokens.clone()
+    oob[0, 1] = cfg.vocab_size
+    with pytest.raises(mmx.MmxError):
+        eng.interpret(images.cuda(), oob.cuda())
+    neg = tokens.clone()
+    neg[0, 1] = -1
+    with pytest.raises(mmx.MmxError):
+        eng.interpret_host(images, neg)
+    with pytest.raises(mmx.MmxError):
+        eng.interpret_host(images, tokens, out=(torch.empty(1, 2, 2), torch.empty(1, 3)))

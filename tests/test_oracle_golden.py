@@ -80,3 +80,19 @@ def test_otsu_oracle_matches_cv2_golden(golden_dir):
     masks, ths = R.otsu_masks(torch.from_numpy(g["cams"]))
     assert np.array_equal(ths.numpy(), g["thresholds"])
     assert np.array_equal(masks.numpy(), g["masks"])
+
+
+@pytest.mark.parametrize("index", [None, 0, 1, 2])
+def test_clip_oracle_matches_example_py_golden(golden_dir, index):
+    """The older unbatched interpret of CLIP/example.py:8-53 (one image, N texts, ``index`` picks the text, all image
+    blocks): its relevance for text ``index`` is the notebook rule with start_layer = 0 on the pair (image, text[index])."""
+    g = _load(golden_dir, "clip_example.npz")
+    cfg = co.ClipConfig(*[int(v) for v in g["cfg"]])
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    image, tokens = torch.from_numpy(g["image"]), torch.from_numpy(g["tokens"])
+    n = int(np.argmax(g["logits_per_image"][0])) if index is None else index
+    _, ri = co.clip_interpret(sd, cfg, image, tokens[n:n + 1], 0, cfg.transformer_layers - 1)
+    assert rel_err(ri[0], g[f"R.index{index}"]) < 1e-5
+    with torch.no_grad():
+        logits = co.clip_forward(sd, cfg, image.expand(tokens.shape[0], -1, -1, -1), tokens)[0]
+    assert rel_err(logits[:1], g["logits_per_image"]) < 1e-5

@@ -13,8 +13,10 @@ the library is missing or no sm_100 GPU is present).
 from ._lib import MmxError, lib, LIB_PATH, exported_symbols  # noqa: F401
 from .rules import (avg_heads, avg_heads_batched, apply_self_attention_rules, apply_mm_attention_rules,  # noqa: F401
                     apply_mm_attention_rules_lxmert, handle_residual, compute_rollout_attention, self_update, minmax_normalize, otsu_masks)
-from .clip import ClipConfig, ClipEngine, interpret, VIT_B32, VIT_L14_336  # noqa: F401
-from .synthetic import clip_init_state_dict, clip_synthetic_inputs  # noqa: F401
+from .clip import ClipConfig, ClipEngine, interpret, interpret_example, engine_for, refresh_engine, VIT_B32, VIT_L14_336  # noqa: F401
+from .synthetic import (clip_init_state_dict, clip_synthetic_inputs, DetrConfig, DETR_R50, DETR_TINY, detr_init_state_dict,  # noqa: F401
+                        detr_sine_position_embedding, detr_synthetic_inputs, LxmertConfig, LXMERT_BASE, LXMERT_TINY,
+                        lxmert_init_state_dict, lxmert_synthetic_inputs)
 from .vit import ViTEngine, generate_relevance  # noqa: F401
 from .detr import DetrEngine, Generator, GeneratorAlbationNoAgg, MaskGenerator  # noqa: F401
 from .lxmert import LxmertEngine, GeneratorOurs, GeneratorBaselines, GeneratorOursAblationNoAggregation  # noqa: F401

@@ -27,6 +27,7 @@ _SIGS = {
     "mmx_version": (C.c_int, []),
     "mmx_launch_count": (C.c_uint64, []),
     "mmx_set_gemm_backend": (C.c_int, [C.c_int]),
+    "mmx_get_gemm_backend": (C.c_int, []),
     "mmx_set_gemm_tile_n": (C.c_int, [C.c_int]),
     "mmx_profile_gemm": (C.c_int, [C.c_int]),
     "mmx_profile_gemm_report": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -58,6 +59,25 @@ _SIGS = {
                                     C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_linear_dgrad_packed": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, C.c_void_p, c_float_p, C.c_int, C.c_int,
                                           c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_gemm_nt": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, C.c_void_p, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
+                              c_float_p, C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_lrp_split": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "mmx_lrp_safe_divide": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "mmx_lrp_partials_len": (C.c_int, []),
+    "mmx_lrp_sums": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mmx_lrp_renorm": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_lrp_add": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int,
+                              C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mmx_lrp_clone": (C.c_int, [c_float_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, c_float_p, C.c_int,
+                                C.c_longlong, C.c_int, C.c_void_p]),
+    "mmx_lrp_zero_value_fix": (C.c_int, [c_float_p, C.c_int, C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmx_lrp_attn_pv": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, c_float_p,
+                                  c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_lrp_attn_qk": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, C.c_float, c_float_p, C.c_int,
+                                  c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_lrp_attn_scores": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_float, c_float_p, c_float_p, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_add": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, C.c_float, c_float_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     "mmx_gather_rows": (C.c_int, [c_float_p, C.c_int, c_int_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_scatter_add_rows": (C.c_int, [c_float_p, C.c_int, c_int_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -83,6 +103,7 @@ _SIGS = {
     "mmx_clip_destroy": (None, [C.c_void_p]),
     "mmx_clip_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, c_float_p, C.c_size_t]),
     "mmx_clip_finalize": (C.c_int, [C.c_void_p]),
+    "mmx_clip_set_serial": (C.c_int, [C.c_void_p, C.c_int]),
     "mmx_clip_interpret_device": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_int_p, C.c_int, C.c_int, C.c_int,
                                             c_float_p, c_float_p, C.c_void_p]),
     "mmx_clip_interpret_host": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_int_p, C.c_int, C.c_int, C.c_int,

@@ -138,6 +138,7 @@ struct mmx_clip {
   cudaStream_t main = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_v = nullptr, ev_t = nullptr, ev_head = nullptr, ev_rows = nullptr;
   int* rows_pinned = nullptr;   // host copy of the text tower's packed row count (ragged batches)
+  cudaStream_t text_stream = nullptr;   // the text tower's own stream (h->t.st aliases the vision stream in serial mode)
   int lastB = 0, last_start_v = 0, last_start_t = 0;
   size_t bytes = 0;
 };
@@ -499,7 +500,15 @@ int mmx_clip_create(const mmx_clip_config* cfg, int max_batch, mmx_clip** out) {
     set_error("stream/event creation failed");
     return fail(1);
   }
+  h->text_stream = h->t.st;
   *out = h;
+  return 0;
+}
+
+int mmx_clip_set_serial(mmx_clip* h, int serial) {
+  MMX_REQUIRE(h, "null handle");
+  MMX_CHECK_CUDA(cudaDeviceSynchronize());
+  h->t.st = serial ? h->v.st : h->text_stream;
   return 0;
 }
 
@@ -507,6 +516,7 @@ void mmx_clip_destroy(mmx_clip* h) {
   if (!h) return;
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  h->t.st = h->text_stream;
   if (h->v.st) cudaStreamDestroy(h->v.st);
   if (h->t.st) cudaStreamDestroy(h->t.st);
   if (h->main) cudaStreamDestroy(h->main);

@@ -14,14 +14,14 @@ void set_error(const std::string& msg) { g_error = msg; }
 const char* last_error() { return g_error.c_str(); }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaDeviceProp p;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[MMX_MAX_DEVICES];   // zero-initialised; benign race: every writer stores the same value
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 
 // gemm_tcgen05.cu
@@ -118,6 +118,8 @@ int mmx_set_gemm_backend(int backend) {
   return g_backend.load();
 }
 
+int mmx_get_gemm_backend(void) { return gemm_backend(); }
+
 int mmx_set_gemm_tile_n(int bn) { return gemm_tc_tile_n(bn == 0 || bn == 128 || bn == 144 || bn == 160 ? bn : -1); }
 
 int mmx_profile_gemm(int enable) {
@@ -170,6 +172,13 @@ int mmx_linear_packed(const float* A, int lda, const float* W, int ldw, const vo
   GemmEpilogue ep;
   ep.bias = bias; ep.residual = residual; ep.ldres = ldres; ep.C_act = C_act; ep.act = act;
   return gemm_nt_b(A, lda, packed_operand(W, ldw, packed, N, K), C, ldc, M, N, K, ep, (cudaStream_t)stream);
+}
+int mmx_gemm_nt(const float* A, int lda, const float* Bt, int ldb, const void* packed, const float* bias, const float* pre,
+                int ldpre, const float* residual, int ldres, float* C, int ldc, float* C_act, int act, int M, int N, int K,
+                void* stream) {
+  GemmEpilogue ep;
+  ep.bias = bias; ep.pre = pre; ep.ldpre = ldpre; ep.residual = residual; ep.ldres = ldres; ep.C_act = C_act; ep.act = act;
+  return gemm_nt_b(A, lda, packed_operand(Bt, ldb, packed, N, K), C, ldc, M, N, K, ep, (cudaStream_t)stream);
 }
 int mmx_linear(const float* A, int lda, const float* W, int ldw, const float* bias, const float* residual, int ldres, float* C,
                int ldc, float* C_act, int act, int M, int N, int K, void* stream) {

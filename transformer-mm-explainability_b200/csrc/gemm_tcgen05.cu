@@ -30,6 +30,7 @@
 //   warps 4-11  epilogue: tcgen05.ld (main + cross, added with RN) -> registers, TMEM released at once, then
 //               bias / act' / residual / act -> global from registers (overlaps the next tile's main loop)
 #include "gemm.cuh"
+#include <mutex>
 #include "tcgen05_ptx.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -354,7 +355,6 @@ int gemm_tc_tile_n(int bn) {
 }
 namespace tc {
 static long long* g_trace = nullptr;
-static int g_avail = -1;
 
 static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -394,11 +394,13 @@ static int launch_bn(const float* A, int lda, const float* Bt, int ldb, int M, i
   CUtensorMap mapA, mapB;
   MMX_TRY(make_map(&mapA, A, M, K, lda, BM));
   MMX_TRY(make_map(&mapB, Bt, N, K, ldb, BN));
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per device: the attribute belongs to the (function, device) pair
+  static std::atomic<bool> attr_set[MMX_MAX_DEVICES];
+  const int dev = current_device();
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -422,18 +424,33 @@ static int launch(const float* A, int lda, const float* Bt, int ldb, float* C, i
 }  // namespace tc
 
 int gemm_tc_available() {
-  if (tc::g_avail >= 0) return tc::g_avail;
-  tc::g_avail = 0;
-  int dev = 0;
+  // per device (a process may drive several GPUs); -1 = not probed yet
+  static std::atomic<int> avail[MMX_MAX_DEVICES];
+  static std::atomic<bool> init{false};
+  static std::mutex mu;
+  if (!init.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!init.load()) {
+      for (auto& a : avail) a.store(-1);
+      init.store(true, std::memory_order_release);
+    }
+  }
+  const int dev = current_device();
+  int a = avail[dev].load(std::memory_order_acquire);
+  if (a >= 0) return a;
+  std::lock_guard<std::mutex> lk(mu);
+  a = 0;
   cudaDeviceProp prop;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
-  if (prop.major != 10) return 0;                         // tcgen05 / TMEM: sm_100 family only
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) return 0;
-  tc::g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-  tc::g_avail = 1;
-  return 1;
+  if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10) {   // tcgen05 / TMEM: sm_100 family only
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr) {
+      tc::g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+      a = 1;
+    }
+  }
+  avail[dev].store(a, std::memory_order_release);
+  return a;
 }
 
 // Profiling aid: the next tensor-core GEMM launches write CTA 0's clock64 timeline into `buf`

@@ -12,7 +12,16 @@ namespace mmx {
 
 void set_error(const std::string& msg);
 extern std::atomic<uint64_t> g_launches;
-int sm_count();
+int sm_count();          // SM count of the CURRENT device (cached per device)
+
+// One process may drive several GPUs (ClipEngine(device="cuda:1") after a cuda:0 engine): every piece of cached
+// per-device state (function attributes, SM counts, memory-pool settings) is indexed by the device ordinal.
+constexpr int MMX_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MMX_MAX_DEVICES) dev = 0;
+  return dev;
+}
 
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -80,6 +89,11 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// clamp(min=0) and min() with torch's NaN semantics (NaN propagates; fmaxf / fminf would drop it): a numerical blow-up
+// upstream must reach the caller (and trip the reference's `assert diag(R - I).min() >= 0`) instead of being masked.
+__device__ __forceinline__ float relu_nan(float x) { return x < 0.f ? 0.f : x; }
+__device__ __forceinline__ float min_nan(float m, float v) { return (v < m || v != v) ? v : m; }
+
 __device__ __forceinline__ float act_fwd(float x, int act) {
   switch (act) {
     case MMX_ACT_QUICKGELU: return x / (1.f + expf(-1.702f * x));
@@ -102,6 +116,7 @@ __device__ __forceinline__ float act_bwd(float x, int act) {  // d act(x) / dx
     }
     case MMX_ACT_RELU: return x > 0.f ? 1.f : 0.f;
     case MMX_ACT_TANH: { const float t = tanhf(x); return 1.f - t * t; }
+    case MMX_ACT_MUL: return x;   // the epilogue multiplies by `pre` itself (Linear.relprop)
     default: return 1.f;
   }
 }

@@ -35,18 +35,18 @@ __global__ void __launch_bounds__(256) avg_heads_vec4_kernel(const float* __rest
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        acc.x += fmaxf(av[u].x * gv[u].x, 0.f);
-        acc.y += fmaxf(av[u].y * gv[u].y, 0.f);
-        acc.z += fmaxf(av[u].z * gv[u].z, 0.f);
-        acc.w += fmaxf(av[u].w * gv[u].w, 0.f);
+        acc.x += relu_nan(av[u].x * gv[u].x);
+        acc.y += relu_nan(av[u].y * gv[u].y);
+        acc.z += relu_nan(av[u].z * gv[u].z);
+        acc.w += relu_nan(av[u].w * gv[u].w);
       }
     }
     for (; h < H; ++h) {
       float4 av = ld_stream4(a + h * plane), gv = ld_stream4(g + h * plane);
-      acc.x += fmaxf(av.x * gv.x, 0.f);
-      acc.y += fmaxf(av.y * gv.y, 0.f);
-      acc.z += fmaxf(av.z * gv.z, 0.f);
-      acc.w += fmaxf(av.w * gv.w, 0.f);
+      acc.x += relu_nan(av.x * gv.x);
+      acc.y += relu_nan(av.y * gv.y);
+      acc.z += relu_nan(av.z * gv.z);
+      acc.w += relu_nan(av.w * gv.w);
     }
     acc.x *= inv_h; acc.y *= inv_h; acc.z *= inv_h; acc.w *= inv_h;
     *reinterpret_cast<float4*>(out + b * plane + 4LL * i) = acc;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) gradcam_kernel(const float* __restrict__ 
     const long long off = (b * H) * plane + (long long)t * ld_in + s;
     float acc = 0.f;
     for (int h = 0; h < H; ++h) acc = fmaf(A[off + h * plane], gbar[b * H + h], acc);
-    out[(b * T + t) * ld_out + s] = fmaxf(acc / (float)H, 0.f);
+    out[(b * T + t) * ld_out + s] = relu_nan(acc / (float)H);
   }
 }
 
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) avg_heads_scalar_kernel(const float* __re
     const long long off = (b * H) * plane + (long long)t * ld_in + s;
     float acc = 0.f;
 #pragma unroll 4
-    for (int h = 0; h < H; ++h) acc += fmaxf(ld_stream1(A + off + h * plane) * ld_stream1(G + off + h * plane), 0.f);
+    for (int h = 0; h < H; ++h) acc += relu_nan(ld_stream1(A + off + h * plane) * ld_stream1(G + off + h * plane));
     out[(b * T + t) * ld_out + s] = acc * inv_h;
   }
 }
@@ -185,12 +185,12 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
     // diag(R-I) minimum over the whole batch (the reference asserts it is >= 0 on the host)
     __shared__ float red[8];
     float m = CUDART_INF_F;
-    for (int r = threadIdx.x; r < rows_total; r += blockDim.x) m = fminf(m, R[(long long)r * ld + (r % S)] - 1.f);
-    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int r = threadIdx.x; r < rows_total; r += blockDim.x) m = min_nan(m, R[(long long)r * ld + (r % S)] - 1.f);
+    for (int o = 16; o > 0; o >>= 1) m = min_nan(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fminf(m, red[w]);
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = min_nan(m, red[w]);
       *min_diag = m;
     }
   }
@@ -280,15 +280,15 @@ static int self_update_tc(const float* Abar, int ld_a, const float* R, float* R_
   if (gemm_backend() < 1 || S < 128 || Q < 128 || (ld_a % 4) || (ld % 4) || ld < round_up(Q, 4) || !aligned16(Abar) ||
       !aligned16(R) || !aligned16(R_out))
     return 0;
-  static bool pool_set = false;
-  if (!pool_set) {                       // keep stream-ordered scratch cached across synchronisation points
+  static std::atomic<bool> pool_set[MMX_MAX_DEVICES];
+  const int dev = current_device();
+  if (!pool_set[dev].load(std::memory_order_acquire)) {   // keep stream-ordered scratch cached across synchronisation points
     cudaMemPool_t pool;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       unsigned long long thr = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    pool_set = true;
+    pool_set[dev].store(true, std::memory_order_release);
   }
   const int Kp = round_up(S, 4), Np = round_up(Q, 4);
   float* Rt = nullptr;
@@ -536,6 +536,12 @@ int mmx_mm_update(const float* R_ss, int ld_ss, const float* R_qq, int ld_qq, co
     MMX_TRY(bmm_add(Xs, lxs, (long long)T * lxs, 1, ws_t, S, (long long)T * S, nullptr, 0, 0, R_sq_add, ld_sq_add,
                     (long long)T * ld_sq_add, B, T, S, T, nan0, st));
   } else {
+    // the reference normalises (and asserts diag(R - I) >= 0) before it discards the product
+    // (DETR/modules/ExplanationGenerator.py:36-41), so the assert's operand is still produced
+    if ((flags & MMX_MM_NORMALIZE) && min_diag) {
+      MMX_TRY(handle_residual(R_ss, ws_ss, ld_ss, T, B, T, 0, min_diag, st));
+      MMX_TRY(handle_residual(R_qq, ws_qq, ld_qq, S, B, S, 0, min_diag + 1, st));
+    }
     // R_sq_addition = cam_sq (a copy; NaN->0 still applies for DETR)
     for (int b = 0; b < B; ++b)
       MMX_TRY(copy2d(Abar_sq + (size_t)b * T * ld_a, ld_a, R_sq_add + (size_t)b * T * ld_sq_add, ld_sq_add, T, S, nan0, st));

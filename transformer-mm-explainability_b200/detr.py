@@ -14,7 +14,7 @@ from typing import Dict, List, Optional
 import torch
 
 from ._lib import lib, check, ptr, current_stream, MmxError
-from .nn import Tape, Var, Weight, AttnRecord, ACT_RELU, _f32
+from .nn import fp32_gemms, Tape, Var, Weight, AttnRecord, ACT_RELU, _f32
 from . import rules
 
 
@@ -82,11 +82,22 @@ class DetrEngine:
         H = self.nhead
         q, k, v = tape.linear(query, m["q"]), tape.linear(key, m["k"]), tape.linear(value, m["v"])
         o = tape.attention(q, k, v, B, H, T, S, float(self.d_model // H) ** -0.5, 0, None, m["rec"])
+        m["rec"].saved.update(Xq=query, Xk=key, Xv=value)
         return tape.linear(o, m["o"])
 
-    def forward_backward(self, src: torch.Tensor, pos: torch.Tensor, target_index, index=None, backward: bool = True):
+    def forward_backward(self, *args, lrp: bool = False, **kwargs):
+        """See ``_forward_backward``.  With ``lrp=True`` every GEMM of the call (forward, dgrad and the relprop sweep) runs
+        on the fp32 FFMA backend (``nn.fp32_gemms``: the sweep amplifies tensor-core split rounding)."""
+        if lrp:
+            with fp32_gemms():
+                return self._forward_backward(*args, lrp=True, **kwargs)
+        return self._forward_backward(*args, lrp=False, **kwargs)
+
+    def _forward_backward(self, src: torch.Tensor, pos: torch.Tensor, target_index, index=None, backward: bool = True,
+                         lrp: bool = False):
         """Forward staging every A, one-hot on pred_logits[b, target_b, class_b], backward staging every dA
-        (``backward=False``: forward only, for the raw-attention / rollout baselines)."""
+        (``backward=False``: forward only, for the raw-attention / rollout baselines); ``lrp=True`` adds the relprop
+        sweep from the same one-hot (DETR/models/detr.py:79-92), staging the relevance of every A."""
         dev = self.device
         with torch.cuda.device(dev):
             B, d, h, w = src.shape
@@ -97,24 +108,33 @@ class DetrEngine:
             qe = self.query_embed.repeat(B, 1)                                    # [B*Q, d]
             for L in self.encoder:                                                # transformer.py:230-254
                 qk = tape.add_const(x, pe)
-                x = tape.layernorm(tape.add(x, self._mha(tape, L.self_attn, qk, qk, x, B, S, S)), *L.n1, 1e-5)
-                ff = tape.linear(tape.linear(x, L.l1, ACT_RELU), L.l2)
-                x = tape.layernorm(tape.add(x, ff), *L.n2, 1e-5)
+                att = self._mha(tape, L.self_attn, qk, qk, x, B, S, S)
+                x1 = tape.layernorm(tape.add(x, att), *L.n1, 1e-5)
+                hdn = tape.linear(x1, L.l1, ACT_RELU)
+                ff = tape.linear(hdn, L.l2)
+                L.saved = dict(src=x, webmd=qk, drop=att, x1=x1, h=hdn, ff=ff)
+                x = tape.layernorm(tape.add(x1, ff), *L.n2, 1e-5)
             memory = x
             mem_pe = tape.add_const(memory, pe)
             t = Var(torch.zeros(B * Q, d, device=dev))
             for L in self.decoder:                                                # transformer.py:372-408
                 qk = tape.add_const(t, qe)
-                t = tape.layernorm(tape.add(t, self._mha(tape, L.self_attn, qk, qk, t, B, Q, Q)), *L.n1, 1e-5)
-                tq = tape.add_const(t, qe)
-                t = tape.layernorm(tape.add(t, self._mha(tape, L.multihead_attn, tq, mem_pe, memory, B, Q, S)), *L.n2, 1e-5)
-                ff = tape.linear(tape.linear(t, L.l1, ACT_RELU), L.l2)
-                t = tape.layernorm(tape.add(t, ff), *L.n3, 1e-5)
+                drop1 = self._mha(tape, L.self_attn, qk, qk, t, B, Q, Q)
+                x1 = tape.layernorm(tape.add(t, drop1), *L.n1, 1e-5)
+                tq = tape.add_const(x1, qe)
+                drop2 = self._mha(tape, L.multihead_attn, tq, mem_pe, memory, B, Q, S)
+                x2 = tape.layernorm(tape.add(x1, drop2), *L.n2, 1e-5)
+                hdn = tape.linear(x2, L.l1, ACT_RELU)
+                ff = tape.linear(hdn, L.l2)
+                L.saved = dict(tgt=t, memory=memory, webmd=qk, drop1=drop1, x1=x1, drop2=drop2, x2=x2, h=hdn, ff=ff)
+                t = tape.layernorm(tape.add(x2, ff), *L.n3, 1e-5)
+                L.saved["out"] = t
             hs = tape.layernorm(t, *self.dec_norm, 1e-5)
             logits = tape.linear(hs, self.class_embed)                             # [B*Q, C+1]
             C1 = logits.cols
             self.pred_logits = logits.v.view(B, Q, C1)
             self._shape = (B, S, Q)
+            self.saved = dict(B=B, memory=memory, hs=hs, logits=logits)
             if not backward:
                 return {"pred_logits": self.pred_logits}
             tq_idx = torch.as_tensor(target_index, device=dev).reshape(B).long()
@@ -127,7 +147,9 @@ class DetrEngine:
             one_hot[rows, cls] = 1.0
             tape.seed(logits, one_hot, B)
             tape.backward()
-            self._shape = (B, S, Q)
+            if lrp:
+                from .lrp import detr_sweep
+                detr_sweep(self, one_hot)
         return {"pred_logits": self.pred_logits}
 
 
@@ -142,15 +164,15 @@ class Generator:
 
     def handle_self_attention_image(self, blocks):                                 # :110-118
         for blk in blocks:
-            cam = rules.avg_heads_record(blk.self_attn["rec"], self.B)
+            cam = rules.avg_heads_record(blk.self_attn["rec"], self.B, self.use_lrp)
             self.R_i_i, _ = rules.self_update(self.R_i_i, cam)
 
     def handle_co_attn_self_query(self, block):                                    # :120-129
-        cam = rules.avg_heads_record(block.self_attn["rec"], self.B)
+        cam = rules.avg_heads_record(block.self_attn["rec"], self.B, self.use_lrp)
         self.R_q_q, self.R_q_i = rules.self_update(self.R_q_q, cam, self.R_q_i)
 
     def handle_co_attn_query(self, block):                                         # :131-140
-        cam_q_i = rules.avg_heads_record(block.multihead_attn["rec"], self.B)
+        cam_q_i = rules.avg_heads_record(block.multihead_attn["rec"], self.B, self.use_lrp)
         add, _, md = rules.mm_update_batched(self.R_q_q, self.R_i_i, None, cam_q_i,
                                              apply_normalization=self.normalize_self_attention,
                                              apply_self_in_rule_10=self.apply_self_in_rule_10, nan_to_zero=True)
@@ -159,15 +181,12 @@ class Generator:
 
     def generate_ours(self, img, target_index, index=None, use_lrp=True, normalize_self_attention=True,
                       apply_self_in_rule_10=True):
-        if use_lrp:
-            raise NotImplementedError("use_lrp=True (LRP relprop sweep, DETR/modules/layers.py:770-801) is outside the "
-                                      "hot-path scope; call with use_lrp=False as the notebooks and the ours_no_lrp CLI do")
-        self.use_lrp = use_lrp
+        self.use_lrp = bool(use_lrp)
         self.normalize_self_attention = normalize_self_attention
         self.apply_self_in_rule_10 = apply_self_in_rule_10
         src, pos = img
         m = self.model
-        m.forward_backward(src, pos, target_index, index)
+        m.forward_backward(src, pos, target_index, index, lrp=self.use_lrp)
         B, S, Q = m._shape
         self.B = B
         dev = m.device
@@ -179,9 +198,34 @@ class Generator:
         for blk in m.decoder:
             self.handle_co_attn_self_query(blk)
             self.handle_co_attn_query(blk)
-        if normalize_self_attention and apply_self_in_rule_10 and self._min_diag:
-            assert torch.stack(self._min_diag).min().item() >= 0                     # handle_residual's assert (:50)
+        self.min_diag = torch.stack(self._min_diag).min() if (normalize_self_attention and self._min_diag) else None
+        if not getattr(self, "_defer_assert", False):
+            self.check_min_diag()
         return self._pick(target_index)
+
+    def check_min_diag(self):
+        """handle_residual's ``assert self_attention[diag].min() >= 0`` (:50) over every cross-attention step of the last
+        call (one host read; deferred to after the replay when the call runs as a CUDA graph)."""
+        if getattr(self, "min_diag", None) is not None:
+            assert self.min_diag.item() >= 0
+
+    def capture(self, img, target_index, index=None, use_lrp=True, normalize_self_attention=True, apply_self_in_rule_10=True):
+        """``generate_ours`` for these shapes / flags as a CUDA graph (``mmx_b200.graphs.Graphed``): returns a callable
+        ``g(src, pos, target_index)`` that replays the captured kernels on new inputs and yields the (static) result
+        tensor; ``g.check()`` runs the deferred ``diag(R - I) >= 0`` assert.  ``target_index`` must be a tensor."""
+        from .graphs import Graphed
+        src, pos = img
+        dev = self.model.device
+        tq = torch.as_tensor(target_index).reshape(-1).to(dev)
+        idx = None if index is None else torch.as_tensor(index).reshape(-1).to(dev)
+
+        def fn(s, p, t):
+            return self.generate_ours((s, p), t, idx, use_lrp, normalize_self_attention, apply_self_in_rule_10)
+        self._defer_assert = True
+        try:
+            return Graphed(fn, (src, pos, tq), dev, deferred_checks=[self.check_min_diag])
+        finally:
+            self._defer_assert = False
 
     def _pick(self, target_index):
         """``aggregated[:, target_index, :].unsqueeze_(0)`` (:192-194): [1,1,1,S] for a tensor index, [1,1,S] for an int;
@@ -230,10 +274,25 @@ class Generator:
         return self._pick(target_index)
 
     def generate_partial_lrp(self, img, target_index, index=None):
-        raise NotImplementedError("partial LRP needs the relprop sweep (DETR/modules/layers.py:770-801): outside the hot-path scope")
+        """Partial LRP (DETR/modules/ExplanationGenerator.py:197-224): head mean of the LRP relevance of the last decoder
+        cross-attention, min-max normalised over the whole [Q, S] map."""
+        src, pos = img
+        m = self.model
+        m.forward_backward(src, pos, target_index, index, lrp=True)
+        self.B = B = m._shape[0]
+        cam = rules.head_mean_record(m.decoder[-1].multihead_attn["rec"], B, use_cam=True).contiguous()
+        self.R_q_i = rules.minmax_normalize(cam)
+        return self._pick(target_index)
 
     def generate_transformer_att(self, img, target_index, index=None):
-        raise NotImplementedError("transformer attribution needs the relprop sweep: outside the hot-path scope")
+        """Transformer attribution (DETR/modules/ExplanationGenerator.py:64-108): rule 5 on the last decoder
+        cross-attention with the LRP relevance in place of the probabilities."""
+        src, pos = img
+        m = self.model
+        m.forward_backward(src, pos, target_index, index, lrp=True)
+        self.B = B = m._shape[0]
+        self.R_q_i = rules.avg_heads_record(m.decoder[-1].multihead_attn["rec"], B, use_cam=True).contiguous()
+        return self._pick(target_index)
 
 
 class GeneratorAlbationNoAgg(Generator):
@@ -243,14 +302,14 @@ class GeneratorAlbationNoAgg(Generator):
 
     def handle_self_attention_image(self, blocks):                                 # :314-322
         for blk in blocks:
-            self.R_i_i = rules.bmm(rules.avg_heads_record(blk.self_attn["rec"], self.B), self.R_i_i)
+            self.R_i_i = rules.bmm(rules.avg_heads_record(blk.self_attn["rec"], self.B, self.use_lrp), self.R_i_i)
 
     def handle_co_attn_self_query(self, block):                                    # :324-333
-        cam = rules.avg_heads_record(block.self_attn["rec"], self.B)
+        cam = rules.avg_heads_record(block.self_attn["rec"], self.B, self.use_lrp)
         self.R_q_q, self.R_q_i = rules.bmm(cam, self.R_q_q), rules.bmm(cam, self.R_q_i)
 
     def handle_co_attn_query(self, block):                                         # :335-344
-        cam_q_i = rules.avg_heads_record(block.multihead_attn["rec"], self.B)
+        cam_q_i = rules.avg_heads_record(block.multihead_attn["rec"], self.B, self.use_lrp)
         self.R_q_i, _, md = rules.mm_update_batched(self.R_q_q, self.R_i_i, None, cam_q_i,
                                                     apply_normalization=self.normalize_self_attention,
                                                     apply_self_in_rule_10=self.apply_self_in_rule_10, nan_to_zero=True)
@@ -270,8 +329,8 @@ class MaskGenerator:
     kept queries with one forward + backward and one CPU cv2 call each; here the queries of an image form ONE batch and
     the masks come from one kernel launch.  The visualisation / COCO panoptic bookkeeping around it is out of scope."""
 
-    METHODS = ("ours_no_lrp", "ablation_no_self_in_10", "ablation_no_aggregation", "ours_no_lrp_no_norm", "raw_attn",
-               "attn_gradcam", "rollout")
+    METHODS = ("ours_with_lrp", "ours_no_lrp", "ablation_no_self_in_10", "ablation_no_aggregation", "ours_no_lrp_no_norm",
+               "transformer_att", "partial_lrp", "raw_attn", "attn_gradcam", "rollout")
 
     def __init__(self, model: DetrEngine):
         self.gen = Generator(model)
@@ -301,8 +360,12 @@ class MaskGenerator:
             cam = self.gen.generate_attn_gradcam(batch, q)
         elif method == "rollout":
             cam = self.gen.generate_rollout(batch, q)
-        elif method in ("ours_with_lrp", "transformer_att", "partial_lrp"):
-            raise NotImplementedError(f"{method} needs the relprop sweep (DETR/modules/layers.py:770-801): outside the hot-path scope")
+        elif method == "ours_with_lrp":                                       # mask_generator.py:93-94
+            cam = self.gen.generate_ours(batch, q, use_lrp=True)
+        elif method == "transformer_att":
+            cam = self.gen.generate_transformer_att(batch, q)
+        elif method == "partial_lrp":
+            cam = self.gen.generate_partial_lrp(batch, q)
         else:
             print("please provide a valid explainability method")            # mask_generator.py:111-113
             return None

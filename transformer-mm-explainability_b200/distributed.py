@@ -41,6 +41,27 @@ def all_gather_maps(local: torch.Tensor, n_total: int, group=None) -> torch.Tens
     return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(world)], dim=0)
 
 
+def gather_maps_packed(R_text: torch.Tensor, R_image: torch.Tensor, n_total: int, group=None, async_op: bool = False):
+    """THE collective of the path: both maps of every local sample packed into one ``[n_local, ctx*ctx + P]``
+    buffer and exchanged with ONE ``all_gather_into_tensor`` (NCCL: one ncclAllGather).  Equal shards only (the bench /
+    serving shape; ragged shards go through :func:`all_gather_maps`).  Returns ``(work, full)``: ``full`` is
+    ``[n_total, ctx*ctx + P]`` in rank order (split it with :func:`split_packed`); with ``async_op`` the collective runs on
+    NCCL's stream and ``work.wait()`` orders the current stream after it - enqueue the next step's forward in between."""
+    world = dist.get_world_size(group)
+    n_local = R_text.shape[0]
+    assert n_local * world == n_total, "gather_maps_packed needs equal shards"
+    packed = torch.cat((R_text.reshape(n_local, -1), R_image.reshape(n_local, -1)), dim=1)
+    full = torch.empty((n_total, packed.shape[1]), dtype=packed.dtype, device=packed.device)
+    work = dist.all_gather_into_tensor(full, packed, group=group, async_op=async_op)
+    return work, full
+
+
+def split_packed(full: torch.Tensor, ctx: int, patches: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``[n, ctx*ctx + patches]`` -> ``(R_text [n,ctx,ctx], R_image [n,patches])`` (views)."""
+    n = full.shape[0]
+    return full[:, :ctx * ctx].reshape(n, ctx, ctx), full[:, ctx * ctx:ctx * ctx + patches]
+
+
 def interpret_sharded(interpret_fn: Callable, images: torch.Tensor, tokens: torch.Tensor, start_layer: int = -1,
                       start_layer_text: int = -1, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Every rank holds the same global batch; rank r computes samples shard_range(B, r, world) with
@@ -58,6 +79,9 @@ def interpret_sharded(interpret_fn: Callable, images: torch.Tensor, tokens: torc
         rt, ri = rt0[:0], ri0[:0]
     if world == 1:
         return rt, ri
+    if B % world == 0:                                   # equal shards: ONE all-gather of the packed maps
+        _, full = gather_maps_packed(rt, ri, B, group)
+        return split_packed(full, rt.shape[-1], ri.shape[-1])
     return all_gather_maps(rt, B, group), all_gather_maps(ri, B, group)
 
 

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional
 import torch
 
 from ._lib import lib, check, ptr, current_stream, MmxError
-from .nn import Tape, Var, Weight, AttnRecord, ACT_GELU, ACT_TANH, ATTN_SCALE_SCORES, _f32
+from .nn import fp32_gemms, Tape, Var, Weight, AttnRecord, ACT_GELU, ACT_TANH, ATTN_SCALE_SCORES, _f32
 from . import rules
 
 EPS = 1e-12
@@ -100,13 +100,28 @@ class LxmertEngine:
         H = self.heads
         q, k, v = tape.linear(x, a.q), tape.linear(ctx, a.k), tape.linear(ctx, a.v)
         o = tape.attention(q, k, v, B, H, T, S, 1.0 / math.sqrt(self.hidden // H), ATTN_SCALE_SCORES, key_bias, rec)
-        return tape.layernorm(tape.add(tape.linear(o, a.o), x), *a.ln, EPS)
+        dense = tape.linear(o, a.o)
+        rec.saved.update(Xq=x, Xk=ctx, Xv=ctx, dense=dense)
+        return tape.layernorm(tape.add(dense, x), *a.ln, EPS)
 
-    def _ffn(self, tape: Tape, f: _Ffn, x: Var) -> Var:
-        return tape.layernorm(tape.add(tape.linear(tape.linear(x, f.fc1, ACT_GELU), f.fc2), x), *f.ln, EPS)
+    def _ffn(self, tape: Tape, f: _Ffn, x: Var, saved: Optional[dict] = None) -> Var:
+        inter = tape.linear(x, f.fc1, ACT_GELU)
+        dense = tape.linear(inter, f.fc2)
+        if saved is not None:
+            saved.update(x=x, inter=inter, dense=dense)
+        return tape.layernorm(tape.add(dense, x), *f.ln, EPS)
 
-    def forward_backward(self, input_ids, visual_feats, visual_pos, index=None, attention_mask=None,
-                         visual_attention_mask=None, backward: bool = True, lang_key_bias=None, vis_key_bias=None):
+    def forward_backward(self, *args, lrp: bool = False, **kwargs):
+        """See ``_forward_backward``.  With ``lrp=True`` every GEMM of the call (forward, dgrad and the relprop sweep) runs
+        on the fp32 FFMA backend (``nn.fp32_gemms``: the sweep amplifies tensor-core split rounding)."""
+        if lrp:
+            with fp32_gemms():
+                return self._forward_backward(*args, lrp=True, **kwargs)
+        return self._forward_backward(*args, lrp=False, **kwargs)
+
+    def _forward_backward(self, input_ids, visual_feats, visual_pos, index=None, attention_mask=None,
+                         visual_attention_mask=None, backward: bool = True, lang_key_bias=None, vis_key_bias=None,
+                         lrp: bool = False):
         """Forward staging every A (29 attention maps for the base model), one-hot on the answer logit, backward
         staging every dA.  input_ids [B,T] int, visual_feats [B,I,F], visual_pos [B,I,4]."""
         dev, l = self.device, lib()
@@ -139,21 +154,27 @@ class LxmertEngine:
             check(l.mmx_add(ptr(vis_sum.v), Hd, ptr(vis_sum.v), Hd, C.c_float(-0.5), ptr(half), Hd, B * I, Hd, current_stream()))
             vis = Var(half)
             for b in self.layer:                                                # 9 language layers (:818-823)
-                lang = self._ffn(tape, b.ffn, self._att_layer(tape, b.att, b.att.recs[0], lang, lang, B, T, T, bias_t))
+                b.saved = dict(ffn={})
+                lang = self._ffn(tape, b.ffn, self._att_layer(tape, b.att, b.att.recs[0], lang, lang, B, T, T, bias_t), b.saved["ffn"])
             for b in self.r_layers:                                             # 5 relational layers (:826-831)
-                vis = self._ffn(tape, b.ffn, self._att_layer(tape, b.att, b.att.recs[0], vis, vis, B, I, I, bias_i))
+                b.saved = dict(ffn={})
+                vis = self._ffn(tape, b.ffn, self._att_layer(tape, b.att, b.att.recs[0], vis, vis, B, I, I, bias_i), b.saved["ffn"])
             for b in self.x_layers:                                             # 5 cross layers (:701-733)
+                b.saved = dict(lang_in=lang, vis_in=vis, lang_ffn={}, visn_ffn={})
                 l2 = self._att_layer(tape, b.cross, b.cross.recs[0], lang, vis, B, T, I, bias_i)
                 v2 = self._att_layer(tape, b.cross, b.cross.recs[1], vis, lang, B, I, T, bias_t)
                 l3 = self._att_layer(tape, b.lang_self, b.lang_self.recs[0], l2, l2, B, T, T, bias_t)
                 v3 = self._att_layer(tape, b.visn_self, b.visn_self.recs[0], v2, v2, B, I, I, bias_i)
-                lang, vis = self._ffn(tape, b.lang_ffn, l3), self._ffn(tape, b.visn_ffn, v3)
+                lang = self._ffn(tape, b.lang_ffn, l3, b.saved["lang_ffn"])
+                vis = self._ffn(tape, b.visn_ffn, v3, b.saved["visn_ffn"])
             rows0 = torch.arange(B, device=dev, dtype=torch.int32) * T
-            pooled = tape.linear(tape.gather_rows(lang, rows0), self.pooler, ACT_TANH)      # (:876-884)
+            first = tape.gather_rows(lang, rows0)
+            pooled = tape.linear(first, self.pooler, ACT_TANH)                  # (:876-884)
             h = tape.layernorm(tape.linear(pooled, self.head0, ACT_GELU), *self.head_ln, EPS)
             logits = tape.linear(h, self.head3)
             self.question_answering_score = logits.v
             self._shape = (B, T, I)
+            self.saved = dict(B=B, T=T, I=I, lang=lang, vis=vis, first=first, rows0=rows0, pooled=pooled, h=h)
             if not backward:
                 return self.question_answering_score
             idx = logits.v.argmax(-1) if index is None else torch.as_tensor(index, device=dev).reshape(B).long()
@@ -161,7 +182,9 @@ class LxmertEngine:
             one_hot[torch.arange(B, device=dev), idx] = 1.0                     # ExplanationGenerator.py:152-160
             tape.seed(logits, one_hot, B)
             tape.backward()
-            self._shape = (B, T, I)
+            if lrp:
+                from .lrp import lxmert_sweep
+                lxmert_sweep(self, one_hot)
         return self.question_answering_score
 
 
@@ -176,29 +199,26 @@ class GeneratorOurs:
         self.save_visualization = save_visualization
 
     def _self(self, rec, lang: bool):
-        cam = rules.avg_heads_record(rec, self.B)
+        cam = rules.avg_heads_record(rec, self.B, self.use_lrp)
         if lang:                                                               # EG:61-71 / :85-94
             self.R_t_t, self.R_t_i = rules.self_update(self.R_t_t, cam, self.R_t_i)
         else:                                                                  # EG:73-83 / :96-105
             self.R_i_i, self.R_i_t = rules.self_update(self.R_i_i, cam, self.R_i_t)
 
     def _mm(self, R_ss, R_qq, R_qs, rec):
-        cam = rules.avg_heads_record(rec, self.B)
+        cam = rules.avg_heads_record(rec, self.B, self.use_lrp)
         sq, ss, md = rules.mm_update_batched(R_ss, R_qq, R_qs, cam, self.normalize_self_attention, self.apply_self_in_rule_10)
         self._min_diag.append(md)
         return sq, ss
 
     def generate_ours(self, input, index=None, use_lrp=True, normalize_self_attention=True, apply_self_in_rule_10=True,
                       method_name="ours"):
-        if use_lrp:
-            raise NotImplementedError("use_lrp=True (LRP relprop sweep, lxmert_lrp.py:422-461) is outside the hot-path "
-                                      "scope; call with use_lrp=False as perturbation.py's ours_no_lrp does")
-        self.use_lrp = use_lrp
+        self.use_lrp = bool(use_lrp)
         self.normalize_self_attention = normalize_self_attention
         self.apply_self_in_rule_10 = apply_self_in_rule_10
         m = self.model_usage
         ids, feats, boxes = input
-        m.forward_backward(ids, feats, boxes, index)
+        m.forward_backward(ids, feats, boxes, index, lrp=self.use_lrp)
         B, T, I = m._shape
         self.B = B
         dev = m.device
@@ -223,12 +243,35 @@ class GeneratorOurs:
             self._self(b.lang_self.recs[0], True)
             if not last:
                 self._self(b.visn_self.recs[0], False)
-        if normalize_self_attention and apply_self_in_rule_10:
-            assert torch.stack(self._min_diag).min().item() >= 0                 # handle_residual's assert (EG:50)
+        self.min_diag = torch.stack(self._min_diag).min() if normalize_self_attention else None
+        if not getattr(self, "_defer_assert", False):
+            self.check_min_diag()
         self.R_t_t[:, 0, 0] = 0                                                  # EG:210
         if B == 1:
             self.R_t_t, self.R_t_i, self.R_i_i, self.R_i_t = self.R_t_t[0], self.R_t_i[0], self.R_i_i[0], self.R_i_t[0]
         return self.R_t_t, self.R_t_i
+
+    def check_min_diag(self):
+        """handle_residual's ``assert self_attention[diag].min() >= 0`` (EG:50) over every cross-modal step of the last call
+        (one host read; deferred to after the replay when the call runs as a CUDA graph)."""
+        if getattr(self, "min_diag", None) is not None:
+            assert self.min_diag.item() >= 0
+
+    def capture(self, input, index=None, use_lrp=True, normalize_self_attention=True, apply_self_in_rule_10=True):
+        """``generate_ours`` for these shapes / flags as a CUDA graph (``mmx_b200.graphs.Graphed``): returns a callable
+        ``g(input_ids, visual_feats, visual_pos)`` that replays the captured kernels on new inputs and yields the (static)
+        ``(R_t_t, R_t_i)``; ``g.check()`` runs the deferred ``diag(R - I) >= 0`` assert."""
+        from .graphs import Graphed
+        dev = self.model_usage.device
+        idx = None if index is None else torch.as_tensor(index).reshape(-1).to(dev)
+
+        def fn(ids, feats, boxes):
+            return self.generate_ours((ids, feats, boxes), idx, use_lrp, normalize_self_attention, apply_self_in_rule_10)
+        self._defer_assert = True
+        try:
+            return Graphed(fn, tuple(input), dev, deferred_checks=[self.check_min_diag])
+        finally:
+            self._defer_assert = False
 
 
 class GeneratorBaselines:
@@ -285,11 +328,39 @@ class GeneratorBaselines:
         self.R_t_t = rules.compute_rollout_attention(cams_text)
         return self._finish()
 
-    def generate_transformer_attr(self, input, index=None, method_name="transformer_attr"):
-        raise NotImplementedError("transformer attribution needs the relprop sweep (lxmert_lrp.py:422-461): outside the hot-path scope")
+    def generate_transformer_attr(self, input, index=None, method_name="transformer_attr"):      # EG:373-457
+        """Transformer attribution: rule 5 with the LRP relevance over the self-attention layers only; R_t_i is the last
+        cross layer's rule-5 map."""
+        m = self.model_usage
+        m.forward_backward(*input, index=index, lrp=True)
+        B, T, I = m._shape
+        dev = m.device
+        R_t_t = torch.eye(T, device=dev).repeat(B, 1, 1)
+        R_i_i = torch.eye(I, device=dev).repeat(B, 1, 1)
+        cam_of = lambda rec: rules.avg_heads_record(rec, B, use_cam=True)
+        for b in m.layer:
+            R_t_t, _ = rules.self_update(R_t_t, cam_of(b.att.recs[0]))
+        for b in m.r_layers:
+            R_i_i, _ = rules.self_update(R_i_i, cam_of(b.att.recs[0]))
+        for b in m.x_layers[:-1]:
+            R_t_t, _ = rules.self_update(R_t_t, cam_of(b.lang_self.recs[0]))
+            R_i_i, _ = rules.self_update(R_i_i, cam_of(b.visn_self.recs[0]))
+        last = m.x_layers[-1]
+        self.R_t_i = cam_of(last.cross.recs[0]).contiguous()
+        R_t_t, _ = rules.self_update(R_t_t, cam_of(last.lang_self.recs[0]))
+        self.R_t_t, self.R_i_i = R_t_t.contiguous(), R_i_i
+        return self._finish()
 
-    def generate_partial_lrp(self, input, index=None, method_name="partial_lrp"):
-        raise NotImplementedError("partial LRP needs the relprop sweep: outside the hot-path scope")
+    def generate_partial_lrp(self, input, index=None, method_name="partial_lrp"):                  # EG:459-506
+        """Partial LRP: head mean of the LRP relevance of the last cross layer (text -> image and the text self-attention),
+        each min-max normalised."""
+        m = self.model_usage
+        m.forward_backward(*input, index=index, lrp=True)
+        B = m._shape[0]
+        last = m.x_layers[-1]
+        self.R_t_i = rules.minmax_normalize(rules.head_mean_record(last.cross.recs[0], B, use_cam=True).contiguous())
+        self.R_t_t = rules.minmax_normalize(rules.head_mean_record(last.lang_self.recs[0], B, use_cam=True).contiguous())
+        return self._finish()
 
 
 class GeneratorOursAblationNoAggregation:
@@ -303,26 +374,24 @@ class GeneratorOursAblationNoAggregation:
         self.save_visualization = save_visualization
 
     def _self(self, rec, lang: bool):                                            # EG:220-268
-        cam = rules.avg_heads_record(rec, self.B)
+        cam = rules.avg_heads_record(rec, self.B, self.use_lrp)
         if lang:
             self.R_t_t, self.R_t_i = rules.bmm(cam, self.R_t_t), rules.bmm(cam, self.R_t_i)
         else:
             self.R_i_i, self.R_i_t = rules.bmm(cam, self.R_i_i), rules.bmm(cam, self.R_i_t)
 
     def _mm(self, R_ss, R_qq, R_qs, rec):                                        # EG:270-288 (rule 10 always with R_ss, R_qq)
-        cam = rules.avg_heads_record(rec, self.B)
+        cam = rules.avg_heads_record(rec, self.B, self.use_lrp)
         sq, ss, md = rules.mm_update_batched(R_ss, R_qq, R_qs, cam, self.normalize_self_attention, True)
         self._min_diag.append(md)
         return sq, ss
 
     def generate_ours_no_agg(self, input, index=None, use_lrp=False, normalize_self_attention=True, method_name="ours_no_agg"):
-        if use_lrp:
-            raise NotImplementedError("use_lrp=True needs the relprop sweep (lxmert_lrp.py:422-461): outside the hot-path scope")
-        self.use_lrp = use_lrp
+        self.use_lrp = bool(use_lrp)
         self.normalize_self_attention = normalize_self_attention
         m = self.model_usage
         ids, feats, boxes = input
-        m.forward_backward(ids, feats, boxes, index)
+        m.forward_backward(ids, feats, boxes, index, lrp=self.use_lrp)
         B, T, I = m._shape
         self.B = B
         dev = m.device

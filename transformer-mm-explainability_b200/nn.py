@@ -68,6 +68,25 @@ class Weight:
         self.pw, self.pwt = pack_weight(self.w), pack_weight(self.wt)
 
 
+class fp32_gemms:
+    """Context manager: every linear inside runs on the fp32 FFMA GEMM backend (``mmx_set_gemm_backend(0)``), restored on
+    exit.  Used by the LRP paths: relprop divides by activations, attention scores and whole-tensor sums that nearly cancel,
+    so the ~1e-6 (of max|C|) rounding of the tensor-core fp16x3 / 3xTF32 products - harmless for the gradient path - is
+    amplified to the 1e-1 level there, against ~1e-7-grade fp32 products for which the sweep's own fp32 noise dominates
+    (the reference's fp32 sweep is itself 1e-2 .. 1e-1 away from its fp64 evaluation at DETR-R50 / LXMERT-base size with
+    random-init weights; tests/test_lrp_gpu.py measures both on the same box)."""
+
+    def __enter__(self):
+        l = lib()
+        self.prev = l.mmx_get_gemm_backend()
+        l.mmx_set_gemm_backend(0)
+        return self
+
+    def __exit__(self, *exc):
+        lib().mmx_set_gemm_backend(self.prev)
+        return False
+
+
 class Tape:
     # Power-of-two factor the seed gradient is multiplied by (and every staged dA divided by, exactly): keeps the
     # operands of the fp16x3 dgrad GEMMs well inside fp16's exponent range (csrc/gemm_f16x3.cu).
@@ -204,7 +223,9 @@ class Tape:
                                          ptr(A), ldA, ptr(out), Dm, B, H, T, S, hd, C.c_float(scale), flags, current_stream()))
         y = Var(out)
         if record is not None:
-            record.A, record.S, record.dA = A, S, None
+            record.A, record.S, record.dA, record.cam = A, S, None, None
+            # what the relprop sweep of this attention reads (mmx_b200/lrp.py); references only, nothing is copied
+            record.saved = dict(q=q, k=k, v=v, o=y, B=B, H=H, T=T, S=S, hd=hd)
 
         def bwd():
             if y.g is None:
@@ -232,6 +253,8 @@ class AttnRecord:
     def __init__(self):
         self.A: Optional[torch.Tensor] = None
         self.dA: Optional[torch.Tensor] = None
+        self.cam: Optional[torch.Tensor] = None      # LRP relevance of A (``get_attn_cam()``), staged by mmx_b200.lrp
+        self.saved: dict = {}
         self.S = 0
 
     def get_attn(self) -> torch.Tensor:
@@ -240,6 +263,14 @@ class AttnRecord:
     def get_attn_gradients(self) -> Optional[torch.Tensor]:
         return None if self.dA is None else self.dA[..., :self.S]
 
-    def padded(self):
-        """(A, dA, ld) with the zero-padded row stride the rule-5 kernel can read directly."""
+    def get_attn_cam(self) -> Optional[torch.Tensor]:
+        return None if self.cam is None else self.cam[..., :self.S]
+
+    def padded(self, use_cam: bool = False):
+        """(A, dA, ld) with the zero-padded row stride the rule-5 kernel can read directly; ``use_cam``: the LRP relevance
+        of A in place of A (the ``use_lrp`` branches of the generators, DETR/modules/ExplanationGenerator.py:112-115)."""
+        if use_cam:
+            if self.cam is None:
+                raise MmxError("no LRP relevance recorded for this attention (run the relprop sweep first)")
+            return self.cam, self.dA, self.A.shape[-1]
         return self.A, self.dA, self.A.shape[-1]

@@ -31,11 +31,11 @@ def avg_heads_batched(cam: torch.Tensor, grad: torch.Tensor, batch: int) -> torc
     return out
 
 
-def avg_heads_record(rec, batch: int) -> torch.Tensor:
+def avg_heads_record(rec, batch: int, use_cam: bool = False) -> torch.Tensor:
     """Rule 5 straight from an attention record (nn.AttnRecord): reads the zero-padded staged A / dA in place with the
     128-bit kernel and returns a [B,T,S] VIEW of a zero-padded [B,T,ld] buffer (row stride ld = round_up(S,4)), the
     layout the tensor-core R update wants."""
-    A, dA, ld = rec.padded()
+    A, dA, ld = rec.padded(use_cam)
     if dA is None:
         raise MmxError("no attention gradient recorded (backward did not reach this attention)")
     B, H, T = A.shape[0], A.shape[1], A.shape[2]
@@ -127,8 +127,8 @@ def _mm(R_ss, R_qq, R_qs, cam_sq, flags):
     md = torch.zeros(2, device=Rs.device, dtype=torch.float32)
     check(l.mmx_mm_update(ptr(Rs), T, ptr(Rq), S, ptr(Rqs), T, ptr(Ab), S, ptr(sq_add), S, ptr(ss_add), T, 1, T, S, flags,
                           ptr(ws), ptr(md), current_stream()))
-    if (flags & MM_NORMALIZE) and (flags & MM_SELF_IN_10):
-        assert md.min().item() >= 0          # the reference's assert in handle_residual
+    if flags & MM_NORMALIZE:
+        assert md.min().item() >= 0          # the reference's assert in handle_residual (also when rule 10 drops the product)
     return sq_add[0], (ss_add[0] if ss_add is not None else None)
 
 
@@ -192,15 +192,22 @@ def mm_update_batched(R_ss, R_qq, R_qs, cam_sq, apply_normalization=True, apply_
     return sq_add, ss_add, md
 
 
-def head_mean_record(rec, batch: int) -> torch.Tensor:
+def head_mean_record(rec, batch: int, use_cam: bool = False) -> torch.Tensor:
     """mean over heads of the staged A (raw-attention / rollout baselines: ``cam.mean(dim=0)``,
-    DETR/modules/ExplanationGenerator.py:229-230,247-249).  A >= 0, so it is rule 5 with a gradient of ones."""
-    A, _, ld = rec.padded()
+    DETR/modules/ExplanationGenerator.py:229-230,247-249).  A >= 0, so it is rule 5 with a gradient of ones.
+    ``use_cam``: the head mean of the LRP relevance of A (partial LRP, :215-217), which is signed:
+    mean(x) = mean(relu(x)) - mean(relu(-x)), two rule-5 passes."""
+    A, _, ld = rec.padded(use_cam)
     B, H, T = A.shape[0], A.shape[1], A.shape[2]
     assert B == batch
     ones = torch.ones_like(A)
     out = torch.empty(B, T, ld, device=A.device, dtype=torch.float32)
     check(lib().mmx_avg_heads(ptr(A), ptr(ones), ptr(out), B, H, T, ld, ld, ld, current_stream()))
+    if use_cam:
+        import ctypes as C
+        neg = torch.empty_like(out)
+        check(lib().mmx_avg_heads(ptr(A), ptr(-ones), ptr(neg), B, H, T, ld, ld, ld, current_stream()))
+        check(lib().mmx_add(ptr(out), ld, ptr(neg), ld, C.c_float(-1.0), ptr(out), ld, B * T, ld, current_stream()))
     return out[..., :rec.S]
 
 

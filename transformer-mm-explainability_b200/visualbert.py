@@ -17,7 +17,7 @@ from typing import Dict, List, Optional
 import torch
 
 from ._lib import lib, check, ptr, current_stream, MmxError
-from .nn import Tape, Var, Weight, AttnRecord, ACT_GELU, ATTN_SCALE_SCORES, _f32
+from .nn import fp32_gemms, Tape, Var, Weight, AttnRecord, ACT_GELU, ATTN_SCALE_SCORES, _f32
 from . import rules
 
 EPS = 1e-12
@@ -66,8 +66,17 @@ class VisualBertEngine:
     def zero_grad(self):
         return None
 
-    def forward_backward(self, input: Dict[str, torch.Tensor], index=None, backward: bool = True) -> torch.Tensor:
-        """Forward staging A of every layer, one-hot on the answer score, backward staging dA (EG:68-81)."""
+    def forward_backward(self, *args, lrp: bool = False, **kwargs):
+        """See ``_forward_backward``.  With ``lrp=True`` every GEMM of the call (forward, dgrad and the relprop sweep) runs
+        on the fp32 FFMA backend (``nn.fp32_gemms``: the sweep amplifies tensor-core split rounding)."""
+        if lrp:
+            with fp32_gemms():
+                return self._forward_backward(*args, lrp=True, **kwargs)
+        return self._forward_backward(*args, lrp=False, **kwargs)
+
+    def _forward_backward(self, input: Dict[str, torch.Tensor], index=None, backward: bool = True, lrp: bool = False) -> torch.Tensor:
+        """Forward staging A of every layer, one-hot on the answer score, backward staging dA (EG:68-81); ``lrp=True``
+        adds the relprop sweep from the same one-hot (visual_bert.py:398-403), staging the relevance of every A."""
         dev, l = self.device, lib()
         with torch.cuda.device(dev):
             ids = input["input_ids"].to(dev).long()
@@ -100,19 +109,28 @@ class VisualBertEngine:
             for L in self.layers:
                 q, k, v = tape.linear(x, L.q), tape.linear(x, L.k), tape.linear(x, L.v)
                 o = tape.attention(q, k, v, B, H, S, S, scale, ATTN_SCALE_SCORES, key_bias, L.rec)       # BERT_ours.py:322-338
-                a = tape.layernorm(tape.add(tape.linear(o, L.o), x), *L.ln1, EPS)
-                x = tape.layernorm(tape.add(tape.linear(tape.linear(a, L.fc1, ACT_GELU), L.fc2), a), *L.ln2, EPS)
+                dense = tape.linear(o, L.o)
+                a = tape.layernorm(tape.add(dense, x), *L.ln1, EPS)
+                inter = tape.linear(a, L.fc1, ACT_GELU)
+                dense2 = tape.linear(inter, L.fc2)
+                L.saved = dict(x=x, dense=dense, ffn=dict(x=a, inter=inter, dense=dense2))
+                x = tape.layernorm(tape.add(dense2, a), *L.ln2, EPS)
             self.cls_index = input["input_mask"].to(dev).long().sum(1) - 2                             # visual_bert.py:382
             rows = (torch.arange(B, device=dev) * S + self.cls_index).to(torch.int32)
-            h = tape.layernorm(tape.linear(tape.gather_rows(x, rows), self.head_dense, ACT_GELU), *self.head_ln, EPS)
+            pooled = tape.gather_rows(x, rows)
+            h = tape.layernorm(tape.linear(pooled, self.head_dense, ACT_GELU), *self.head_ln, EPS)
             scores = tape.linear(h, self.head_out)
             self.scores, self._shape = scores.v, (B, S)
+            self.saved = dict(B=B, x=x, rows=rows, pooled=pooled, h=h, key_bias=key_bias)
             if backward:
                 idx = scores.v.argmax(-1) if index is None else torch.as_tensor(index, device=dev).reshape(-1).expand(B).long()
                 one_hot = torch.zeros_like(scores.v)
                 one_hot[torch.arange(B, device=dev), idx] = 1.0
                 tape.seed(scores, one_hot, B)
                 tape.backward()
+                if lrp:
+                    from .lrp import visualbert_sweep
+                    visualbert_sweep(self, one_hot)
         return self.scores
 
     def __call__(self, input):
@@ -166,8 +184,17 @@ class SelfAttentionGenerator:
 
     def generate_transformer_att(self, input, index=None, start_layer=0, save_visualization=False,
                                  save_visualization_per_token=False):
-        raise NotImplementedError("transformer attribution needs the relprop sweep (BERT_ours.py relprop methods): outside "
-                                  "the hot-path scope")
+        """Transformer attribution (EG:24-66): rule 5 on (grad, LRP relevance of A) per layer, then the non-normalising
+        rollout (EG:5-18) from ``start_layer``."""
+        m = self.model
+        m.forward_backward(input, index, lrp=True)
+        B = m._shape[0]
+        mats = [rules.avg_heads_record(L.rec, B, use_cam=True) for L in m.layers]
+        return self._cls_row(rules.compute_rollout_attention(mats, start_layer=start_layer, normalize=False))
 
     def generate_partial_lrp(self, input, index=None, save_visualization=False):
-        raise NotImplementedError("partial LRP needs the relprop sweep: outside the hot-path scope")
+        """Partial LRP (EG:109-131): head mean of the last layer's LRP relevance, min-max normalised."""
+        m = self.model
+        m.forward_backward(input, index, lrp=True)
+        cam = rules.head_mean_record(m.layers[-1].rec, m._shape[0], use_cam=True).contiguous()
+        return self._cls_row(rules.minmax_normalize(cam))
