@@ -689,7 +689,10 @@ def main():
     eager = None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        eager = torch_eager_leg(D, cfg, B)
+        try:
+            eager = torch_eager_leg(D, cfg, B)
+        except Exception as exc:              # informational leg only
+            eager = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     del eng, inputs
     torch.cuda.empty_cache()
 

@@ -104,6 +104,14 @@ int mmx_mm_update(const float* R_ss, int ld_ss, const float* R_qq, int ld_qq, co
                   const float* Abar_sq, int ld_a, float* R_sq_add, int ld_sq_add, float* R_ss_add, int ld_ss_add,
                   int B, int T, int S, int flags, void* workspace, float* min_diag, void* stream);
 
+/* The whole rule-6 chain of one tower in ONE launch: R = I, then R <- R + Abar[l] R for l = 0 .. L-1, with R resident in
+ * shared memory and the products on the tensor cores (mma.sync 3xTF32).  Replaces the per-block `R = R + torch.bmm(cam, R)`
+ * loop (CLIP_explainability.ipynb:169-183; ViT ipynb:1193-1199; VisualBERT ExplanationGenerator.py:84-93).
+ * Abar: [L][B][S][ld] (layer_stride elements between layers, S*ld between samples, ld % 4 == 0, pad columns zero);
+ * R_out: [B][S][ld_out].  S <= 128 (larger S: mmx_self_update per layer, which runs on the tcgen05 GEMM). */
+int mmx_self_chain(const float* Abar, long long layer_stride, int ld, float* R_out, int ld_out, int B, int S, int L,
+                   void* stream);
+
 /* Rollout baseline: prod_l rownorm(mats[l] + I), l = start_layer .. L-1, later layers multiplied on the left.
  * Replaces compute_rollout_attention (DETR/modules/ExplanationGenerator.py:5-16; normalize=0 gives the
  * VisualBERT variant, VisualBERT/mmf/models/transformers/backends/ExplanationGenerator.py:5-17).

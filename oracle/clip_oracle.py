@@ -119,7 +119,7 @@ def clip_forward(sd, cfg: ClipConfig, images, tokens):
     W = cfg.vision_width
     x = F.conv2d(images, sd["visual.conv1.weight"], stride=cfg.vision_patch_size)        # model.py:230
     x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
-    cls = sd["visual.class_embedding"] + torch.zeros(x.shape[0], 1, W, dtype=x.dtype)
+    cls = sd["visual.class_embedding"] + torch.zeros(x.shape[0], 1, W, dtype=x.dtype, device=x.device)
     x = torch.cat([cls, x], dim=1) + sd["visual.positional_embedding"]
     x = F.layer_norm(x, (W,), sd["visual.ln_pre.weight"], sd["visual.ln_pre.bias"])
     A_v: List[torch.Tensor] = []
@@ -129,13 +129,13 @@ def clip_forward(sd, cfg: ClipConfig, images, tokens):
     img_f = x @ sd["visual.proj"]                                                         # model.py:243-244
 
     Wt = cfg.transformer_width
-    mask = torch.full((cfg.context_length, cfg.context_length), float("-inf"), dtype=images.dtype).triu_(1)
+    mask = torch.full((cfg.context_length, cfg.context_length), float("-inf"), dtype=images.dtype, device=images.device).triu_(1)
     t = F.embedding(tokens, sd["token_embedding.weight"]) + sd["positional_embedding"]   # model.py:350-352
     A_t: List[torch.Tensor] = []
     t = _tower(t.permute(1, 0, 2), sd, "transformer.", cfg.transformer_layers, cfg.transformer_heads, mask, A_t)
     t = t.permute(1, 0, 2)
     t = F.layer_norm(t, (Wt,), sd["ln_final.weight"], sd["ln_final.bias"])
-    txt_f = t[torch.arange(t.shape[0]), tokens.argmax(dim=-1)] @ sd["text_projection"]   # model.py:360
+    txt_f = t[torch.arange(t.shape[0], device=t.device), tokens.argmax(dim=-1)] @ sd["text_projection"]   # model.py:360
     img_n = img_f / img_f.norm(dim=-1, keepdim=True)
     txt_n = txt_f / txt_f.norm(dim=-1, keepdim=True)
     logits = sd["logit_scale"].exp() * img_n @ txt_n.t()                                  # model.py:373-374
@@ -170,7 +170,7 @@ def clip_interpret(sd, cfg: ClipConfig, images, tokens, start_layer: int = -1, s
         if start == -1:
             start = L - 1                                                                 # ipynb:165-167
         S = A[0].shape[-1]
-        R = torch.eye(S, dtype=dtype).unsqueeze(0).expand(B, S, S)
+        R = torch.eye(S, dtype=dtype, device=A[0].device).unsqueeze(0).expand(B, S, S)
         bars = {}
         for i in range(L):
             if i < start:

@@ -73,6 +73,29 @@ def golden_clip_example():
     print("wrote clip_example", {k: v.shape for k, v in out.items() if not k.startswith("sd.")})
 
 
+def golden_lxmert_perturbation():
+    """lxmert/lxmert/perturbation.py:85-194 (the two perturbation loops, unmodified source) on one synthetic item; the model
+    behind ``self.lxmert_vqa`` is the unmodified reference LXMERT (ref_lxmert)."""
+    from . import lxmert_oracle as lo, ref_lxmert, ref_perturbation as rp
+    cfg = lo.LXMERT_TINY
+    sd = lo.init_state_dict(cfg, 3)
+    ids, feats, boxes = lo.synthetic_inputs(cfg, 1, 9, 11, seed=6)
+    rtt, rti = ref_lxmert.generate_ours(cfg, sd, ids, feats, boxes, use_lrp=False)
+    cam_image, cam_text = rti[0][0].clone(), rtt[0][0].clone()          # perturbation.py:241-244: row of [CLS]
+    model_fn = ref_lxmert.forward_fn(cfg, sd)
+    out = {"ids": ids.numpy(), "feats": feats.numpy(), "boxes": boxes.numpy(), "cam_image": cam_image.numpy(),
+           "cam_text": cam_text.numpy()}
+    for k, v in sd.items():
+        out["sd." + k] = v.numpy()
+    for modality in ("image", "text"):
+        for positive in (False, True):
+            scores, steps = rp.run(model_fn, ids, feats, boxes, cam_image, cam_text, modality, positive, cfg.num_labels)
+            out[f"scores.{modality}.{int(positive)}"] = scores.numpy()
+    out["pert_steps"] = np.array(steps)
+    np.savez_compressed(os.path.join(OUT, "lxmert_perturbation.npz"), **out)
+    print("wrote lxmert_perturbation", {k: v.shape for k, v in out.items() if not k.startswith("sd.")})
+
+
 def golden_rules():
     detr = _load_module("ref_detr_eg", "DETR/modules/ExplanationGenerator.py")
     lx = _load_module("ref_lxmert_eg", "lxmert/lxmert/src/ExplanationGenerator.py")
@@ -238,6 +261,9 @@ def main():
     if "--clip-example" in argv:
         golden_clip_example()
         return
+    if "--lxmert-perturbation" in argv:
+        golden_lxmert_perturbation()
+        return
     if "--only-new" in argv:
         golden_detr()
         golden_lxmert()
@@ -250,6 +276,7 @@ def main():
     golden_clip_example()
     golden_detr()
     golden_lxmert()
+    golden_lxmert_perturbation()
     golden_visualbert()
     golden_otsu()
 

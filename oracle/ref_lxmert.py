@@ -142,3 +142,14 @@ def generate_ours_no_agg(cfg, sd, ids, feats, boxes, **kw):
             a, c = gen.generate_ours_no_agg(None, use_lrp=False, **kw)
             Rtt.append(a.detach().clone()); Rti.append(c.detach().clone())
     return torch.stack(Rtt), torch.stack(Rti)
+
+
+def forward_fn(cfg, sd):
+    """(input_ids, visual_feats, visual_pos) -> answer scores through the unmodified reference LXMERT modules (what
+    ``ModelPert.lxmert_vqa(...)`` returns as ``question_answering_score``), for oracle/ref_perturbation.py."""
+    m, _ = build(cfg, sd)
+
+    def fn(ids, feats, boxes):
+        with torch.enable_grad():                       # the attention hooks of lxmert_lrp.py register on tensors that require grad
+            return m(ids, feats, boxes).detach()
+    return fn

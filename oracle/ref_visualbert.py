@@ -1,10 +1,11 @@
 """Runs the UNMODIFIED reference VisualBERT encoder / head modules + SelfAttentionGenerator on CPU (build container only;
 TEST INFRASTRUCTURE).  ``BERT_ours.py``, ``layers_ours.py`` and ``ExplanationGenerator.py`` of
 VisualBERT/mmf/models/transformers/backends are loaded by file path under a private package name (importing the ``mmf``
-package itself needs omegaconf and the mmf registry).  The mmf embeddings module has the same problem, so
-``BertVisioLinguisticEmbeddings`` (VisualBERT/mmf/modules/embeddings.py:305-451) is restated here with nn.Embedding /
-nn.Linear / nn.LayerNorm under the reference's parameter names; everything above it (12 x BertLayer with the attention
-hooks, BertPredictionHeadTransform, the generator) is the reference's own code."""
+package itself needs omegaconf and the mmf registry).  ``BertVisioLinguisticEmbeddings`` is the reference's own class too:
+VisualBERT/mmf/modules/embeddings.py is executed by file path with its unrelated imports (attention / bottleneck / layers /
+file_io / vocab modules, none of which the class touches) stubbed and ``transformers.modeling_bert`` aliased to the module
+transformers 5.x keeps ``BertEmbeddings`` in.  So the whole model - embeddings, 12 x BertLayer with the attention hooks,
+BertPredictionHeadTransform - and the generator are the reference's code."""
 from __future__ import annotations
 
 import importlib.util
@@ -39,37 +40,53 @@ def _import_ref():
     return mods
 
 
+def _import_embeddings():
+    """``BertVisioLinguisticEmbeddings`` (VisualBERT/mmf/modules/embeddings.py:305-451) from the reference file itself."""
+    rs._ensure_path()
+    full = f"{_PKG}.mmf_embeddings"
+    if full in sys.modules:
+        return sys.modules[full].BertVisioLinguisticEmbeddings
+    import transformers.models.bert.modeling_bert as mb
+    sys.modules.setdefault("transformers.modeling_bert", mb)
+    stubs = {"VisualBERT": [], "VisualBERT.mmf": [], "VisualBERT.mmf.modules": [], "VisualBERT.mmf.utils": [],
+             "VisualBERT.mmf.modules.attention": ["AttentionLayer", "SelfAttention", "SelfGuidedAttention"],
+             "VisualBERT.mmf.modules.bottleneck": ["MovieBottleneck"],
+             "VisualBERT.mmf.modules.layers": ["AttnPool1d", "Identity"],
+             "VisualBERT.mmf.utils.file_io": ["PathManager"], "VisualBERT.mmf.utils.vocab": ["Vocab"]}
+    added = []
+    for name, attrs in stubs.items():
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            for a in attrs:
+                setattr(m, a, type(a, (), {}))
+            sys.modules[name] = m
+            added.append(name)
+    try:
+        spec = importlib.util.spec_from_file_location(full, os.path.join(rs.REFERENCE_ROOT, "VisualBERT", "mmf", "modules", "embeddings.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[full] = m
+        spec.loader.exec_module(m)
+    finally:
+        for name in added:                 # the stubs must not shadow anything for later imports
+            sys.modules.pop(name, None)
+    return m.BertVisioLinguisticEmbeddings
+
+
 def build(cfg, sd):
     lo, bo, eg = _import_ref()
+    RefEmbeddings = _import_embeddings()
     from transformers import BertConfig
     hc = BertConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads,
                     intermediate_size=cfg.intermediate, hidden_act="gelu", hidden_dropout_prob=0.0,
                     attention_probs_dropout_prob=0.0, max_position_embeddings=cfg.max_pos, type_vocab_size=cfg.type_vocab,
                     layer_norm_eps=1e-12)
-
-    class Embeddings(nn.Module):            # embeddings.py:305-451, "plain" strategy
-        def __init__(self):
-            super().__init__()
-            self.word_embeddings = nn.Embedding(cfg.vocab, cfg.hidden)
-            self.position_embeddings = nn.Embedding(cfg.max_pos, cfg.hidden)
-            self.token_type_embeddings = nn.Embedding(cfg.type_vocab, cfg.hidden)
-            self.LayerNorm = nn.LayerNorm(cfg.hidden, eps=1e-12)
-            self.token_type_embeddings_visual = nn.Embedding(cfg.type_vocab, cfg.hidden)
-            self.position_embeddings_visual = nn.Embedding(cfg.max_pos, cfg.hidden)
-            self.projection = nn.Linear(cfg.visual_dim, cfg.hidden)
-
-        def forward(self, input_ids, token_type_ids, visual_embeddings, visual_embeddings_type):
-            pos = torch.arange(input_ids.size(1)).unsqueeze(0).expand_as(input_ids)
-            text = self.word_embeddings(input_ids) + self.position_embeddings(pos) + self.token_type_embeddings(token_type_ids)
-            v = self.projection(visual_embeddings)
-            v = v + self.position_embeddings_visual(torch.zeros(v.shape[:-1], dtype=torch.long)) \
-                + self.token_type_embeddings_visual(visual_embeddings_type)
-            return self.LayerNorm(torch.cat((text, v), dim=1))
+    hc.visual_embedding_dim = cfg.visual_dim
 
     class Bert(nn.Module):
         def __init__(self):
             super().__init__()
-            self.embeddings = Embeddings()
+            self.embeddings = RefEmbeddings(hc)       # the reference class (embeddings.py:305-451), "plain" strategy
             self.encoder = bo.BertEncoder(hc)
 
         def relprop(self, cam, **kwargs):          # VisualBERTBase.relprop, visual_bert.py:150-152
@@ -85,8 +102,8 @@ def build(cfg, sd):
         def forward(self, inp):
             am = inp["attention_mask"]
             ext = (1.0 - am.unsqueeze(1).unsqueeze(2).to(torch.float32)) * -10000.0
-            emb = self.bert.embeddings(inp["input_ids"], inp["token_type_ids"], inp["visual_embeddings"],
-                                       inp["visual_embeddings_type"])
+            emb = self.bert.embeddings(inp["input_ids"], inp["token_type_ids"], visual_embeddings=inp["visual_embeddings"],
+                                       visual_embeddings_type=inp["visual_embeddings_type"])       # visual_bert.py:112-118
             seq = self.bert.encoder(emb, ext)[0]
             idx = inp["input_mask"].sum(1) - 2
             pooled = self.vqa_pooler(seq, 1, idx.clone().detach())

@@ -233,10 +233,11 @@ def generate_partial_lrp(sd, cfg, inp, index=None, dtype=torch.float32):
     return torch.stack(out)
 
 
-PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]      # VisualBERT/mmf/trainers/core/evaluation_loop.py:96
+PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]      # VisualBERT/mmf/trainers/core/evaluation_loop.py:96 (text)
+PERT_STEPS_IMAGE = [0, 0.5, 0.75, 0.95, 0.96, 0.97, 0.98, 0.99, 1]   # :94 (image: the 100 boxes are thinned more aggressively)
 
 
-def perturbation_image(sd, cfg, inp, method_cam, is_positive_pert=False, steps=PERT_STEPS):
+def perturbation_image(sd, cfg, inp, method_cam, is_positive_pert=False, steps=PERT_STEPS_IMAGE):
     """evaluation_loop.py:105-124 on one sample: per step keep the top ``int((1-step)*V)`` visual tokens (gathered in topk
     order) and re-run the model; returns the scores per step.  PARITY UNPINNED for the loop itself (the mmf trainer and
     dataset cannot be imported here); the model it calls is pinned through the VisualBERT goldens."""

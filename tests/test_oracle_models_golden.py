@@ -131,3 +131,18 @@ def test_lxmert_lrp_baselines_oracle_golden(golden_dir, method):
     rtt, rti = lo.generate_lrp_baseline(_sd(g), lo.LXMERT_TINY, torch.from_numpy(g["ids"]), torch.from_numpy(g["feats"]),
                                         torch.from_numpy(g["boxes"]), method)
     assert rel_err(rtt, g[f"base.{method}.Rtt"]) < 1e-5 and rel_err(rti, g[f"base.{method}.Rti"]) < 1e-5
+
+
+@pytest.mark.parametrize("positive", [False, True])
+@pytest.mark.parametrize("modality", ["image", "text"])
+def test_lxmert_perturbation_oracle_golden(golden_dir, modality, positive):
+    """The perturbation loops: the oracle restatement against the per-step answer scores produced by the
+    UNMODIFIED loops of lxmert/lxmert/perturbation.py:85-194 driving the unmodified reference LXMERT
+    (oracle/ref_perturbation.py; golden written by oracle/make_golden.py --lxmert-perturbation)."""
+    g = np.load(os.path.join(golden_dir, "lxmert_perturbation.npz"))
+    sd = _sd(g)
+    ids, feats, boxes = (torch.from_numpy(g[k]) for k in ("ids", "feats", "boxes"))
+    assert list(g["pert_steps"]) == lo.PERT_STEPS
+    fn = lo.perturbation_image if modality == "image" else lo.perturbation_text
+    got = fn(sd, lo.LXMERT_TINY, ids, feats, boxes, torch.from_numpy(g["cam_" + modality]), positive)
+    assert rel_err(got, g[f"scores.{modality}.{int(positive)}"]) < 1e-5

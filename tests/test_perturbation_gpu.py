@@ -84,6 +84,26 @@ def test_lxmert_perturbation_vs_oracle(modality, positive):
 
 @pytest.mark.parametrize("positive", [False, True])
 @pytest.mark.parametrize("modality", ["image", "text"])
+def test_lxmert_perturbation_reference_golden(golden_dir, modality, positive):
+    """Against the per-step answer scores of the UNMODIFIED reference loops (lxmert/lxmert/perturbation.py:85-194 driving the
+    unmodified reference LXMERT; tests/golden/lxmert_perturbation.npz, oracle/ref_perturbation.py)."""
+    import os
+    import mmx_b200
+    g = np.load(os.path.join(golden_dir, "lxmert_perturbation.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    eng = mmx_b200.LxmertEngine(sd, num_heads=lo.LXMERT_TINY.heads, device="cuda:0")
+    item = tuple(torch.from_numpy(g[k]).cuda() for k in ("ids", "feats", "boxes"))
+    cam_image, cam_text = torch.from_numpy(g["cam_image"]).cuda(), torch.from_numpy(g["cam_text"]).cuda()
+    pert = mmx_b200.LxmertPerturbation(eng)
+    assert pert.pert_steps == list(g["pert_steps"])
+    ans = getattr(pert, "perturbation_" + modality)(item, cam_image, cam_text, positive)
+    ref = g[f"scores.{modality}.{int(positive)}"]
+    assert rel_err(pert.scores, ref) < TOL
+    assert torch.equal(ans.cpu(), torch.from_numpy(ref).argmax(-1))
+
+
+@pytest.mark.parametrize("positive", [False, True])
+@pytest.mark.parametrize("modality", ["image", "text"])
 def test_visualbert_perturbation_vs_oracle(modality, positive):
     import mmx_b200
     from oracle import visualbert_oracle as vo
@@ -98,6 +118,8 @@ def test_visualbert_perturbation_vs_oracle(modality, positive):
     fn = "perturbation_" + modality
     ans = getattr(pert, fn)(dinp, cam, positive)
     ref = getattr(vo, fn)(sd, cfg, inp, cam.cpu(), positive)
-    assert pert.scores.shape == ref.shape == (len(vo.PERT_STEPS), cfg.num_labels)
+    steps = vo.PERT_STEPS_IMAGE if modality == "image" else vo.PERT_STEPS          # evaluation_loop.py:93-96
+    assert pert.steps_for(modality) == steps
+    assert pert.scores.shape == ref.shape == (len(steps), cfg.num_labels)
     assert rel_err(pert.scores, ref) < TOL
     assert torch.equal(ans.cpu(), ref.argmax(-1))

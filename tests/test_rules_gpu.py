@@ -142,3 +142,33 @@ def test_rollout_batched_visualbert_variant(mmx):
     assert rel_err(out, orules.compute_rollout_attention(mats, 0, normalize=True)) < 1e-5
     # rows of a normalised rollout sum to 1
     assert rel_err(out.sum(-1), torch.ones(3, 30)) < 1e-5
+
+
+@pytest.mark.parametrize("S,L,B", [(50, 12, 5), (77, 12, 3), (20, 9, 4), (36, 5, 2), (100, 6, 2), (128, 2, 1), (7, 1, 3), (77, 1, 2)])
+def test_rule6_chain_kernel(S, L, B):
+    """mmx_self_chain: R = I; R <- R + Abar_l R for all layers in ONE launch (R resident in shared memory, mma.sync 3xTF32)
+    vs the per-layer fp64 loop of CLIP_explainability.ipynb:169-183."""
+    import ctypes as C
+    import mmx_b200
+    from mmx_b200._lib import lib, check, ptr, current_stream
+    g = torch.Generator().manual_seed(S * 100 + L)
+    ld = (S + 3) // 4 * 4
+    Ab = torch.zeros(L, B, S, ld)
+    Ab[..., :S] = torch.rand(L, B, S, S, generator=g) * (2.0 / S)           # rule-5 outputs: non-negative, rows of O(1) mass
+    if B > 1:
+        Ab[:, 1, S // 2:, :] = 0                                            # a ragged sample: dead rows / columns stay identity
+        Ab[:, 1, :, S // 2:] = 0
+    out = torch.full((B, S, ld), float("nan"), device="cuda")
+    check(lib().mmx_self_chain(ptr(Ab.cuda()), B * S * ld, ld, ptr(out), ld, B, S, L, current_stream()))
+    R = torch.eye(S, dtype=torch.float64).repeat(B, 1, 1)
+    for l in range(L):
+        R = R + Ab[l, :, :, :S].double() @ R
+    assert rel_err(out[..., :S], R) < 1e-5
+    if ld > S:
+        assert (out[..., S:] == 0).all()
+    if B > 1:
+        assert torch.equal(out[1, S // 2:, :S].cpu(), torch.eye(S)[S // 2:])
+    # one sample alone == inside the batch, bit for bit
+    one = torch.empty(1, S, ld, device="cuda")
+    check(lib().mmx_self_chain(ptr(Ab[:, :1].contiguous().cuda()), S * ld, ld, ptr(one), ld, 1, S, L, current_stream()))
+    assert torch.equal(one[0], out[0])

@@ -37,6 +37,7 @@ _SIGS = {
     "mmx_attn_gradcam": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p] + [C.c_int] * 6 + [C.c_void_p]),
     "mmx_self_update": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mmx_self_chain": (C.c_int, [c_float_p, C.c_longlong, C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mmx_handle_residual": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p]),
     "mmx_mm_update_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "mmx_mm_update": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int,

@@ -1,10 +1,11 @@
 // Attention forward that stages A = softmax(QK^T) to HBM, and the attention backward that stages dA = dO V^T
 // (the two tensors the reference captures with forward / backward hooks) and continues to dQ, dK, dV.
-// 3xTF32 mma.sync products with fp32 softmax; one CTA = one (batch, head, 64-query tile), 8 warps; score rows live in shared memory so any S <= ~1500
+// fp16x3 mma.sync (m16n8k16) products with fp32 softmax; one CTA = one (batch, head, 64-query tile), 8 warps; score rows live in shared memory so any S <= ~1500
 // (DETR 850, ViT-L/14@336 577) is handled without a second pass.  Deterministic (no atomics): dK/dV come from a
 // second kernel that walks the query tiles for one key tile.
 #include "mmx_common.cuh"
 #include <math_constants.h>
+#include <cuda_fp16.h>
 
 namespace mmx {
 
@@ -21,75 +22,86 @@ struct Ragged {
 constexpr int TKEY = 64;  // keys per shared-memory tile
 constexpr int KV_THREADS = 256;
 
-// The three small matrix products per head (scores, P.V and their backward twins) run on the tensor cores as
-// mma.sync.m16n8k8 TF32 with the same fp32-faithful 3-pass split as the linear GEMMs (gemm_tcgen05.cu): x = hi + lo,
-// hi*hi into one accumulator, lo*hi + hi*lo into a second one that is added once at the end.  tcgen05 / TMEM is the
-// wrong tool here: a head is 50x50x64 (or 77x77x64), far below one 128-row UMMA tile, and the kernels are bound by
-// instruction issue and the staged A / dA traffic, not by math.  The FFMA version of these loops issued 3x the
-// instructions and 5x the shared-memory wavefronts (profiles/attn_r1.md).
+// The small matrix products per head (scores, P.V and their backward twins) run on the tensor cores as
+// mma.sync.m16n8k16 with fp16 operands and the same fp32-faithful 3-pass split as the linear GEMMs (gemm_f16x3.cu):
+// x = hi + lo' / 2048 with hi = fp16(x), lo' = fp16((x - hi) * 2048); hi*hi goes into one fp32 accumulator, lo'*hi + hi*lo'
+// into a second one that is folded in once (x 1/2048) at the end.  fp16 x fp16 products are exact in the fp32 accumulator,
+// one instruction covers K = 16 (m16n8k8 TF32: 8) at twice the TF32 rate, so against the 3xTF32 version this halves the
+// MMA count and the fragment loads per unit of K.  Operand range: |x| <= 65504 and an absolute floor of 3e-11 - activations,
+// probabilities and the (power-of-two normalised, see gscale) gradient stream sit well inside.  tcgen05 / TMEM is the wrong
+// tool here: a head is 50x50x64 (or 77x77x64), far below one 128-row UMMA tile.
 //
-// Fragment layout of m16n8k8 (g = lane / 4, t = lane % 4):
-//   A (16x8, row)  a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
-//   B ( 8x8, col)  b0 (k=t, n=g)  b1 (k=t+4, n=g)
-//   C (16x8)       c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
-// Shared-memory strides are chosen so that each fragment load hits 32 different banks: operands indexed
-// [row or n = g][k = t] use a stride = 4 (mod 8) floats, operands indexed [k = t][n = g] a stride = 8 (mod 16).
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xFFFFE000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+// Fragment layout of m16n8k16 (g = lane / 4, t = lane % 4), every register = two consecutive-k fp16 values:
+//   A (16x16, row)  a0 (g, 2t..2t+1)  a1 (g+8, 2t..)  a2 (g, 2t+8..)  a3 (g+8, 2t+8..)
+//   B (16x8, col)   b0 (k = 2t..2t+1, n = g)  b1 (k = 2t+8.., n = g)
+//   C (16x8)        c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+// Shared memory keeps fp32; the split happens at fragment-load time.  Strides are chosen so that each fragment load is
+// bank-conflict free: operands indexed [row or n = g][k = 2t] are read with 64-bit loads and want a stride = 8 (mod 16)
+// floats; operands indexed [k = 2t][n or row = g] are read with 32-bit loads from rows 2t and 2t+1 and want a stride
+// = 4 (mod 16).
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+__device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);            // x0 in the low half: element k sits below element k+1
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 struct FragA { uint32_t hi[4], lo[4]; };
 struct FragB { uint32_t hi[2], lo[2]; };
-// A fragment of a [row][k] operand (stride ld): p points at (row0 + g, k0 + t)
-__device__ __forceinline__ FragA frag_a_rowmajor(const float* p, int ld) {
+// A fragment of a [row][k] operand (stride ld): p points at (row0 + g, k0 + 2t); `mul` scales the operand before the split
+__device__ __forceinline__ FragA frag_a_rowmajor(const float* p, int ld, float mul = 1.f) {
   FragA f;
-  split_tf32(p[0], f.hi[0], f.lo[0]);
-  split_tf32(p[8 * ld], f.hi[1], f.lo[1]);
-  split_tf32(p[4], f.hi[2], f.lo[2]);
-  split_tf32(p[8 * ld + 4], f.hi[3], f.lo[3]);
+  const float2 x0 = *reinterpret_cast<const float2*>(p), x1 = *reinterpret_cast<const float2*>(p + 8 * ld);
+  const float2 x2 = *reinterpret_cast<const float2*>(p + 8), x3 = *reinterpret_cast<const float2*>(p + 8 * ld + 8);
+  split_f16(x0.x * mul, x0.y * mul, f.hi[0], f.lo[0]);
+  split_f16(x1.x * mul, x1.y * mul, f.hi[1], f.lo[1]);
+  split_f16(x2.x * mul, x2.y * mul, f.hi[2], f.lo[2]);
+  split_f16(x3.x * mul, x3.y * mul, f.hi[3], f.lo[3]);
   return f;
 }
-// A fragment of a TRANSPOSED operand stored [k][row] (stride ld): p points at (k0 + t, row0 + g)
+// A fragment of a TRANSPOSED operand stored [k][row] (stride ld): p points at (k0 + 2t, row0 + g)
 __device__ __forceinline__ FragA frag_a_kmajor(const float* p, int ld) {
   FragA f;
-  split_tf32(p[0], f.hi[0], f.lo[0]);
-  split_tf32(p[8], f.hi[1], f.lo[1]);
-  split_tf32(p[4 * ld], f.hi[2], f.lo[2]);
-  split_tf32(p[4 * ld + 8], f.hi[3], f.lo[3]);
+  split_f16(p[0], p[ld], f.hi[0], f.lo[0]);
+  split_f16(p[8], p[ld + 8], f.hi[1], f.lo[1]);
+  split_f16(p[8 * ld], p[9 * ld], f.hi[2], f.lo[2]);
+  split_f16(p[8 * ld + 8], p[9 * ld + 8], f.hi[3], f.lo[3]);
   return f;
 }
-// B fragment of an operand stored [n][k] (stride ld): p points at (n0 + g, k0 + t)
+// B fragment of an operand stored [n][k] (stride ld): p points at (n0 + g, k0 + 2t)
 __device__ __forceinline__ FragB frag_b_nmajor(const float* p) {
   FragB f;
-  split_tf32(p[0], f.hi[0], f.lo[0]);
-  split_tf32(p[4], f.hi[1], f.lo[1]);
+  const float2 x0 = *reinterpret_cast<const float2*>(p), x1 = *reinterpret_cast<const float2*>(p + 8);
+  split_f16(x0.x, x0.y, f.hi[0], f.lo[0]);
+  split_f16(x1.x, x1.y, f.hi[1], f.lo[1]);
   return f;
 }
-// B fragment of an operand stored [k][n] (stride ld): p points at (k0 + t, n0 + g)
+// B fragment of an operand stored [k][n] (stride ld): p points at (k0 + 2t, n0 + g)
 __device__ __forceinline__ FragB frag_b_kmajor(const float* p, int ld) {
   FragB f;
-  split_tf32(p[0], f.hi[0], f.lo[0]);
-  split_tf32(p[4 * ld], f.hi[1], f.lo[1]);
+  split_f16(p[0], p[ld], f.hi[0], f.lo[0]);
+  split_f16(p[8 * ld], p[9 * ld], f.hi[1], f.lo[1]);
   return f;
 }
 __device__ __forceinline__ void mma3(float (&main)[4], float (&cross)[4], const FragA& a, const FragB& b) {
-  mma_tf32(cross, a.lo, b.hi);
-  mma_tf32(cross, a.hi, b.lo);
-  mma_tf32(main, a.hi, b.hi);
+  mma_f16(cross, a.lo, b.hi);
+  mma_f16(cross, a.hi, b.lo);
+  mma_f16(main, a.hi, b.hi);
 }
 
-__host__ __device__ inline int score_ld(int S) { return round_up(S, 8) + 4; }   // smem stride of a score row: = 4 (mod 8)
+__host__ __device__ inline int score_ld(int S) { return round_up(S, 16) + 8; }  // smem stride of a score row: = 8 (mod 16)
 
 template <int HD>
 struct AttnSmem {
-  static constexpr int LDX = HD + 4;   // [row / key][d] operands (Q, dO tiles; K, V as the scores' B operand)
-  static constexpr int LDV = HD + 8;   // [key][d] operand of the P.V product
-  static size_t bytes(int S, int TQ) { return sizeof(float) * ((size_t)TQ * score_ld(S) + (size_t)TQ * LDX + (size_t)TKEY * LDV); }
+  static constexpr int LDX = HD + 8;   // [row / key][d] operands (Q, dO tiles; K, V as the scores' B operand): = 8 (mod 16)
+  static constexpr int LDV = HD + 4;   // [key][d] operand of the P.V product: = 4 (mod 16)
+  static size_t bytes(int S, int TQ) { return sizeof(float) * ((size_t)TQ * score_ld(S) + (size_t)TQ * LDX + (size_t)TKEY * LDX); }
 };
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching src
@@ -134,19 +146,13 @@ __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy
     // live 8-key blocks of this warp's half (may be <= 0); a row block entirely past the sample's rows does no math
     const int ntiles = m0 < live_rows ? (S - j0 - kh + 7) >> 3 : 0;
 #pragma unroll 2
-    for (int k0 = 0; k0 < HD; k0 += 8) {
-      FragA a;
-      {
-        const float* xa = sX + (m0 + g) * LDX + k0 + t;   // the reference scales q before the product (auxilary.py:173)
-        split_tf32(xa[0] * pre_scale, a.hi[0], a.lo[0]);
-        split_tf32(xa[8 * LDX] * pre_scale, a.hi[1], a.lo[1]);
-        split_tf32(xa[4] * pre_scale, a.hi[2], a.lo[2]);
-        split_tf32(xa[8 * LDX + 4] * pre_scale, a.hi[3], a.lo[3]);
-      }
+    for (int k0 = 0; k0 < HD; k0 += 16) {
+      // the reference scales q before the product (auxilary.py:173)
+      const FragA a = frag_a_rowmajor(sX + (m0 + g) * LDX + k0 + 2 * t, LDX, pre_scale);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         if (nt < ntiles) {
-          const FragB b = frag_b_nmajor(sY + (kh + nt * 8 + g) * LDX + k0 + t);
+          const FragB b = frag_b_nmajor(sY + (kh + nt * 8 + g) * LDX + k0 + 2 * t);
           mma3(acc[nt], crs[nt], a, b);
         }
       }
@@ -156,9 +162,10 @@ __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy
       const int j = j0 + kh + nt * 8 + 2 * t;           // even; ldP is even
       if (j < ldP) {
         float* p0 = sP + (m0 + g) * ldP + j;
-        *reinterpret_cast<float2*>(p0) = make_float2((acc[nt][0] + crs[nt][0]) * post_scale, (acc[nt][1] + crs[nt][1]) * post_scale);
-        *reinterpret_cast<float2*>(p0 + 8 * ldP) =
-            make_float2((acc[nt][2] + crs[nt][2]) * post_scale, (acc[nt][3] + crs[nt][3]) * post_scale);
+        *reinterpret_cast<float2*>(p0) = make_float2(fmaf(crs[nt][0], LO_INV, acc[nt][0]) * post_scale,
+                                                     fmaf(crs[nt][1], LO_INV, acc[nt][1]) * post_scale);
+        *reinterpret_cast<float2*>(p0 + 8 * ldP) = make_float2(fmaf(crs[nt][2], LO_INV, acc[nt][2]) * post_scale,
+                                                               fmaf(crs[nt][3], LO_INV, acc[nt][3]) * post_scale);
       }
     }
   }
@@ -187,14 +194,14 @@ __device__ __forceinline__ void tile_pv(const float* __restrict__ Y, int ldy, lo
     }
     cp_async_wait_all();
     __syncthreads();
-    // keys jn .. round_up(jn, 8) are zero rows of sY, finite columns of sP; dead row blocks skip the math
+    // keys jn .. round_up(jn, 16) are zero rows of sY, finite columns of sP; dead row blocks skip the math
     const int jn = m0 < live_rows ? min(TKEY, S - j0) : 0;
 #pragma unroll 2
-    for (int kk = 0; kk < jn; kk += 8) {
-      const FragA a = frag_a_rowmajor(sP + (m0 + g) * ldP + j0 + kk + t, ldP);
+    for (int kk = 0; kk < jn; kk += 16) {
+      const FragA a = frag_a_rowmajor(sP + (m0 + g) * ldP + j0 + kk + 2 * t, ldP);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const FragB b = frag_b_kmajor(sY + (kk + t) * LDV + d0 + nt * 8 + g, LDV);
+        const FragB b = frag_b_kmajor(sY + (kk + 2 * t) * LDV + d0 + nt * 8 + g, LDV);
         mma3(out[nt], crs[nt], a, b);
       }
     }
@@ -202,7 +209,7 @@ __device__ __forceinline__ void tile_pv(const float* __restrict__ Y, int ldy, lo
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[nt][c] += crs[nt][c];
+    for (int c = 0; c < 4; ++c) out[nt][c] = fmaf(crs[nt][c], LO_INV, out[nt][c]);
 }
 
 // stores the P.V fragments of tile_pv: rows i0 + m0 + g (+8), columns h*HD + d0 + 8*nt + 2t
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
     const float* __restrict__ dO, int lddo, const float* __restrict__ Q, int ldq, const float* __restrict__ A,
     const float* __restrict__ dA, int ldA, const float* __restrict__ delta, float* __restrict__ dK, int lddk,
     float* __restrict__ dV, int lddv, int H, int T, int S, float scale, Ragged rg, const float* __restrict__ gscale) {
-  constexpr int LDH = HD + 8, LDK = KV_KEYS + 8, NT = HD / 16;   // both are [k][n]-indexed operands: stride = 8 (mod 16)
+  constexpr int LDH = HD + 4, LDK = KV_KEYS + 4, NT = HD / 16;   // both are [k][n]-indexed operands: stride = 4 (mod 16)
   extern __shared__ float smem[];
   float* sdO = smem;
   float* sQ = sdO + KV_ROWS * LDH;
@@ -399,17 +406,17 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
     }
     cp_async_wait_all();
     __syncthreads();
-    const int in = min(KV_ROWS, T - i0);                // rows in .. round_up(in, 8) are zero-filled
+    const int in = min(KV_ROWS, T - i0);                // rows in .. round_up(in, 16) are zero-filled
     if (j0 + m0 < S) {                                  // this warp's 16 keys are live (warp-uniform)
 #pragma unroll 2
-      for (int kk = 0; kk < in; kk += 8) {
-        const FragA aA = frag_a_kmajor(sA + (kk + t) * LDK + m0 + g, LDK);
-        const FragA aS = frag_a_kmajor(sS + (kk + t) * LDK + m0 + g, LDK);
+      for (int kk = 0; kk < in; kk += 16) {
+        const FragA aA = frag_a_kmajor(sA + (kk + 2 * t) * LDK + m0 + g, LDK);
+        const FragA aS = frag_a_kmajor(sS + (kk + 2 * t) * LDK + m0 + g, LDK);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          const FragB bo = frag_b_kmajor(sdO + (kk + t) * LDH + d0 + nt * 8 + g, LDH);
+          const FragB bo = frag_b_kmajor(sdO + (kk + 2 * t) * LDH + d0 + nt * 8 + g, LDH);
           mma3(accV[nt], crsV[nt], aA, bo);
-          const FragB bq = frag_b_kmajor(sQ + (kk + t) * LDH + d0 + nt * 8 + g, LDH);
+          const FragB bq = frag_b_kmajor(sQ + (kk + 2 * t) * LDH + d0 + nt * 8 + g, LDH);
           mma3(accK[nt], crsK[nt], aS, bq);
         }
       }
@@ -423,10 +430,10 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
     float* krow = dK + (krow0 + j) * lddk + h * HD + d0 + 2 * t;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      *reinterpret_cast<float2*>(vrow + nt * 8) =
-          make_float2(accV[nt][2 * half] + crsV[nt][2 * half], accV[nt][2 * half + 1] + crsV[nt][2 * half + 1]);
-      *reinterpret_cast<float2*>(krow + nt * 8) = make_float2((accK[nt][2 * half] + crsK[nt][2 * half]) * scale,
-                                                              (accK[nt][2 * half + 1] + crsK[nt][2 * half + 1]) * scale);
+      *reinterpret_cast<float2*>(vrow + nt * 8) = make_float2(fmaf(crsV[nt][2 * half], LO_INV, accV[nt][2 * half]),
+                                                              fmaf(crsV[nt][2 * half + 1], LO_INV, accV[nt][2 * half + 1]));
+      *reinterpret_cast<float2*>(krow + nt * 8) = make_float2(fmaf(crsK[nt][2 * half], LO_INV, accK[nt][2 * half]) * scale,
+                                                              fmaf(crsK[nt][2 * half + 1], LO_INV, accK[nt][2 * half + 1]) * scale);
     }
   }
 }
@@ -480,7 +487,7 @@ static int launch_bwd(const float* dO, int lddo, const float* Q, int ldq, const 
     MMX_TRY((launch_bwd_q_tq<HD, 32>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, gscale, st)));
   }
   if (dQ == nullptr) return 0;
-  const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 8) + 2 * KV_ROWS * (KV_KEYS + 8));
+  const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 4) + 2 * KV_ROWS * (KV_KEYS + 4));
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   dim3 grid2(cdiv(S, KV_KEYS), H, B);
   attention_bwd_kv_kernel<HD><<<grid2, KV_THREADS, smem2, st>>>(dO, lddo, Q, ldq, A, dA, ldA, delta, dK, lddk, dV, lddv, H,

@@ -35,6 +35,8 @@ int text_embed_packed(const int*, const float*, const float*, float*, int*, int*
 int avg_heads(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int bmm_add(const float*, int, long long, int, const float*, int, long long, const float*, int, long long, float*, int, long long,
             int, int, int, int, int, cudaStream_t);
+bool rule6_chain_ok(int S, int ld, int ld_out, const float* Abar, const float* R_out);
+int rule6_chain(const float* Abar, long long layer_stride, int ld, float* R_out, int ld_out, int B, int S, int L, cudaStream_t st);
 int im2col_patches(const float*, float*, int, int, int, cudaStream_t);
 int vision_tokens_lnpre(const float*, int, const float*, const float*, const float*, const float*, float*, int, int, int, float,
                         cudaStream_t);
@@ -325,6 +327,12 @@ int tower_rules(Tower& T, int B, int start, int* r_idx) {
   const int nl = T.L - start;
   // padded rows (ld) are zero in A and dA, so the plane is treated as dense [S, ld]
   MMX_TRY(avg_heads(T.A + start * plane, T.dA + start * plane, T.Abar + start * bplane, nl * B, T.H, T.S, T.ld, T.ld, T.ld, st));
+  if (rule6_chain_ok(T.S, T.ld, T.ld, T.Abar + start * bplane, T.R[0])) {
+    // the whole chain R = I; R <- R + Abar_l R in one launch, R resident in shared memory (rule_chain.cu)
+    MMX_TRY(rule6_chain(T.Abar + start * bplane, (long long)bplane, T.ld, T.R[0], T.ld, B, T.S, nl, st));
+    *r_idx = 0;
+    return 0;
+  }
   MMX_TRY(set_eye(T.R[0], B, T.S, T.ld, st));
   int cur = 0;
   const long long sp = (long long)T.S * T.ld;

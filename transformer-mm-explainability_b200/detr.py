@@ -144,7 +144,7 @@ class DetrEngine:
             else:
                 cls = torch.as_tensor(index, device=dev).reshape(B).long()
             one_hot = torch.zeros_like(logits.v)
-            one_hot[rows, cls] = 1.0
+            one_hot.view(-1).index_fill_(0, rows * C1 + cls, 1.0)          # one_hot[rows, cls] = 1 without a host scalar (graph-capturable)
             tape.seed(logits, one_hot, B)
             tape.backward()
             if lrp:

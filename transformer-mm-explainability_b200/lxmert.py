@@ -179,7 +179,7 @@ class LxmertEngine:
                 return self.question_answering_score
             idx = logits.v.argmax(-1) if index is None else torch.as_tensor(index, device=dev).reshape(B).long()
             one_hot = torch.zeros_like(logits.v)
-            one_hot[torch.arange(B, device=dev), idx] = 1.0                     # ExplanationGenerator.py:152-160
+            one_hot.scatter_(1, idx.reshape(B, 1), 1.0)                         # ExplanationGenerator.py:152-160 (graph-capturable)
             tape.seed(logits, one_hot, B)
             tape.backward()
             if lrp:

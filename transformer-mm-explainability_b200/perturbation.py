@@ -22,7 +22,8 @@ from ._lib import lib, check, ptr, current_stream, MmxError
 from .lxmert import LxmertEngine
 from .visualbert import VisualBertEngine
 
-PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]          # perturbation.py:42
+PERT_STEPS = [0, 0.25, 0.5, 0.75, 0.8, 0.85, 0.9, 0.95, 1]          # perturbation.py:42; evaluation_loop.py:96 (text test)
+VISUALBERT_IMAGE_STEPS = [0, 0.5, 0.75, 0.95, 0.96, 0.97, 0.98, 0.99, 1]   # evaluation_loop.py:94 (image test of VisualBERT)
 
 
 def topk_select(scores: torch.Tensor, k: Sequence[int]):
@@ -96,12 +97,18 @@ class VisualBertPerturbation:
     Image test: the visual tokens are ranked (:107-120); text test: tokens 1 .. cls_index-1 are ranked and token 0, the
     pooled token ``cls_index`` and the final [SEP] always stay (:133-150).  All steps run as one batch."""
 
-    def __init__(self, model: VisualBertEngine, pert_steps: Sequence[float] = PERT_STEPS):
+    def __init__(self, model: VisualBertEngine, pert_steps: Sequence[float] | None = None):
         if not isinstance(model, VisualBertEngine):
             raise MmxError("model must be a mmx_b200.VisualBertEngine")
         self.model = model
-        self.pert_steps = list(pert_steps)
+        self.pert_steps = None if pert_steps is None else list(pert_steps)      # None: the reference's per-modality lists
         self.scores: torch.Tensor | None = None
+
+    def steps_for(self, modality: str):
+        """evaluation_loop.py:93-96: the image test removes boxes on a finer grid near 100 % than the text test."""
+        if self.pert_steps is not None:
+            return self.pert_steps
+        return list(VISUALBERT_IMAGE_STEPS if modality == "image" else PERT_STEPS)
 
     def _base(self, input, n):
         dev = self.model.device
@@ -114,10 +121,11 @@ class VisualBertPerturbation:
 
     def perturbation_image(self, input, method_cam: torch.Tensor, is_positive_pert: bool = False):
         cam = method_cam.reshape(-1) * (-1 if is_positive_pert else 1)
-        n = len(self.pert_steps)
+        steps = self.steps_for("image")
+        n = len(steps)
         inp, bias, T = self._base(input, n)
         bbox_scores = cam[T:].contiguous()                                           # :107
-        k = [int((1 - step) * bbox_scores.numel()) for step in self.pert_steps]     # :112
+        k = [int((1 - step) * bbox_scores.numel()) for step in steps]               # :112
         keep, _ = topk_select(bbox_scores, k)
         bias[:, T:] = bias[:, T:].masked_fill(keep == 0, float("-inf"))
         inp["key_bias"] = bias
@@ -126,13 +134,14 @@ class VisualBertPerturbation:
 
     def perturbation_text(self, input, method_cam: torch.Tensor, is_positive_pert: bool = False):
         cam = method_cam.reshape(-1) * (-1 if is_positive_pert else 1)
-        n = len(self.pert_steps)
+        steps = self.steps_for("text")
+        n = len(steps)
         inp, bias, T = self._base(input, n)
         dev = self.model.device
         cls_index = T - 2                                                            # :130
         text_scores = cam[1:cls_index].contiguous()                                  # :134
         text_len = text_scores.numel()
-        k = [int((1 - step) * text_len) for step in self.pert_steps]
+        k = [int((1 - step) * text_len) for step in steps]
         keep, pos = topk_select(text_scores, k)
         kk = torch.tensor(k, device=dev)
         ar = torch.arange(n, device=dev)

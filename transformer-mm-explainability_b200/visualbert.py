@@ -125,7 +125,7 @@ class VisualBertEngine:
             if backward:
                 idx = scores.v.argmax(-1) if index is None else torch.as_tensor(index, device=dev).reshape(-1).expand(B).long()
                 one_hot = torch.zeros_like(scores.v)
-                one_hot[torch.arange(B, device=dev), idx] = 1.0
+                one_hot.scatter_(1, idx.reshape(B, 1), 1.0)
                 tape.seed(scores, one_hot, B)
                 tape.backward()
                 if lrp:

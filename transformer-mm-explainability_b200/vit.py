@@ -84,7 +84,7 @@ class ViTEngine:
             self.logits = logits.v
             idx = logits.v.argmax(-1) if index is None else torch.as_tensor(index, device=self.device).reshape(B)
             one_hot = torch.zeros_like(logits.v)
-            one_hot[torch.arange(B, device=self.device), idx.long()] = 1.0      # ipynb:1186-1190
+            one_hot.scatter_(1, idx.long().reshape(B, 1), 1.0)                   # ipynb:1186-1190
             tape.seed(logits, one_hot, B)
             tape.backward()
         return self.logits
