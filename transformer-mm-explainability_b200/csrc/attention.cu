@@ -1,8 +1,27 @@
 // Attention forward that stages A = softmax(QK^T) to HBM, and the attention backward that stages dA = dO V^T
 // (the two tensors the reference captures with forward / backward hooks) and continues to dQ, dK, dV.
-// fp16x3 mma.sync (m16n8k16) products with fp32 softmax; one CTA = one (batch, head, 64-query tile), 8 warps; score rows live in shared memory so any S <= ~1500
-// (DETR 850, ViT-L/14@336 577) is handled without a second pass.  Deterministic (no atomics): dK/dV come from a
-// second kernel that walks the query tiles for one key tile.
+//
+// Numerics: fp32-faithful products from THREE fp16 tensor-core passes (the scheme of gemm_f16x3.cu):
+//   x = hi + lo' / 2048,  hi = fp16(x),  lo' = fp16((x - hi) * 2048);   a.b = hi.hi + (lo'.hi + hi.lo') / 2048
+// with hi.hi in one fp32 accumulator and the two cross products in a second one that is folded in once.  fp16 x fp16
+// products are exact in the fp32 accumulator.  Operand range: |x| <= 65504 and an absolute floor of 3e-11 - activations,
+// probabilities and the (power-of-two normalised, see gscale) gradient stream sit well inside.
+//
+// Structure.  The fp32 operands (Q, K, V, dO) are split ONCE per call into fp16 hi / lo planes by a streaming pre-pass
+// (split_planes_kernel; 8 bytes moved per element, ~1 % of the attention time), so that the attention kernels themselves
+// contain no conversion work: operand tiles arrive in shared memory with cp.async already in MMA precision, fragments are
+// fetched with ldmatrix (one instruction per 16x16 A fragment or per two 16x8 B fragments, transposing on the fly where
+// the product needs the other orientation), and the inner loops are 3 mma.sync.m16n8k16 per fragment pair.  The earlier
+// version split fp32 tiles at every fragment load: each K / V tile was re-split by every warp that touched it and by
+// every query tile of the head (10x at ViT-L/14@336), which made the kernels ALU-bound at long sequences
+// (profiles/launches_l14_r2_before.md: attention = 61 % of the ViT-L/14@336 step).
+// The softmax keeps each score row in registers across max / exp / normalise (one shared-memory read and one write per
+// element), stages A with coalesced 8-byte stores and leaves the probabilities in shared memory as fp16 planes for P.V.
+//
+// One CTA = one (batch, head, TQ-query tile), TQ/8 warps; the score rows of the tile live in shared memory, so any S up
+// to ~700 (TQ = 64) / ~1024 (TQ = 32: DETR at 800x1066 has 850 keys) is handled without a second pass.  tcgen05 / TMEM is
+// the wrong tool for CLIP ViT-B/32 (a head is 50x50x64, far below one 128-row UMMA tile).  Deterministic (no atomics):
+// dK / dV come from a second kernel that walks the query tiles for one key tile.
 #include "mmx_common.cuh"
 #include <math_constants.h>
 #include <cuda_fp16.h>
@@ -16,144 +35,214 @@ struct Ragged {
   const int* lens = nullptr;
 };
 
-// Query rows per CTA: TQ = 64 (four m16 row blocks, 8 warps: one CTA covers a whole CLIP ViT-B/32 head of 50 rows)
-// while the score rows fit in shared memory (S <= ~730), TQ = 32 (4 warps) beyond that (DETR at 800x1066: 850 keys).
-// A CTA has TQ/8 warps; warp w owns row block w % (TQ/16) and half w / (TQ/16) of the keys (scores) or of d (P.V).
 constexpr int TKEY = 64;  // keys per shared-memory tile
 constexpr int KV_THREADS = 256;
-
-// The small matrix products per head (scores, P.V and their backward twins) run on the tensor cores as
-// mma.sync.m16n8k16 with fp16 operands and the same fp32-faithful 3-pass split as the linear GEMMs (gemm_f16x3.cu):
-// x = hi + lo' / 2048 with hi = fp16(x), lo' = fp16((x - hi) * 2048); hi*hi goes into one fp32 accumulator, lo'*hi + hi*lo'
-// into a second one that is folded in once (x 1/2048) at the end.  fp16 x fp16 products are exact in the fp32 accumulator,
-// one instruction covers K = 16 (m16n8k8 TF32: 8) at twice the TF32 rate, so against the 3xTF32 version this halves the
-// MMA count and the fragment loads per unit of K.  Operand range: |x| <= 65504 and an absolute floor of 3e-11 - activations,
-// probabilities and the (power-of-two normalised, see gscale) gradient stream sit well inside.  tcgen05 / TMEM is the wrong
-// tool here: a head is 50x50x64 (or 77x77x64), far below one 128-row UMMA tile.
-//
-// Fragment layout of m16n8k16 (g = lane / 4, t = lane % 4), every register = two consecutive-k fp16 values:
-//   A (16x16, row)  a0 (g, 2t..2t+1)  a1 (g+8, 2t..)  a2 (g, 2t+8..)  a3 (g+8, 2t+8..)
-//   B (16x8, col)   b0 (k = 2t..2t+1, n = g)  b1 (k = 2t+8.., n = g)
-//   C (16x8)        c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
-// Shared memory keeps fp32; the split happens at fragment-load time.  Strides are chosen so that each fragment load is
-// bank-conflict free: operands indexed [row or n = g][k = 2t] are read with 64-bit loads and want a stride = 8 (mod 16)
-// floats; operands indexed [k = 2t][n or row = g] are read with 32-bit loads from rows 2t and 2t+1 and want a stride
-// = 4 (mod 16).
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+constexpr int MAX_PAIRS = 16;   // score-row elements per lane held in registers: 2 * 32 * 16 = 1024 keys (NP = 2: S <= 128)
+
+// (x0, x1) -> packed fp16 pair hi (x0 in the low half: element k sits below element k+1) and the packed pair of the
+// scaled residuals
 __device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x0, x1);            // x0 in the low half: element k sits below element k+1
+  const __half2 h = __floats2half2_rn(x0, x1);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pre-pass: fp32 [rows, cols] (row stride ldx) -> fp16 planes hi / lo [rows, ldp]; columns < scale_cols are multiplied by
+// `mul` first (the reference scales q before the product, auxilary.py:173).  8 columns per thread.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ X, int ldx, long long rows, int cols, float mul,
+                                                           int scale_cols, __half* __restrict__ hi, __half* __restrict__ lo, int ldp) {
+  const int cpr = cols / 8;
+  const long long n = rows * cpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cpr;
+    const int c = (int)(i - r * cpr) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(X + r * ldx + c), b = *reinterpret_cast<const float4*>(X + r * ldx + c + 4);
+    const float m = c < scale_cols ? mul : 1.f;
+    uint4 h, l;
+    split_f16(a.x * m, a.y * m, h.x, l.x);
+    split_f16(a.z * m, a.w * m, h.y, l.y);
+    split_f16(b.x * m, b.y * m, h.z, l.z);
+    split_f16(b.z * m, b.w * m, h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + r * ldp + c) = h;
+    *reinterpret_cast<uint4*>(lo + r * ldp + c) = l;
+  }
+}
+
+static int split_planes(const float* X, int ldx, long long rows, int cols, float mul, int scale_cols, __half* hi, __half* lo,
+                        int ldp, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return 0;
+  const long long n = rows * (cols / 8);
+  long long g = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  split_planes_kernel<<<(int)(g > cap ? cap : g), 256, 0, st>>>(X, ldx, rows, cols, mul, scale_cols, hi, lo, ldp);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MMA / ldmatrix helpers.  Fragment layout of m16n8k16 (g = lane / 4, t = lane % 4), every register = two consecutive-k
+// fp16 values:  A (16x16, row)  a0 (g, 2t..2t+1)  a1 (g+8, 2t..)  a2 (g, 2t+8..)  a3 (g+8, 2t+8..)
+//               B (16x8, col)   b0 (k = 2t..2t+1, n = g)  b1 (k = 2t+8.., n = g)
+//               C (16x8)        c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+// Shared-memory planes are [row][k] halves with a row stride of (cols + 8) halves: the eight 16-byte rows of every 8x8
+// ldmatrix tile then fall into eight different 16-byte bank groups (stride bytes = 16 mod 32).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t* b) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-struct FragA { uint32_t hi[4], lo[4]; };
-struct FragB { uint32_t hi[2], lo[2]; };
-// A fragment of a [row][k] operand (stride ld): p points at (row0 + g, k0 + 2t); `mul` scales the operand before the split
-__device__ __forceinline__ FragA frag_a_rowmajor(const float* p, int ld, float mul = 1.f) {
-  FragA f;
-  const float2 x0 = *reinterpret_cast<const float2*>(p), x1 = *reinterpret_cast<const float2*>(p + 8 * ld);
-  const float2 x2 = *reinterpret_cast<const float2*>(p + 8), x3 = *reinterpret_cast<const float2*>(p + 8 * ld + 8);
-  split_f16(x0.x * mul, x0.y * mul, f.hi[0], f.lo[0]);
-  split_f16(x1.x * mul, x1.y * mul, f.hi[1], f.lo[1]);
-  split_f16(x2.x * mul, x2.y * mul, f.hi[2], f.lo[2]);
-  split_f16(x3.x * mul, x3.y * mul, f.hi[3], f.lo[3]);
-  return f;
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __half* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
-// A fragment of a TRANSPOSED operand stored [k][row] (stride ld): p points at (k0 + 2t, row0 + g)
-__device__ __forceinline__ FragA frag_a_kmajor(const float* p, int ld) {
-  FragA f;
-  split_f16(p[0], p[ld], f.hi[0], f.lo[0]);
-  split_f16(p[8], p[ld + 8], f.hi[1], f.lo[1]);
-  split_f16(p[8 * ld], p[9 * ld], f.hi[2], f.lo[2]);
-  split_f16(p[8 * ld + 8], p[9 * ld + 8], f.hi[3], f.lo[3]);
-  return f;
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __half* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
-// B fragment of an operand stored [n][k] (stride ld): p points at (n0 + g, k0 + 2t)
-__device__ __forceinline__ FragB frag_b_nmajor(const float* p) {
-  FragB f;
-  const float2 x0 = *reinterpret_cast<const float2*>(p), x1 = *reinterpret_cast<const float2*>(p + 8);
-  split_f16(x0.x, x0.y, f.hi[0], f.lo[0]);
-  split_f16(x1.x, x1.y, f.hi[1], f.lo[1]);
-  return f;
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], const __half* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
 }
-// B fragment of an operand stored [k][n] (stride ld): p points at (k0 + 2t, n0 + g)
-__device__ __forceinline__ FragB frag_b_kmajor(const float* p, int ld) {
-  FragB f;
-  split_f16(p[0], p[ld], f.hi[0], f.lo[0]);
-  split_f16(p[8 * ld], p[9 * ld], f.hi[1], f.lo[1]);
-  return f;
+// per-lane row addresses of the 8x8 tiles (lane l supplies row l & 7 of tile l >> 3)
+//   A fragment of a [row][k] plane at (m0, k0):          tiles (m, k), (m+8, k), (m, k+8), (m+8, k+8)
+__device__ __forceinline__ const __half* addr_a(const __half* base, int ld, int m0, int k0, int lane) {
+  return base + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ld + k0 + ((lane >> 4) & 1) * 8;
 }
-__device__ __forceinline__ void mma3(float (&main)[4], float (&cross)[4], const FragA& a, const FragB& b) {
-  mma_f16(cross, a.lo, b.hi);
-  mma_f16(cross, a.hi, b.lo);
-  mma_f16(main, a.hi, b.hi);
+//   two B fragments (n0, n0+8) of a [n][k] plane at k0:  tiles (n, k), (n, k+8), (n+8, k), (n+8, k+8)
+__device__ __forceinline__ const __half* addr_b2(const __half* base, int ld, int n0, int k0, int lane) {
+  return base + (n0 + (lane & 7) + ((lane >> 4) & 1) * 8) * ld + k0 + ((lane >> 3) & 1) * 8;
+}
+//   two B fragments (n0, n0+8) of a [k][n] plane at k0, transposed on load:  tiles (k, n), (k+8, n), (k, n+8), (k+8, n+8)
+__device__ __forceinline__ const __half* addr_bt2(const __half* base, int ld, int k0, int n0, int lane) {
+  return base + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ld + n0 + ((lane >> 4) & 1) * 8;
+}
+//   A fragment of a TRANSPOSED operand stored [k][m], transposed on load:  tiles (k, m), (k, m+8), (k+8, m), (k+8, m+8)
+__device__ __forceinline__ const __half* addr_at(const __half* base, int ld, int k0, int m0, int lane) {
+  return base + (k0 + (lane & 7) + ((lane >> 4) & 1) * 8) * ld + m0 + ((lane >> 3) & 1) * 8;
+}
+// 3-pass product on one fragment pair
+__device__ __forceinline__ void mma3(float (&main)[4], float (&cross)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
+                                     const uint32_t* bhi, const uint32_t* blo) {
+  mma_f16(cross, alo, bhi);
+  mma_f16(cross, ahi, blo);
+  mma_f16(main, ahi, bhi);
 }
 
-__host__ __device__ inline int score_ld(int S) { return round_up(S, 16) + 8; }  // smem stride of a score row: = 8 (mod 16)
+// A score row holds round_up(S,16) + 4 floats: the row stride is then = 16 (mod 32) bytes, so the eight rows of an ldmatrix
+// tile of the P planes fall into eight different 16-byte bank groups.  After the softmax the same bytes hold the fp16 planes
+// of the probabilities: hi at halves [0, S16), lo at halves [S16 + 8, 2 S16 + 8) (16-byte aligned, ends with the row).
+__host__ __device__ inline int score_ld(int S) { return round_up(S, 16) + 4; }
+__host__ __device__ inline int plane_lo_off(int S) { return round_up(S, 16) + 8; }
 
 template <int HD>
 struct AttnSmem {
-  static constexpr int LDX = HD + 8;   // [row / key][d] operands (Q, dO tiles; K, V as the scores' B operand): = 8 (mod 16)
-  static constexpr int LDV = HD + 4;   // [key][d] operand of the P.V product: = 4 (mod 16)
-  static size_t bytes(int S, int TQ) { return sizeof(float) * ((size_t)TQ * score_ld(S) + (size_t)TQ * LDX + (size_t)TKEY * LDX); }
+  static constexpr int LDH = HD + 8;   // halves per row of an operand plane
+  static constexpr int STAGE = 2 * TKEY * LDH;   // halves per K / V tile stage: hi plane then lo plane
+  // score rows (fp32, later the P planes in place) + Q (or dO) planes + NS stages of K / V tile planes
+  static size_t bytes(int S, int TQ, int NS = 2) {
+    return sizeof(float) * (size_t)TQ * score_ld(S) + sizeof(__half) * (2 * (size_t)TQ * LDH + (size_t)NS * STAGE);
+  }
 };
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching src
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// rows r0 .. r0+ROWS-1 of Y (zero beyond `limit`) -> sY with row stride ld, asynchronously (commit + wait by the caller)
+// rows r0 .. r0+ROWS-1 (zero beyond `limit`) of an operand -> the hi / lo planes sHi / sLo (row stride LDH halves).
+// Two sources: ready-made planes (Ylo != nullptr: cp.async, the caller commits / waits), or - for short sequences, where a
+// tile is used by ONE CTA only and a separate split pass would cost more than it saves - the fp32 matrix itself
+// (Ylo == nullptr, Yhi is a float pointer, ldp its row stride in floats): the tile is read with 128-bit loads, multiplied by
+// `mul` and split on the way into shared memory, once per CTA.
 template <int HD, int ROWS>
-__device__ __forceinline__ void load_rows_async(const float* __restrict__ Y, int ldy, long long ybase, int r0, int limit,
-                                                float* sY, int ld) {
-  for (int e = threadIdx.x; e < ROWS * (HD / 4); e += blockDim.x) {
-    const int r = e / (HD / 4), d = (e % (HD / 4)) * 4;
-    const bool ok = r0 + r < limit;
-    cp_async16(sY + r * ld + d, ok ? Y + ybase + (long long)(r0 + r) * ldy + d : Y, ok);
+__device__ __forceinline__ void load_planes_async(const __half* __restrict__ Yhi, const __half* __restrict__ Ylo, int ldp, long long ybase,
+                                                  int r0, int limit, __half* sHi, __half* sLo, float mul = 1.f) {
+  constexpr int LDH = HD + 8;
+  if (Ylo != nullptr) {
+    constexpr int CH = HD / 8;
+    for (int e = threadIdx.x; e < ROWS * CH; e += blockDim.x) {
+      const int r = e / CH, d = (e % CH) * 8;
+      const bool ok = r0 + r < limit;
+      const long long off = ok ? ybase + (long long)(r0 + r) * ldp + d : 0;
+      cp_async16(sHi + r * LDH + d, Yhi + off, ok);
+      cp_async16(sLo + r * LDH + d, Ylo + off, ok);
+    }
+  } else {
+    const float* __restrict__ Yf = reinterpret_cast<const float*>(Yhi);
+    constexpr int CH = HD / 4;
+    for (int e = threadIdx.x; e < ROWS * CH; e += blockDim.x) {
+      const int r = e / CH, d = (e % CH) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < limit) x = *reinterpret_cast<const float4*>(Yf + ybase + (long long)(r0 + r) * ldp + d);
+      uint2 h, l;
+      split_f16(x.x * mul, x.y * mul, h.x, l.x);
+      split_f16(x.z * mul, x.w * mul, h.y, l.y);
+      *reinterpret_cast<uint2*>(sHi + r * LDH + d) = h;
+      *reinterpret_cast<uint2*>(sLo + r * LDH + d) = l;
+    }
   }
 }
 
-// scores[i][j] (i in the 64-row tile, j in [0,S)) = post_scale * sum_d (pre_scale * X[i][d]) * Y[j][d].  The caller has
-// issued (cp.async, committed) the X tile into sX and the FIRST key tile into sY; later key tiles stream through sY.
-// Warp w owns row block w&3 and the 32-key half w>>2 of each key tile.
-template <int HD, int MB>
-__device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy, long long ybase, int S,
-                                            const float* sX, float* sY, float* sP, int ldP, float pre_scale, float post_scale,
-                                            int live_rows) {
-  constexpr int LDX = AttnSmem<HD>::LDX;
+// K / V tiles stream through a ring of NS shared-memory stages (cp.async, one commit group per tile): while tile t is
+// multiplied, tiles t+1 .. t+NS-1 are in flight, so the L2 latency of a tile (~1 us) is overlapped instead of paid once per
+// tile.  Protocol: the caller has issued and committed tiles 0 .. NS-2 (tile 0 may share its group with the X tile); every
+// iteration issues tile t+NS-1 into the stage consumed in iteration t-1, commits (an empty group when there is no tile
+// left), waits until at most NS-1 groups are pending (tile t has landed) and multiplies.
+template <int HD>
+__device__ __forceinline__ void issue_kv_tile(const __half* __restrict__ Yhi, const __half* __restrict__ Ylo, int ldp, long long ybase,
+                                              int tile, int S, __half* sKV, int NS) {
+  if (tile * TKEY < S) {
+    __half* st = sKV + (size_t)(tile % NS) * AttnSmem<HD>::STAGE;
+    load_planes_async<HD, TKEY>(Yhi, Ylo, ldp, ybase, tile * TKEY, S, st, st + TKEY * (HD + 8));
+  }
+  cp_async_commit();
+}
+
+// scores[i][j] (i in the TQ-row tile, j in [0,S)) = post_scale * sum_d X[i][d] * Y[j][d] on pre-split planes.
+// Warp w owns row block w % MB and the 32-key half w / MB of each key tile.
+template <int HD, int MB, int NS>
+__device__ __forceinline__ void tile_scores(const __half* __restrict__ Yhi, const __half* __restrict__ Ylo, int ldp, long long ybase, int S,
+                                            const __half* sXh, const __half* sXl, __half* sKV, float* sP, int ldP,
+                                            float post_scale, int live_rows) {
+  constexpr int LDH = HD + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int m0 = (warp % MB) * 16, kh = (warp / MB) * 32;
-  for (int j0 = 0; j0 < S; j0 += TKEY) {
-    if (j0 > 0) {
-      __syncthreads();
-      load_rows_async<HD, TKEY>(Y, ldy, ybase, j0, S, sY, LDX);
-      cp_async_commit();
-    }
-    cp_async_wait_all();
+  int tile = 0;
+  for (int j0 = 0; j0 < S; j0 += TKEY, ++tile) {
+    issue_kv_tile<HD>(Yhi, Ylo, ldp, ybase, tile + NS - 1, S, sKV, NS);
+    cp_async_wait<NS - 1>();
     __syncthreads();
+    const __half* sYh = sKV + (size_t)(tile % NS) * AttnSmem<HD>::STAGE;
+    const __half* sYl = sYh + TKEY * LDH;
     float acc[4][4] = {}, crs[4][4] = {};
     // live 8-key blocks of this warp's half (may be <= 0); a row block entirely past the sample's rows does no math
     const int ntiles = m0 < live_rows ? (S - j0 - kh + 7) >> 3 : 0;
-#pragma unroll 2
-    for (int k0 = 0; k0 < HD; k0 += 16) {
-      // the reference scales q before the product (auxilary.py:173)
-      const FragA a = frag_a_rowmajor(sX + (m0 + g) * LDX + k0 + 2 * t, LDX, pre_scale);
+    if (ntiles > 0) {
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (nt < ntiles) {
-          const FragB b = frag_b_nmajor(sY + (kh + nt * 8 + g) * LDX + k0 + 2 * t);
-          mma3(acc[nt], crs[nt], a, b);
+      for (int k0 = 0; k0 < HD; k0 += 16) {
+        uint32_t ahi[4], alo[4];
+        ldsm_x4(ahi, addr_a(sXh, LDH, m0, k0, lane));
+        ldsm_x4(alo, addr_a(sXl, LDH, m0, k0, lane));
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {                      // two pairs of 8-key tiles
+          if (2 * np < ntiles) {
+            uint32_t bhi[4], blo[4];
+            ldsm_x4(bhi, addr_b2(sYh, LDH, kh + np * 16, k0, lane));
+            ldsm_x4(blo, addr_b2(sYl, LDH, kh + np * 16, k0, lane));
+            mma3(acc[2 * np], crs[2 * np], ahi, alo, bhi, blo);
+            mma3(acc[2 * np + 1], crs[2 * np + 1], ahi, alo, bhi + 2, blo + 2);
+          }
         }
       }
     }
@@ -168,43 +257,58 @@ __device__ __forceinline__ void tile_scores(const float* __restrict__ Y, int ldy
                                                                fmaf(crs[nt][3], LO_INV, acc[nt][3]) * post_scale);
       }
     }
+    __syncthreads();                                    // the stage is refilled in the next iteration; the scores are visible
   }
-  __syncthreads();
 }
 
-// out[i][d] = sum_j sP[i][j] * Y[j][d].  Warp w owns row block w&3 and the d half w>>2; its HD/16 accumulator
-// fragments hold rows m0+g, m0+g+8 and columns d0 + 8*nt + 2t, +1.  The caller has issued the first Y tile into sY
-// (stride LDV) with cp.async and passed a __syncthreads after the last write of sP.
-template <int HD, int MB>
-__device__ __forceinline__ void tile_pv(const float* __restrict__ Y, int ldy, long long ybase, int S, const float* sP,
-                                        int ldP, float* sY, float (&out)[HD / 16][4], int live_rows) {
-  constexpr int LDV = AttnSmem<HD>::LDV, NT = HD / 16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+// out[i][d] = sum_j P[i][j] * Y[j][d] with P as fp16 planes in the score rows (hi at halves [0, S16), lo from `lo_off` of
+// each row) and Y tiles [key][d] as planes (transposed on load).  Warp w owns row block w % MB and the d half w / MB; its
+// HD/16 accumulator fragments hold rows m0+g, m0+g+8 and columns d0 + 8*nt + 2t, +1.  The caller has issued the first Y
+// tile into sY* with cp.async and passed a __syncthreads after the last write of the P planes.
+template <int HD, int MB, int NS>
+__device__ __forceinline__ void tile_pv(const __half* __restrict__ Yhi, const __half* __restrict__ Ylo, int ldp, long long ybase, int S,
+                                        const __half* sP16, int ldP, int lo_off, __half* sKV, float (&out)[HD / 16][4],
+                                        int live_rows) {
+  constexpr int LDH = HD + 8, NT = HD / 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = (warp % MB) * 16, d0 = (warp / MB) * (HD / 2);
+  const int ldp16 = 2 * ldP;                              // halves per score row
   float crs[NT][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[nt][c] = crs[nt][c] = 0.f;
-  for (int j0 = 0; j0 < S; j0 += TKEY) {
-    if (j0 > 0) {
-      __syncthreads();
-      load_rows_async<HD, TKEY>(Y, ldy, ybase, j0, S, sY, LDV);
-      cp_async_commit();
-    }
-    cp_async_wait_all();
+  int tile = 0;
+  for (int j0 = 0; j0 < S; j0 += TKEY, ++tile) {
+    issue_kv_tile<HD>(Yhi, Ylo, ldp, ybase, tile + NS - 1, S, sKV, NS);
+    cp_async_wait<NS - 1>();
     __syncthreads();
-    // keys jn .. round_up(jn, 16) are zero rows of sY, finite columns of sP; dead row blocks skip the math
+    const __half* sYh = sKV + (size_t)(tile % NS) * AttnSmem<HD>::STAGE;
+    const __half* sYl = sYh + TKEY * LDH;
+    // keys jn .. round_up(jn, 16) are zero rows of sY and finite (zero) entries of the P planes; dead row blocks skip the math
     const int jn = m0 < live_rows ? min(TKEY, S - j0) : 0;
 #pragma unroll 2
     for (int kk = 0; kk < jn; kk += 16) {
-      const FragA a = frag_a_rowmajor(sP + (m0 + g) * ldP + j0 + kk + 2 * t, ldP);
+      uint32_t ahi[4], alo[4];
+      ldsm_x4(ahi, addr_a(sP16, ldp16, m0, j0 + kk, lane));
+      ldsm_x4(alo, addr_a(sP16 + lo_off, ldp16, m0, j0 + kk, lane));
+      if constexpr (NT >= 2) {
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const FragB b = frag_b_kmajor(sY + (kk + 2 * t) * LDV + d0 + nt * 8 + g, LDV);
-        mma3(out[nt], crs[nt], a, b);
+        for (int np = 0; np < NT / 2; ++np) {
+          uint32_t bhi[4], blo[4];
+          ldsm_x4_t(bhi, addr_bt2(sYh, LDH, kk, d0 + np * 16, lane));
+          ldsm_x4_t(blo, addr_bt2(sYl, LDH, kk, d0 + np * 16, lane));
+          mma3(out[2 * np], crs[2 * np], ahi, alo, bhi, blo);
+          mma3(out[2 * np + 1], crs[2 * np + 1], ahi, alo, bhi + 2, blo + 2);
+        }
+      } else {
+        uint32_t bhi[2], blo[2];
+        ldsm_x2_t(bhi, addr_bt2(sYh, LDH, kk, d0, lane & 15));
+        ldsm_x2_t(blo, addr_bt2(sYl, LDH, kk, d0, lane & 15));
+        mma3(out[0], crs[0], ahi, alo, bhi, blo);
       }
     }
+    __syncthreads();                                    // the stage is refilled in the next iteration
   }
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
@@ -229,17 +333,21 @@ __device__ __forceinline__ void store_pv(float* __restrict__ O, int ldo, long lo
   }
 }
 
-template <int HD, int TQ>
-__global__ void __launch_bounds__(TQ * 4) attention_fwd_kernel(
-    const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
-    const float* __restrict__ key_bias, float* __restrict__ A, int ldA, float* __restrict__ O, int ldo, int H, int T, int S,
-    float scale, int flags, Ragged rg) {
-  constexpr int LDH = AttnSmem<HD>::LDX, ATT_THREADS = TQ * 4, ATT_WARPS = TQ / 8, MB = TQ / 16;
-  extern __shared__ float smem[];
-  const int S_pad = score_ld(S);  // shared-memory stride of a score row (from the dense S, also for ragged samples)
-  float* sP = smem;
-  float* sQ = sP + (size_t)TQ * S_pad;
-  float* sKV = sQ + TQ * LDH;
+// One score row in registers: lane l holds the pairs (2l + 64m, 2l + 64m + 1), m < MAX_PAIRS.
+template <int NP> struct RowRegs { float2 v[NP]; };
+
+template <int HD, int TQ, int NP, int NS>
+__global__ void __launch_bounds__(TQ * 4, NP <= 2 ? 3 : 1) attention_fwd_kernel(
+    const __half* __restrict__ Qh, const __half* __restrict__ Ql, const __half* __restrict__ Kh, const __half* __restrict__ Kl,
+    const __half* __restrict__ Vh, const __half* __restrict__ Vl, int ldp, const float* __restrict__ key_bias, float* __restrict__ A,
+    int ldA, float* __restrict__ O, int ldo, int H, int T, int S, float q_mul, float post_scale, int flags, Ragged rg) {
+  constexpr int LDH = AttnSmem<HD>::LDH, ATT_THREADS = TQ * 4, ATT_WARPS = TQ / 8, MB = TQ / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int S_pad = score_ld(S);  // floats per score row (from the dense S, also for ragged samples)
+  float* sP = reinterpret_cast<float*>(smem_raw);
+  __half* sQh = reinterpret_cast<__half*>(sP + (size_t)TQ * S_pad);
+  __half* sQl = sQh + TQ * LDH;
+  __half* sKV = sQl + TQ * LDH;                       // NS stages of K (then V) tile planes
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TQ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Tm = T;                                   // height of the staged plane
@@ -252,29 +360,41 @@ __global__ void __launch_bounds__(TQ * 4) attention_fwd_kernel(
     }
     return;
   }
-  const bool scale_scores = flags & MMX_ATTN_SCALE_SCORES;
-  load_rows_async<HD, TQ>(Q, ldq, qrow0 * ldq + h * HD, i0, T, sQ, LDH);                 // Q tile and the first K tile together
-  load_rows_async<HD, TKEY>(K, ldk, krow0 * ldk + h * HD, 0, S, sKV, LDH);
-  cp_async_commit();
-  tile_scores<HD, MB>(K, ldk, krow0 * ldk + h * HD, S, sQ, sKV, sP, S_pad, scale_scores ? 1.f : scale, scale_scores ? scale : 1.f,
-                  T - i0);
-  load_rows_async<HD, TKEY>(V, ldv, krow0 * ldv + h * HD, 0, S, sKV, AttnSmem<HD>::LDV);     // lands during the softmax
-  cp_async_commit();
-  // softmax per row (warp w owns rows w*8 .. w*8+7), stage A
+  load_planes_async<HD, TQ>(Qh, Ql, ldp, qrow0 * ldp + h * HD, i0, T, sQh, sQl, q_mul);     // Q tile and the first K tiles together
+#pragma unroll
+  for (int pt = 0; pt < NS - 1; ++pt) issue_kv_tile<HD>(Kh, Kl, ldp, krow0 * ldp + h * HD, pt, S, sKV, NS);
+  tile_scores<HD, MB, NS>(Kh, Kl, ldp, krow0 * ldp + h * HD, S, sQh, sQl, sKV, sP, S_pad, post_scale, T - i0);
+#pragma unroll
+  for (int pt = 0; pt < NS - 1; ++pt) issue_kv_tile<HD>(Vh, Vl, ldp, krow0 * ldp + h * HD, pt, S, sKV, NS);   // land during the softmax
+  // softmax per row (warp w owns rows w*8 .. w*8+7): the row is read once into registers, normalised there, staged to A
+  // with 8-byte stores and written back as fp16 hi / lo planes for the P.V product
+  const int npairs = (S + 63) >> 6;                   // pairs per lane
+  const int S16 = round_up(S, 16), lo_off = plane_lo_off(S);
   for (int rr = 0; rr < TQ / ATT_WARPS; ++rr) {
     const int r = warp * (TQ / ATT_WARPS) + rr, i = i0 + r;
-    if (i >= T) {
+    float* row = sP + (size_t)r * S_pad;
+    __half* prow = reinterpret_cast<__half*>(row);
+    if (i >= T) {                                     // dead row of a live tile: zero A row, zero P planes (they multiply V rows)
       if (i < Tm) for (int j = lane; j < ldA; j += 32) A[(((long long)b * H + h) * Tm + i) * ldA + j] = 0.f;
+      for (int j = lane; j < S_pad; j += 32) row[j] = 0.f;
       continue;
     }
-    float* row = sP + (size_t)r * S_pad;
+    RowRegs<NP> x;
     float mx = -CUDART_INF_F;
-    for (int j = lane; j < S; j += 32) {
-      float v = row[j];
-      if (key_bias) v += key_bias[(long long)b * S + j];
-      if ((flags & MMX_ATTN_CAUSAL) && j > i) v = -CUDART_INF_F;
-      row[j] = v;
-      mx = fmaxf(mx, v);
+#pragma unroll
+    for (int m = 0; m < NP; ++m) {
+      if (m < npairs) {
+        const int j = 2 * lane + 64 * m;
+        float2 v = make_float2(-CUDART_INF_F, -CUDART_INF_F);
+        if (j < S) {                                  // j even, S_pad even and > S: the pair is readable; the entry S is masked
+          v = *reinterpret_cast<const float2*>(row + j);
+          if (key_bias) { v.x += key_bias[(long long)b * S + j]; if (j + 1 < S) v.y += key_bias[(long long)b * S + j + 1]; }
+          if (j + 1 >= S) v.y = -CUDART_INF_F;
+          if (flags & MMX_ATTN_CAUSAL) { if (j > i) v.x = -CUDART_INF_F; if (j + 1 > i) v.y = -CUDART_INF_F; }
+        }
+        x.v[m] = v;
+        mx = fmaxf(mx, fmaxf(v.x, v.y));
+      }
     }
     mx = warp_max(mx);
     // A key whose bias is -inf is REMOVED (exp(-inf) = 0 exactly, the same bits a -10000 mask gives); a row whose keys are
@@ -282,33 +402,52 @@ __global__ void __launch_bounds__(TQ * 4) attention_fwd_kernel(
     // perturbation drivers drop every box (lxmert/lxmert/perturbation.py:110-117 at step 1.0).
     const float mref = mx == -CUDART_INF_F ? 0.f : mx;
     float sum = 0.f;
-    for (int j = lane; j < S; j += 32) { const float e = expf(row[j] - mref); row[j] = e; sum += e; }
+#pragma unroll
+    for (int m = 0; m < NP; ++m) {
+      if (m < npairs) {
+        x.v[m].x = expf(x.v[m].x - mref);
+        x.v[m].y = expf(x.v[m].y - mref);
+        sum += x.v[m].x + x.v[m].y;
+      }
+    }
     sum = warp_sum(sum);
     float* arow = A + (((long long)b * H + h) * Tm + i) * ldA;
-    for (int j = lane; j < ldA; j += 32) {
-      float p = 0.f;
-      if (j < S) { p = sum > 0.f ? row[j] / sum : 0.f; row[j] = p; }
-      arow[j] = p;
+    __syncwarp();                                     // every lane has read its part of the fp32 row before the planes overwrite it
+#pragma unroll
+    for (int m = 0; m < NP; ++m) {
+      if (m < npairs) {
+        const int j = 2 * lane + 64 * m;
+        const float2 p = make_float2(sum > 0.f ? x.v[m].x / sum : 0.f, sum > 0.f ? x.v[m].y / sum : 0.f);   // exp(-inf) = 0 beyond S
+        if (j < ldA) *reinterpret_cast<float2*>(arow + j) = p;          // ldA % 4 == 0 and j even: the pair is inside the row
+        if (j < S16) {
+          uint32_t ph, pl;
+          split_f16(p.x, p.y, ph, pl);
+          *reinterpret_cast<uint32_t*>(prow + j) = ph;
+          *reinterpret_cast<uint32_t*>(prow + lo_off + j) = pl;
+        }
+      }
     }
   }
   __syncthreads();
   float out[HD / 16][4];
-  tile_pv<HD, MB>(V, ldv, krow0 * ldv + h * HD, S, sP, S_pad, sKV, out, T - i0);
+  tile_pv<HD, MB, NS>(Vh, Vl, ldp, krow0 * ldp + h * HD, S, reinterpret_cast<const __half*>(sP), S_pad, lo_off, sKV, out, T - i0);
   store_pv<HD, MB>(O, ldo, qrow0, i0, T, h, out, 1.f);
 }
 
 // backward, query side: dA (staged), delta, dQ
-template <int HD, int TQ>
-__global__ void __launch_bounds__(TQ * 4) attention_bwd_q_kernel(
-    const float* __restrict__ dO, int lddo, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
-    const float* __restrict__ A, float* __restrict__ dA, int ldA, float* __restrict__ delta, float* __restrict__ dQ,
-    int lddq, int H, int T, int S, float scale, Ragged rg, const float* __restrict__ gscale) {
-  constexpr int LDH = AttnSmem<HD>::LDX, ATT_THREADS = TQ * 4, ATT_WARPS = TQ / 8, MB = TQ / 16;
-  extern __shared__ float smem[];
+template <int HD, int TQ, int NP, int NS>
+__global__ void __launch_bounds__(TQ * 4, NP <= 2 ? 3 : 1) attention_bwd_q_kernel(
+    const __half* __restrict__ Gh, const __half* __restrict__ Gl, int ldg, const __half* __restrict__ Kh, const __half* __restrict__ Kl,
+    const __half* __restrict__ Vh, const __half* __restrict__ Vl, int ldp, const float* __restrict__ A, float* __restrict__ dA, int ldA,
+    float* __restrict__ delta, float* __restrict__ dQ, int lddq, int H, int T, int S, float scale, Ragged rg,
+    const float* __restrict__ gscale) {
+  constexpr int LDH = AttnSmem<HD>::LDH, ATT_THREADS = TQ * 4, ATT_WARPS = TQ / 8, MB = TQ / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S_pad = score_ld(S);
-  float* sP = smem;
-  float* sX = sP + (size_t)TQ * S_pad;
-  float* sKV = sX + TQ * LDH;
+  float* sP = reinterpret_cast<float*>(smem_raw);
+  __half* sXh = reinterpret_cast<__half*>(sP + (size_t)TQ * S_pad);
+  __half* sXl = sXh + TQ * LDH;
+  __half* sKV = sXl + TQ * LDH;                       // NS stages of V (then K) tile planes
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TQ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Tm = T;
@@ -321,59 +460,94 @@ __global__ void __launch_bounds__(TQ * 4) attention_bwd_q_kernel(
     }
     return;
   }
-  // The gradient stream of sample b may carry a power-of-two factor gscale[b] (fp16x3 GEMM range, see gemm_f16x3.cu);
-  // the staged dA is divided by it (exact), everything that continues the backward (delta, dS, dQ) stays scaled.
+  // The gradient stream of sample b may carry a power-of-two factor gscale[b] (fp16 range, see gemm_f16x3.cu); the staged
+  // dA is divided by it (exact), everything that continues the backward (delta, dS, dQ) stays scaled.
   const float ginv = gscale ? 1.f / gscale[b] : 1.f;
-  load_rows_async<HD, TQ>(dO, lddo, qrow0 * lddo + h * HD, i0, T, sX, LDH);
-  load_rows_async<HD, TKEY>(V, ldv, krow0 * ldv + h * HD, 0, S, sKV, LDH);
-  cp_async_commit();
-  tile_scores<HD, MB>(V, ldv, krow0 * ldv + h * HD, S, sX, sKV, sP, S_pad, 1.f, 1.f, T - i0);
-  if (dQ != nullptr) {                                                                    // lands while dA is staged
-    load_rows_async<HD, TKEY>(K, ldk, krow0 * ldk + h * HD, 0, S, sKV, AttnSmem<HD>::LDV);
-    cp_async_commit();
+  load_planes_async<HD, TQ>(Gh, Gl, ldg, qrow0 * ldg + h * HD, i0, T, sXh, sXl);
+#pragma unroll
+  for (int pt = 0; pt < NS - 1; ++pt) issue_kv_tile<HD>(Vh, Vl, ldp, krow0 * ldp + h * HD, pt, S, sKV, NS);
+  tile_scores<HD, MB, NS>(Vh, Vl, ldp, krow0 * ldp + h * HD, S, sXh, sXl, sKV, sP, S_pad, 1.f, T - i0);
+  if (dQ != nullptr) {                                                                    // land while dA is staged
+#pragma unroll
+    for (int pt = 0; pt < NS - 1; ++pt) issue_kv_tile<HD>(Kh, Kl, ldp, krow0 * ldp + h * HD, pt, S, sKV, NS);
   }
+  const int npairs = (S + 63) >> 6;
+  const int S16 = round_up(S, 16), lo_off = plane_lo_off(S);
   for (int rr = 0; rr < TQ / ATT_WARPS; ++rr) {
     const int r = warp * (TQ / ATT_WARPS) + rr, i = i0 + r;
+    float* row = sP + (size_t)r * S_pad;
+    __half* prow = reinterpret_cast<__half*>(row);
     if (i >= T) {
       if (i < Tm) for (int j = lane; j < ldA; j += 32) dA[(((long long)b * H + h) * Tm + i) * ldA + j] = 0.f;
+      if (dQ != nullptr) for (int j = lane; j < S_pad; j += 32) row[j] = 0.f;
       continue;
     }
-    float* row = sP + (size_t)r * S_pad;
     const long long goff = (((long long)b * H + h) * Tm + i) * ldA;
+    RowRegs<NP> gr, ar;
     float dl = 0.f;
-    for (int j = lane; j < ldA; j += 32) {
-      const float g = (j < S) ? row[j] : 0.f;
-      dA[goff + j] = g * ginv;                // the hooked gradient, unmasked (autograd of bmm(A, v)), in TRUE units
-      if (j < S) dl = fmaf(g, A[goff + j], dl);
+#pragma unroll
+    for (int m = 0; m < NP; ++m) {
+      if (m < npairs) {
+        const int j = 2 * lane + 64 * m;
+        float2 gv = make_float2(0.f, 0.f), av = make_float2(0.f, 0.f);
+        if (j < S) {
+          gv = *reinterpret_cast<const float2*>(row + j);
+          if (j + 1 >= S) gv.y = 0.f;
+        }
+        if (j < ldA) {
+          av = *reinterpret_cast<const float2*>(A + goff + j);           // pad columns of A are zero
+          *reinterpret_cast<float2*>(dA + goff + j) = make_float2(gv.x * ginv, gv.y * ginv);   // the hooked gradient, unmasked, in TRUE units
+        }
+        gr.v[m] = gv; ar.v[m] = av;
+        dl = fmaf(gv.x, av.x, dl);
+        dl = fmaf(gv.y, av.y, dl);
+      }
     }
     dl = warp_sum(dl);
-    if (dQ != nullptr) {
-      for (int j = lane; j < S; j += 32) row[j] = A[goff + j] * (row[j] - dl);   // dS
-    }
     if (lane == 0 && delta) delta[((long long)b * H + h) * Tm + i] = dl;
+    if (dQ != nullptr) {
+      __syncwarp();                                   // the fp32 row has been read by every lane before dS overwrites it
+#pragma unroll
+      for (int m = 0; m < NP; ++m) {
+        if (m < npairs) {
+          const int j = 2 * lane + 64 * m;
+          if (j < S16) {
+            uint32_t sh, sl;                                                      // dS = A (.) (dA - delta); A = 0 beyond S
+            split_f16(ar.v[m].x * (gr.v[m].x - dl), ar.v[m].y * (gr.v[m].y - dl), sh, sl);
+            *reinterpret_cast<uint32_t*>(prow + j) = sh;
+            *reinterpret_cast<uint32_t*>(prow + lo_off + j) = sl;
+          }
+        }
+      }
+    }
   }
   if (dQ == nullptr) return;
   __syncthreads();
   float out[HD / 16][4];
-  tile_pv<HD, MB>(K, ldk, krow0 * ldk + h * HD, S, sP, S_pad, sKV, out, T - i0);
+  tile_pv<HD, MB, NS>(Kh, Kl, ldp, krow0 * ldp + h * HD, S, reinterpret_cast<const __half*>(sP), S_pad, lo_off, sKV, out, T - i0);
   store_pv<HD, MB>(dQ, lddq, qrow0, i0, T, h, out, scale);
 }
 
 // backward, key side: one CTA = 64 keys of one (b,h) (a whole CLIP ViT-B/32 head); walks the query rows in tiles of 64.
 //   dV[j] = sum_i A[i][j] dO[i]      dK[j] = scale * sum_i dS[i][j] Q[i],  dS = A (.) (dA - delta_i)
-// Warp w owns the 16-key block w&3 and the d half w>>2 of both products.
+// Warp w owns the 16-key block w&3 and the d half w>>2 of both products.  A and dS tiles are built from the staged fp32
+// planes (split on the fly: every element is used by one CTA only), dO and Q tiles arrive as pre-split planes.
 constexpr int KV_KEYS = 64, KV_ROWS = 64;
 template <int HD>
 __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
-    const float* __restrict__ dO, int lddo, const float* __restrict__ Q, int ldq, const float* __restrict__ A,
-    const float* __restrict__ dA, int ldA, const float* __restrict__ delta, float* __restrict__ dK, int lddk,
+    const __half* __restrict__ Gh, const __half* __restrict__ Gl, int ldg, const __half* __restrict__ Qh, const __half* __restrict__ Ql,
+    int ldp, const float* __restrict__ A, const float* __restrict__ dA, int ldA, const float* __restrict__ delta, float* __restrict__ dK, int lddk,
     float* __restrict__ dV, int lddv, int H, int T, int S, float scale, Ragged rg, const float* __restrict__ gscale) {
-  constexpr int LDH = HD + 4, LDK = KV_KEYS + 4, NT = HD / 16;   // both are [k][n]-indexed operands: stride = 4 (mod 16)
-  extern __shared__ float smem[];
-  float* sdO = smem;
-  float* sQ = sdO + KV_ROWS * LDH;
-  float* sA = sQ + KV_ROWS * LDH;          // [KV_ROWS][LDK]  A[i][j]
-  float* sS = sA + KV_ROWS * LDK;          // [KV_ROWS][LDK]  dS[i][j]
+  constexpr int LDH = HD + 8, LDK = KV_KEYS + 8, NT = HD / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* sGh = reinterpret_cast<__half*>(smem_raw);
+  __half* sGl = sGh + KV_ROWS * LDH;
+  __half* sQh = sGl + KV_ROWS * LDH;
+  __half* sQl = sQh + KV_ROWS * LDH;
+  __half* sAh = sQl + KV_ROWS * LDH;       // [KV_ROWS][LDK]  A[i][j]
+  __half* sAl = sAh + KV_ROWS * LDK;
+  __half* sSh = sAl + KV_ROWS * LDK;       // [KV_ROWS][LDK]  dS[i][j]
+  __half* sSl = sSh + KV_ROWS * LDK;
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * KV_KEYS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int m0 = (warp & 3) * 16, d0 = (warp >> 2) * (HD / 2);   // this warp's 16 keys and d half
@@ -386,8 +560,8 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
   const long long plane = ((long long)b * H + h) * Tm;
   for (int i0 = 0; i0 < T; i0 += KV_ROWS) {
     __syncthreads();
-    load_rows_async<HD, KV_ROWS>(dO, lddo, qrow0 * lddo + h * HD, i0, T, sdO, LDH);
-    load_rows_async<HD, KV_ROWS>(Q, ldq, qrow0 * ldq + h * HD, i0, T, sQ, LDH);
+    load_planes_async<HD, KV_ROWS>(Gh, Gl, ldg, qrow0 * ldg + h * HD, i0, T, sGh, sGl);
+    load_planes_async<HD, KV_ROWS>(Qh, Ql, ldp, qrow0 * ldp + h * HD, i0, T, sQh, sQl);
     cp_async_commit();
     // A and dS tiles: 4 keys per 128-bit load.  Staged rows are ldA (% 4 == 0) wide and zero beyond this sample's
     // keys, so a float4 that starts below ldA is entirely readable and entirely correct.
@@ -401,8 +575,15 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
         const float dl = delta[plane + i0 + r];
         ds = make_float4(a.x * (ga.x * gs - dl), a.y * (ga.y * gs - dl), a.z * (ga.z * gs - dl), a.w * (ga.w * gs - dl));
       }
-      *reinterpret_cast<float4*>(sA + r * LDK + c) = a;
-      *reinterpret_cast<float4*>(sS + r * LDK + c) = ds;
+      uint2 ah, al, sh, sl;
+      split_f16(a.x, a.y, ah.x, al.x);
+      split_f16(a.z, a.w, ah.y, al.y);
+      split_f16(ds.x, ds.y, sh.x, sl.x);
+      split_f16(ds.z, ds.w, sh.y, sl.y);
+      *reinterpret_cast<uint2*>(sAh + r * LDK + c) = ah;
+      *reinterpret_cast<uint2*>(sAl + r * LDK + c) = al;
+      *reinterpret_cast<uint2*>(sSh + r * LDK + c) = sh;
+      *reinterpret_cast<uint2*>(sSl + r * LDK + c) = sl;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -410,14 +591,32 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
     if (j0 + m0 < S) {                                  // this warp's 16 keys are live (warp-uniform)
 #pragma unroll 2
       for (int kk = 0; kk < in; kk += 16) {
-        const FragA aA = frag_a_kmajor(sA + (kk + 2 * t) * LDK + m0 + g, LDK);
-        const FragA aS = frag_a_kmajor(sS + (kk + 2 * t) * LDK + m0 + g, LDK);
+        uint32_t aAh[4], aAl[4], aSh[4], aSl[4];
+        ldsm_x4_t(aAh, addr_at(sAh, LDK, kk, m0, lane));
+        ldsm_x4_t(aAl, addr_at(sAl, LDK, kk, m0, lane));
+        ldsm_x4_t(aSh, addr_at(sSh, LDK, kk, m0, lane));
+        ldsm_x4_t(aSl, addr_at(sSl, LDK, kk, m0, lane));
+        if constexpr (NT >= 2) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const FragB bo = frag_b_kmajor(sdO + (kk + 2 * t) * LDH + d0 + nt * 8 + g, LDH);
-          mma3(accV[nt], crsV[nt], aA, bo);
-          const FragB bq = frag_b_kmajor(sQ + (kk + 2 * t) * LDH + d0 + nt * 8 + g, LDH);
-          mma3(accK[nt], crsK[nt], aS, bq);
+          for (int np = 0; np < NT / 2; ++np) {
+            uint32_t bh[4], bl[4];
+            ldsm_x4_t(bh, addr_bt2(sGh, LDH, kk, d0 + np * 16, lane));
+            ldsm_x4_t(bl, addr_bt2(sGl, LDH, kk, d0 + np * 16, lane));
+            mma3(accV[2 * np], crsV[2 * np], aAh, aAl, bh, bl);
+            mma3(accV[2 * np + 1], crsV[2 * np + 1], aAh, aAl, bh + 2, bl + 2);
+            ldsm_x4_t(bh, addr_bt2(sQh, LDH, kk, d0 + np * 16, lane));
+            ldsm_x4_t(bl, addr_bt2(sQl, LDH, kk, d0 + np * 16, lane));
+            mma3(accK[2 * np], crsK[2 * np], aSh, aSl, bh, bl);
+            mma3(accK[2 * np + 1], crsK[2 * np + 1], aSh, aSl, bh + 2, bl + 2);
+          }
+        } else {
+          uint32_t bh[2], bl[2];
+          ldsm_x2_t(bh, addr_bt2(sGh, LDH, kk, d0, lane & 15));
+          ldsm_x2_t(bl, addr_bt2(sGl, LDH, kk, d0, lane & 15));
+          mma3(accV[0], crsV[0], aAh, aAl, bh, bl);
+          ldsm_x2_t(bh, addr_bt2(sQh, LDH, kk, d0, lane & 15));
+          ldsm_x2_t(bl, addr_bt2(sQl, LDH, kk, d0, lane & 15));
+          mma3(accK[0], crsK[0], aSh, aSl, bh, bl);
         }
       }
     }
@@ -440,38 +639,141 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
 
 constexpr size_t ATT_SMEM_MAX = 227 * 1024;
 
-template <int HD, int TQ>
-static int launch_fwd_tq(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const float* key_bias,
-                         float* A, int ldA, float* O, int ldo, int B, int H, int T, int S, float scale, int flags,
-                         Ragged rg, cudaStream_t st) {
-  const size_t smem = AttnSmem<HD>::bytes(S, TQ);
-  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<HD, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+// scratch planes of one call (stream-ordered allocation: cached by the pool, capturable in CUDA graphs)
+struct Planes {
+  __half* buf = nullptr;
+  cudaStream_t st = nullptr;
+  int alloc(size_t halves, cudaStream_t s) {
+    st = s;
+    MMX_CHECK_CUDA(cudaMallocAsync((void**)&buf, halves * sizeof(__half), s));
+    return 0;
+  }
+  ~Planes() { if (buf) cudaFreeAsync(buf, st); }
+};
+
+static void keep_pool_cached() {
+  static std::atomic<bool> done[MMX_MAX_DEVICES];
+  const int dev = current_device();
+  if (!done[dev].load(std::memory_order_acquire)) {     // keep stream-ordered scratch cached across synchronisation points
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[dev].store(true, std::memory_order_release);
+  }
+}
+
+// K / V ring depth that fits next to the score rows (2 .. 4)
+template <int HD>
+static int pick_stages(int S, int TQ) {
+  for (int ns = 4; ns > 2; --ns)
+    if (AttnSmem<HD>::bytes(S, TQ, ns) <= ATT_SMEM_MAX) return ns;
+  return 2;
+}
+
+template <int HD, int TQ, int NP, int NS>
+static int launch_fwd_tq(const __half* Qh, const __half* Ql, const __half* Kh, const __half* Kl, const __half* Vh, const __half* Vl,
+                         int ldp, const float* key_bias, float* A, int ldA, float* O, int ldo, int B, int H, int T, int S,
+                         float q_mul, float post_scale, int flags, Ragged rg, cudaStream_t st) {
+  const size_t smem = AttnSmem<HD>::bytes(S, TQ, NS);
+  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<HD, TQ, NP, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, TQ), H, B);
-  attention_fwd_kernel<HD, TQ><<<grid, TQ * 4, smem, st>>>(Q, ldq, K, ldk, V, ldv, key_bias, A, ldA, O, ldo, H, T, S, scale,
-                                                          flags, rg);
+  attention_fwd_kernel<HD, TQ, NP, NS><<<grid, TQ * 4, smem, st>>>(Qh, Ql, Kh, Kl, Vh, Vl, ldp, key_bias, A, ldA, O, ldo, H, T, S, q_mul,
+                                                                  post_scale, flags, rg);
   MMX_LAUNCH_CHECK();
   return 0;
 }
 
+// forward on ready-made planes (row stride ldp halves; Q already carries the pre-product scale)
+template <int HD>
+static int launch_fwd_planes(const __half* Qh, const __half* Ql, const __half* Kh, const __half* Kl, const __half* Vh, const __half* Vl,
+                             int ldp, const float* key_bias, float* A, int ldA, float* O, int ldo, int B, int H, int T, int S,
+                             float q_mul, float post, int flags, Ragged rg, cudaStream_t st) {
+  MMX_REQUIRE(S <= 64 * MAX_PAIRS, "attention: at most 1024 keys per row");
+  const bool tq64 = AttnSmem<HD>::bytes(S, 64) <= ATT_SMEM_MAX;
+  MMX_REQUIRE(tq64 || AttnSmem<HD>::bytes(S, 32) <= ATT_SMEM_MAX, "sequence too long for the single-pass attention kernel");
+#define MMX_FWD(TQ_, NP_, NS_) \
+  return launch_fwd_tq<HD, TQ_, NP_, NS_>(Qh, Ql, Kh, Kl, Vh, Vl, ldp, key_bias, A, ldA, O, ldo, B, H, T, S, q_mul, post, flags, rg, st)
+  if (S <= 128) MMX_FWD(64, 2, 2);
+  if (tq64) {
+    switch (pick_stages<HD>(S, 64)) { case 4: MMX_FWD(64, MAX_PAIRS, 4); case 3: MMX_FWD(64, MAX_PAIRS, 3); default: MMX_FWD(64, MAX_PAIRS, 2); }
+  }
+  switch (pick_stages<HD>(S, 32)) { case 4: MMX_FWD(32, MAX_PAIRS, 4); case 3: MMX_FWD(32, MAX_PAIRS, 3); default: MMX_FWD(32, MAX_PAIRS, 2); }
+#undef MMX_FWD
+}
+
+// rows of the packed operands: B*T query rows, B*S key rows (upper bounds for ragged batches)
 template <int HD>
 static int launch_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const float* key_bias,
                       float* A, int ldA, float* O, int ldo, int B, int H, int T, int S, float scale, int flags,
                       Ragged rg, cudaStream_t st) {
-  if (AttnSmem<HD>::bytes(S, 64) <= ATT_SMEM_MAX)
-    return launch_fwd_tq<HD, 64>(Q, ldq, K, ldk, V, ldv, key_bias, A, ldA, O, ldo, B, H, T, S, scale, flags, rg, st);
-  MMX_REQUIRE(AttnSmem<HD>::bytes(S, 32) <= ATT_SMEM_MAX, "sequence too long for the single-pass attention kernel");
-  return launch_fwd_tq<HD, 32>(Q, ldq, K, ldk, V, ldv, key_bias, A, ldA, O, ldo, B, H, T, S, scale, flags, rg, st);
+  keep_pool_cached();
+  const int D = H * HD;
+  const long long rq = (long long)B * T, rk = (long long)B * S;
+  const bool scale_scores = flags & MMX_ATTN_SCALE_SCORES;
+  if (S <= 128 && ldq == ldk && ldk == ldv) {          // short sequences: the kernels split their (few) tiles themselves
+    auto f = [](const float* p) { return reinterpret_cast<const __half*>(p); };
+    return launch_fwd_planes<HD>(f(Q), nullptr, f(K), nullptr, f(V), nullptr, ldq, key_bias, A, ldA, O, ldo, B, H, T, S,
+                                 scale_scores ? 1.f : scale, scale_scores ? scale : 1.f, flags, rg, st);
+  }
+  Planes pl;
+  if (T == S && K == Q + D && V == Q + 2 * D && ldq == ldk && ldk == ldv) {     // packed q | k | v rows: ONE split pass, planes [rows, 3D]
+    MMX_TRY(pl.alloc((size_t)2 * 3 * D * rq, st));
+    __half* h3 = pl.buf; __half* l3 = h3 + rq * 3 * D;
+    MMX_TRY(split_planes(Q, ldq, rq, 3 * D, scale_scores ? 1.f : scale, D, h3, l3, 3 * D, st));
+    return launch_fwd_planes<HD>(h3, l3, h3 + D, l3 + D, h3 + 2 * D, l3 + 2 * D, 3 * D, key_bias, A, ldA, O, ldo, B, H, T, S, 1.f,
+                                 scale_scores ? scale : 1.f, flags, rg, st);
+  }
+  MMX_TRY(pl.alloc((size_t)2 * D * (rq + 2 * rk), st));
+  __half* Qh = pl.buf; __half* Ql = Qh + rq * D;
+  __half* Kh = Ql + rq * D; __half* Kl = Kh + rk * D;
+  __half* Vh = Kl + rk * D; __half* Vl = Vh + rk * D;
+  MMX_TRY(split_planes(Q, ldq, rq, D, scale_scores ? 1.f : scale, D, Qh, Ql, D, st));   // the reference scales q before the product
+  MMX_TRY(split_planes(K, ldk, rk, D, 1.f, 0, Kh, Kl, D, st));
+  MMX_TRY(split_planes(V, ldv, rk, D, 1.f, 0, Vh, Vl, D, st));
+  return launch_fwd_planes<HD>(Qh, Ql, Kh, Kl, Vh, Vl, D, key_bias, A, ldA, O, ldo, B, H, T, S, 1.f, scale_scores ? scale : 1.f, flags, rg, st);
 }
 
-template <int HD, int TQ>
-static int launch_bwd_q_tq(const float* dO, int lddo, const float* K, int ldk, const float* V, int ldv, const float* A,
-                           float* dA, int ldA, float* delta, float* dQ, int lddq, int B, int H, int T, int S, float scale,
-                           Ragged rg, const float* gscale, cudaStream_t st) {
-  const size_t smem = AttnSmem<HD>::bytes(S, TQ);
-  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<HD, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int HD, int TQ, int NP, int NS>
+static int launch_bwd_q_tq(const __half* Gh, const __half* Gl, int ldg, const __half* Kh, const __half* Kl, const __half* Vh,
+                           const __half* Vl, int ldp, const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, int B, int H, int T, int S,
+                           float scale, Ragged rg, const float* gscale, cudaStream_t st) {
+  const size_t smem = AttnSmem<HD>::bytes(S, TQ, NS);
+  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<HD, TQ, NP, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, TQ), H, B);
-  attention_bwd_q_kernel<HD, TQ><<<grid, TQ * 4, smem, st>>>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, H, T, S,
-                                                            scale, rg, gscale);
+  attention_bwd_q_kernel<HD, TQ, NP, NS><<<grid, TQ * 4, smem, st>>>(Gh, Gl, ldg, Kh, Kl, Vh, Vl, ldp, A, dA, ldA, delta, dQ, lddq, H, T, S, scale,
+                                                            rg, gscale);
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// backward on ready-made planes: G = dO, Q / K / V planes with row strides ldg / ldp; scale_q multiplies dQ, scale_k
+// multiplies dK (1 when the Q planes already carry the pre-product scale)
+template <int HD>
+static int launch_bwd_planes(const __half* Gh, const __half* Gl, int ldg, const __half* Qh, const __half* Ql, const __half* Kh,
+                             const __half* Kl, const __half* Vh, const __half* Vl, int ldp, const float* A, float* dA, int ldA,
+                             float* delta, float* dQ, int lddq, float* dK, int lddk, float* dV, int lddv, int B, int H, int T, int S,
+                             float scale_q, float scale_k, Ragged rg, const float* gscale, cudaStream_t st) {
+  MMX_REQUIRE(S <= 64 * MAX_PAIRS, "attention: at most 1024 keys per row");
+  const bool tq64 = AttnSmem<HD>::bytes(S, 64) <= ATT_SMEM_MAX;
+  MMX_REQUIRE(tq64 || AttnSmem<HD>::bytes(S, 32) <= ATT_SMEM_MAX, "sequence too long for the single-pass attention kernel");
+#define MMX_BWDQ(TQ_, NP_, NS_) \
+  MMX_TRY((launch_bwd_q_tq<HD, TQ_, NP_, NS_>(Gh, Gl, ldg, Kh, Kl, Vh, Vl, ldp, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale_q, rg, gscale, st)))
+  if (S <= 128) {
+    MMX_BWDQ(64, 2, 2);
+  } else if (tq64) {
+    switch (pick_stages<HD>(S, 64)) { case 4: MMX_BWDQ(64, MAX_PAIRS, 4); break; case 3: MMX_BWDQ(64, MAX_PAIRS, 3); break; default: MMX_BWDQ(64, MAX_PAIRS, 2); }
+  } else {
+    switch (pick_stages<HD>(S, 32)) { case 4: MMX_BWDQ(32, MAX_PAIRS, 4); break; case 3: MMX_BWDQ(32, MAX_PAIRS, 3); break; default: MMX_BWDQ(32, MAX_PAIRS, 2); }
+  }
+#undef MMX_BWDQ
+  if (dQ == nullptr) return 0;
+  const size_t smem2 = sizeof(__half) * (4 * KV_ROWS * (HD + 8) + 4 * KV_ROWS * (KV_KEYS + 8));
+  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  dim3 grid2(cdiv(S, KV_KEYS), H, B);
+  attention_bwd_kv_kernel<HD><<<grid2, KV_THREADS, smem2, st>>>(Gh, Gl, ldg, Qh, Ql, ldp, A, dA, ldA, delta, dK, lddk, dV, lddv, H, T, S,
+                                                                scale_k, rg, gscale);
   MMX_LAUNCH_CHECK();
   return 0;
 }
@@ -480,20 +782,38 @@ template <int HD>
 static int launch_bwd(const float* dO, int lddo, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                       const float* A, float* dA, int ldA, float* delta, float* dQ, int lddq, float* dK, int lddk, float* dV,
                       int lddv, int B, int H, int T, int S, float scale, Ragged rg, const float* gscale, cudaStream_t st) {
-  if (AttnSmem<HD>::bytes(S, 64) <= ATT_SMEM_MAX) {
-    MMX_TRY((launch_bwd_q_tq<HD, 64>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, gscale, st)));
-  } else {
-    MMX_REQUIRE(AttnSmem<HD>::bytes(S, 32) <= ATT_SMEM_MAX, "sequence too long for the single-pass attention kernel");
-    MMX_TRY((launch_bwd_q_tq<HD, 32>(dO, lddo, K, ldk, V, ldv, A, dA, ldA, delta, dQ, lddq, B, H, T, S, scale, rg, gscale, st)));
+  keep_pool_cached();
+  const int D = H * HD;
+  const long long rq = (long long)B * T, rk = (long long)B * S;
+  const bool full = dQ != nullptr;                   // the last relevant block stops after dA: only dO and V are needed
+  if (S <= 128 && ldq == ldk && ldk == ldv) {          // short sequences: the kernels split their (few) tiles themselves
+    auto f = [](const float* p) { return reinterpret_cast<const __half*>(p); };
+    return launch_bwd_planes<HD>(f(dO), nullptr, lddo, f(Q), nullptr, f(K), nullptr, f(V), nullptr, ldq, A, dA, ldA, delta, dQ, lddq, dK,
+                                 lddk, dV, lddv, B, H, T, S, scale, scale, rg, gscale, st);
   }
-  if (dQ == nullptr) return 0;
-  const size_t smem2 = sizeof(float) * (2 * KV_ROWS * (HD + 4) + 2 * KV_ROWS * (KV_KEYS + 4));
-  MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  dim3 grid2(cdiv(S, KV_KEYS), H, B);
-  attention_bwd_kv_kernel<HD><<<grid2, KV_THREADS, smem2, st>>>(dO, lddo, Q, ldq, A, dA, ldA, delta, dK, lddk, dV, lddv, H,
-                                                                T, S, scale, rg, gscale);
-  MMX_LAUNCH_CHECK();
-  return 0;
+  Planes pl;
+  if (T == S && K == Q + D && V == Q + 2 * D && ldq == ldk && ldk == ldv) {     // packed q | k | v rows: one split pass for them
+    MMX_TRY(pl.alloc((size_t)2 * 4 * D * rq, st));
+    __half* g = pl.buf; __half* gl = g + rq * D;
+    __half* h3 = gl + rq * D; __half* l3 = h3 + rq * 3 * D;
+    MMX_TRY(split_planes(dO, lddo, rq, D, 1.f, 0, g, gl, D, st));
+    MMX_TRY(split_planes(Q, ldq, rq, 3 * D, 1.f, 0, h3, l3, 3 * D, st));
+    return launch_bwd_planes<HD>(g, gl, D, h3, l3, h3 + D, l3 + D, h3 + 2 * D, l3 + 2 * D, 3 * D, A, dA, ldA, delta, dQ, lddq, dK, lddk,
+                                 dV, lddv, B, H, T, S, scale, scale, rg, gscale, st);
+  }
+  MMX_TRY(pl.alloc((size_t)2 * D * (rq + rk + (full ? rq + rk : 0)), st));
+  __half* Gh = pl.buf; __half* Gl = Gh + rq * D;
+  __half* Vh = Gl + rq * D; __half* Vl = Vh + rk * D;
+  __half* Kh = Vl + rk * D; __half* Kl = Kh + rk * D;
+  __half* Qh = Kl + rk * D; __half* Ql = Qh + rq * D;
+  MMX_TRY(split_planes(dO, lddo, rq, D, 1.f, 0, Gh, Gl, D, st));
+  MMX_TRY(split_planes(V, ldv, rk, D, 1.f, 0, Vh, Vl, D, st));
+  if (full) {
+    MMX_TRY(split_planes(K, ldk, rk, D, 1.f, 0, Kh, Kl, D, st));
+    MMX_TRY(split_planes(Q, ldq, rq, D, 1.f, 0, Qh, Ql, D, st));
+  }
+  return launch_bwd_planes<HD>(Gh, Gl, D, Qh, Ql, Kh, Kl, Vh, Vl, D, A, dA, ldA, delta, dQ, lddq, dK, lddk, dV, lddv, B, H, T, S, scale,
+                               scale, rg, gscale, st);
 }
 
 int attention_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const float* key_bias, float* A,
