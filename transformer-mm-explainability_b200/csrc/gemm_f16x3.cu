@@ -20,11 +20,17 @@
 // previous kernel) crosses L2 once as raw fp32, is split in registers and written to TMEM (tcgen05.st, packed fp16
 // pairs), and the MMAs take it from there (.ts form).
 //
-// Structure (one CTA per SM, persistent over 128 x BN tiles, 3-stage ring of 128 x 64 K-slabs):
-//   warp 0      TMA producer: A raw fp32 (two 32-wide swizzle-128B boxes), W_hi, W_lo fp16 (64-wide boxes)
-//   warps 12-15 splitters: one A row per thread -> hi / lo' fp16 pairs -> 32 + 32 TMEM columns of the stage
-//   warp 1      MMA issuer: 12 tcgen05.mma.kind::f16 per slab (4 k-steps x 3 products), tcgen05.commit
-//   warp 2      TMEM allocator (512 columns: BN main + BN cross accumulators + 3 x 64 columns of A)
+// Structure (one CTA per SM, persistent over 128 x BN tiles, 128 x 64 K-slabs).  The two operands live in SEPARATE rings,
+// because they are held for different times: a raw A slab is dead as soon as the splitters have moved it into TMEM, a W slab
+// only when its MMAs have retired.  With one combined 3-stage ring (round 1) a stage was held for TMA latency + split +
+// MMA, and three stages could not cover that (ncu: tensor pipe 40 % of active cycles, 2170 clk per slab against 870 clk of
+// MMA work, profiles/gemm_f16x3_r2_ncu.md); now A has 2 shared-memory stages (+ 3-4 slabs of split A in TMEM) and W has 4-5.
+//   warp 0      TMA producer A: raw fp32 (two 32-wide swizzle-128B boxes)            ring: full_a / empty_a   (SA = 2)
+//   warp 3      TMA producer W: W_hi, W_lo fp16 (64-wide boxes)                      ring: full_b / empty_b   (SB = 4 or 5)
+//   warps 12-15 splitters: one A row per thread -> hi / lo' fp16 pairs -> TMEM slab  ring: split_done / tmem_free (TS = 3 or 4);
+//               the shared-memory stage is handed back (empty_a) as soon as the row is in registers
+//   warp 1      MMA issuer: 12 tcgen05.mma.kind::f16 per slab (4 k-steps x 3 products); tcgen05.commit -> empty_b, tmem_free
+//   warp 2      TMEM allocator (512 columns: BN main + BN cross accumulators + TS x 64 columns of A)
 //   warps 4-11  epilogue: tcgen05.ld main + cross/2048 -> registers, TMEM released, bias / act' / residual / act
 #include "gemm.cuh"
 #include "tcgen05_ptx.cuh"
@@ -37,7 +43,7 @@ namespace hx {
 
 using namespace ::mmx::tcp;
 
-constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BK = 64, SA = 2;      // SA: shared-memory stages of raw A
 constexpr int SPLIT_WARPS = 4, EPI_WARP0 = 4, EPI_WARPS = 8, SPLIT_WARP0 = 12;
 constexpr int THREADS = (12 + SPLIT_WARPS) * 32;
 constexpr int A_SUB = BM * 32 * 4;             // one 128 x 32 fp32 swizzle-128B box: 16 KB
@@ -47,10 +53,13 @@ constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
 template <int BN> struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 128 && BN <= 160, "UMMA N for M=128: multiple of 16; TMEM budget caps it at 160");
   static constexpr int B_BYTES = BN * BK * 2;           // per plane (hi / lo): 16-20 KB, a multiple of 1024
-  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr uint32_t TM_MAIN = 0, TM_CROSS = (BN + 31) / 32 * 32, TM_A = 2 * TM_CROSS;   // A ring: hi at +64s, lo at +32
-  static_assert(TM_A + 64 * STAGES <= 512, "TMEM has 512 columns");
+  static constexpr int B_STAGE = 2 * B_BYTES;           // hi plane then lo plane
+  static constexpr int SB = (227 * 1024 - 1024 - 512 - SA * A_BYTES) / B_STAGE > 5 ? 5 : (227 * 1024 - 1024 - 512 - SA * A_BYTES) / B_STAGE;
+  static constexpr int SMEM_BYTES = SA * A_BYTES + SB * B_STAGE + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr uint32_t TM_MAIN = 0, TM_CROSS = (BN + 31) / 32 * 32, TM_A = 2 * TM_CROSS;   // A slabs: hi at +64s, lo at +32
+  static constexpr int TS = (512 - (int)TM_A) / 64;     // TMEM slabs of split A
+  static_assert(SB >= 3 && TS >= 2, "ring depths");
+  static_assert(TM_A + 64 * TS <= 512, "TMEM has 512 columns");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory per CTA");
   static constexpr int CW = BN / 2;                     // accumulator columns per epilogue warp
 };
@@ -83,18 +92,23 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap mapBhi,
                                                                 const __grid_constant__ CUtensorMap mapBlo, Params p) {
   using cfg = Cfg<BN>;
-  constexpr int B_BYTES = cfg::B_BYTES, STAGE_BYTES = cfg::STAGE_BYTES, CW = cfg::CW;
+  constexpr int B_BYTES = cfg::B_BYTES, B_STAGE = cfg::B_STAGE, SB = cfg::SB, TS = cfg::TS, CW = cfg::CW;
   constexpr uint32_t TM_MAIN = cfg::TM_MAIN, TM_CROSS = cfg::TM_CROSS, TM_A = cfg::TM_A;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle-128B tiles need 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  // barriers (8 B each): full_tma[S], split_done[S], empty[S], tmem_full, tmem_empty, then the TMEM base slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (3 * STAGES), tempty_bar = bar_base + 8u * (3 * STAGES + 1);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 2));
+  const uint32_t b_base = smem_base + SA * A_BYTES;                      // W ring behind the A ring
+  const uint32_t bar_base = b_base + SB * B_STAGE;
+  // barriers (8 B each): full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], split_done[TS], tmem_free[TS], tmem_full, tmem_empty
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto empty_a = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto full_b = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto empty_b = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto split_bar = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SB + s); };
+  auto tfree_bar = [&](int s) { return bar_base + 8u * (2 * SA + 2 * SB + TS + s); };
+  constexpr int NBAR = 2 * SA + 2 * SB + 2 * TS;
+  const uint32_t tfull_bar = bar_base + 8u * NBAR, tempty_bar = bar_base + 8u * (NBAR + 1);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + SA * A_BYTES + SB * B_STAGE + 8 * (NBAR + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
@@ -103,7 +117,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
   const int nk = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(split_bar(s), SPLIT_WARPS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), SPLIT_WARPS); }
+    for (int s = 0; s < SB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < TS; ++s) { mbar_init(split_bar(s), SPLIT_WARPS); mbar_init(tfree_bar(s), 1); }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -122,40 +138,57 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+    // ------------------------------------------------------------------ TMA producer, A (whole warp loops, one lane issues)
     int stage = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      const int m0 = (t % tiles_m) * BM;
       for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        mbar_wait(empty_a(stage), phase ^ 1);
+        const uint32_t sa = smem_base + stage * A_BYTES;
         if (elect_one()) {
-          mbar_expect_tx(full_bar(stage), A_BYTES + 2 * B_BYTES);
-          tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sa + A_SUB, &mapA, full_bar(stage), kb * BK + 32, m0);
-          tma_load_2d(sa + A_BYTES, &mapBhi, full_bar(stage), kb * BK, n0);
-          tma_load_2d(sa + A_BYTES + B_BYTES, &mapBlo, full_bar(stage), kb * BK, n0);
+          mbar_expect_tx(full_a(stage), A_BYTES);
+          tma_load_2d(sa, &mapA, full_a(stage), kb * BK, m0);
+          tma_load_2d(sa + A_SUB, &mapA, full_a(stage), kb * BK + 32, m0);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == SA) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA producer, W planes
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n0 = (t / tiles_m) * BN;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(empty_b(stage), phase ^ 1);
+        const uint32_t sb = b_base + stage * B_STAGE;
+        if (elect_one()) {
+          mbar_expect_tx(full_b(stage), 2 * B_BYTES);
+          tma_load_2d(sb, &mapBhi, full_b(stage), kb * BK, n0);
+          tma_load_2d(sb + B_BYTES, &mapBlo, full_b(stage), kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == SB) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
     // instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    int stage = 0; uint32_t phase = 0;
+    int sb = 0; uint32_t pb = 0;
+    int ts = 0; uint32_t pt = 0;
     int it = 0;
     const uint32_t d_main = tmem_base + TM_MAIN, d_cross = tmem_base + TM_CROSS;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       mbar_wait(tempty_bar, (uint32_t)(it & 1) ^ 1);               // epilogue drained the accumulators
       tc_fence_after();
       for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(split_bar(stage), phase);                       // A hi/lo in TMEM (the splitters waited for the TMA: W landed too)
+        mbar_wait(split_bar(ts), pt);                             // A hi/lo of this slab are in TMEM
+        mbar_wait(full_b(sb), pb);                                // W planes of this slab landed
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        const uint64_t b_hi = make_desc(sa + A_BYTES), b_lo = make_desc(sa + A_BYTES + B_BYTES);
-        const uint32_t a_hi = tmem_base + TM_A + 64u * stage, a_lo = a_hi + 32u;
+        const uint32_t sbm = b_base + sb * B_STAGE;
+        const uint64_t b_hi = make_desc(sbm), b_lo = make_desc(sbm + B_BYTES);
+        const uint32_t a_hi = tmem_base + TM_A + 64u * ts, a_lo = a_hi + 32u;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {                     // UMMA_K = 16 (f16): +32 B in smem (+2 in the descriptor), +8 TMEM columns
@@ -165,11 +198,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
             umma_f16_ts(d_cross, a_hi + 8u * k, b_lo + adv, idesc, 1u);
             umma_f16_ts(d_main, a_hi + 8u * k, b_hi + adv, idesc, first);
           }
-          umma_commit(empty_bar(stage));                          // frees the stage (smem + TMEM A slab) when these MMAs retire
+          umma_commit(empty_b(sb));                               // W stage and TMEM A slab are free when these MMAs retire
+          umma_commit(tfree_bar(ts));
           if (kb == nk - 1) umma_commit(tfull_bar);               // accumulators complete -> epilogue
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++sb == SB) { sb = 0; pb ^= 1; }
+        if (++ts == TS) { ts = 0; pt ^= 1; }
       }
     }
   } else if (warp >= SPLIT_WARP0) {
@@ -177,12 +212,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
     const int q = warp & 3;                                     // TMEM lane quarter this warp may write
     const int row = q * 32 + lane;                              // tile row handled by this thread
     const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
-    int stage = 0; uint32_t phase = 0;
+    int sa = 0; uint32_t pa = 0;
+    int ts = 0; uint32_t pt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        const uint8_t* a_raw = smem_gen + stage * STAGE_BYTES + row_off;
-        const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * stage;
+        mbar_wait(full_a(sa), pa);
+        mbar_wait(tfree_bar(ts), pt ^ 1);                       // the MMAs that read this TMEM slab last time have retired
+        tc_fence_after();
+        const uint8_t* a_raw = smem_gen + sa * A_BYTES + row_off;
+        const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * ts;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {                             // the two 32-wide boxes of the slab: k = 32j .. 32j+31 -> columns 16j .. 16j+15
           uint32_t hi[16], lo[16];
@@ -192,14 +230,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
             split2(x.x, x.y, hi[2 * c], lo[2 * c]);
             split2(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
           }
+          if (j == 1) {                                           // the raw slab is in registers: hand the smem stage back to the producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_a(sa));
+          }
           tmem_st16v(t_hi + 16u * j, hi);
           tmem_st16v(t_hi + 32u + 16u * j, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(split_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(split_bar(ts));
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+        if (++ts == TS) { ts = 0; pt ^= 1; }
       }
     }
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
