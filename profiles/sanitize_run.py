@@ -67,5 +67,28 @@ q = torch.randn(1, 850, 64, device="cuda"); Aa = torch.empty(1, 2, 850, 852, dev
 import ctypes as C
 check(l.mmx_attention_fwd(ptr(q), 64, ptr(q), 64, ptr(q), 64, None, ptr(Aa), 852, ptr(Oo), 64, 1, 2, 850, 850, 32, C.c_float(0.17), 0,
                           current_stream()))
+# ---- round 2: LRP sweeps (lrp.cu), the rule-6 chain kernel, the plane-based attention (pre-pass + ring, and the backward at a
+# long sequence), CUDA-graph capture of a generator call
+g.generate_ours((src.cuda(), pos.cuda()), tq)                                 # use_lrp=True (reference default)
+g.generate_transformer_att((src.cuda(), pos.cuda()), tq); g.generate_partial_lrp((src.cuda(), pos.cuda()), tq)
+mmx_b200.GeneratorOurs(le).generate_ours((ids.cuda(), feats.cuda(), boxes.cuda()))
+mmx_b200.GeneratorBaselines(le).generate_transformer_attr((ids.cuda(), feats.cuda(), boxes.cuda()))
+vgen.generate_transformer_att(vinp); vgen.generate_partial_lrp(vinp)
+for S_, L_ in ((77, 3), (50, 2), (128, 1), (5, 2)):
+    ld_ = (S_ + 3) // 4 * 4
+    Ab_ = torch.rand(L_, 2, S_, ld_, device="cuda") * 0.01; Ro_ = torch.empty(2, S_, ld_, device="cuda")
+    check(l.mmx_self_chain(ptr(Ab_), 2 * S_ * ld_, ld_, ptr(Ro_), ld_, 2, S_, L_, current_stream()))
+for S_, hd_ in ((197, 64), (300, 32), (850, 16)):                                # pre-pass planes, 2-4 stage K / V ring, 64- and 32-row tiles
+    H_ = 2; D_ = H_ * hd_; ld_ = (S_ + 3) // 4 * 4
+    qkv_ = torch.randn(S_, 3 * D_, device="cuda"); do_ = torch.randn(S_, D_, device="cuda")
+    A_ = torch.empty(1, H_, S_, ld_, device="cuda"); dA_ = torch.empty_like(A_); O_ = torch.empty(S_, D_, device="cuda")
+    dl_ = torch.empty(H_ * S_, device="cuda"); dqkv_ = torch.empty_like(qkv_)
+    check(l.mmx_attention_fwd(ptr(qkv_), 3 * D_, ptr(qkv_[:, D_:]), 3 * D_, ptr(qkv_[:, 2 * D_:]), 3 * D_, None, ptr(A_), ld_, ptr(O_), D_,
+                              1, H_, S_, S_, hd_, C.c_float(hd_ ** -0.5), 0, current_stream()))
+    check(l.mmx_attention_bwd(ptr(do_), D_, ptr(qkv_), 3 * D_, ptr(qkv_[:, D_:]), 3 * D_, ptr(qkv_[:, 2 * D_:]), 3 * D_, ptr(A_), ptr(dA_),
+                              ld_, ptr(dl_), ptr(dqkv_), 3 * D_, ptr(dqkv_[:, D_:]), 3 * D_, ptr(dqkv_[:, 2 * D_:]), 3 * D_, 1, H_, S_, S_, hd_,
+                              C.c_float(hd_ ** -0.5), 0, current_stream()))
+gr = g.capture((src.cuda(), pos.cuda()), tq, use_lrp=False)
+gr(src.cuda(), pos.cuda(), tq.cuda()); gr.check()
 torch.cuda.synchronize()
 print("sanitize_run: all kernels executed")

@@ -239,3 +239,25 @@ def test_shape_and_token_validation(mmx, golden_dir):
         eng.interpret_host(images, neg)
     with pytest.raises(mmx.MmxError):
         eng.interpret_host(images, tokens, out=(torch.empty(1, 2, 2), torch.empty(1, 3)))
+
+
+def test_ragged_rows_leave_no_stale_columns(mmx):
+    """A short prompt after a long one in the same engine slot: every column of the staged A / dA planes beyond the prompt must
+    be rewritten as zero (the planes are dense [B,H,77,80]; a ragged row covers only round_up(len, 64) columns by itself)."""
+    cfg = co.VIT_B32
+    sd = co.init_state_dict(cfg, seed=0)
+    eng = _engine(mmx, cfg, sd, 2)
+    images, _ = co.synthetic_inputs(cfg, 2, seed=3)
+    def toks(n):
+        t = torch.zeros(2, cfg.context_length, dtype=torch.int64)
+        t[:, 0] = cfg.vocab_size - 2
+        t[:, 1:1 + n] = 7
+        t[:, 1 + n] = cfg.vocab_size - 1
+        return t
+    eng.interpret(images.cuda(), toks(74).cuda(), 0, 0)           # 76 live rows: fills columns up to 75
+    rt, _ = eng.interpret(images.cuda(), toks(10).cuda(), 0, 0)   # 12 live rows
+    for what in ("A", "dA"):
+        t = eng.tap(what, tower=1, layer=3)
+        assert float(t[..., 12:, :].abs().max()) == 0.0 and float(t[..., :, 12:].abs().max()) == 0.0, what
+    ot, _ = co.clip_interpret(sd, cfg, images, toks(10), 0, 0)
+    assert text_rel_err(rt, ot) < TOL

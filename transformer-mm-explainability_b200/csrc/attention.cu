@@ -427,6 +427,8 @@ __global__ void __launch_bounds__(TQ * 4, NP <= 2 ? 3 : 1) attention_fwd_kernel(
         }
       }
     }
+    // a ragged sample covers 64 * npairs columns only: the rest of the dense plane row is zero like everything beyond S
+    for (int j = 64 * npairs + lane; j < ldA; j += 32) arow[j] = 0.f;
   }
   __syncthreads();
   float out[HD / 16][4];
@@ -503,6 +505,7 @@ __global__ void __launch_bounds__(TQ * 4, NP <= 2 ? 3 : 1) attention_bwd_q_kerne
         dl = fmaf(gv.y, av.y, dl);
       }
     }
+    for (int j = 64 * npairs + lane; j < ldA; j += 32) dA[goff + j] = 0.f;   // columns a ragged sample's pairs did not reach
     dl = warp_sum(dl);
     if (lane == 0 && delta) delta[((long long)b * H + h) * Tm + i] = dl;
     if (dQ != nullptr) {
