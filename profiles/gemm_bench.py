@@ -22,7 +22,9 @@ def main():
     backends = (1, 2) if "--tiles" in sys.argv else (0, 1, 2)
     if "--only" in sys.argv:            # e.g. --only 3200,2304,768  (tcgen05 backend only; for ncu captures)
         SHAPES = [tuple(int(v) for v in sys.argv[sys.argv.index("--only") + 1].split(","))]
-        backends = (int(sys.argv[sys.argv.index('--backend') + 1]),) if '--backend' in sys.argv else (2,)
+        backends = (2,)
+    if "--backend" in sys.argv:
+        backends = (int(sys.argv[sys.argv.index("--backend") + 1]),)
     for backend in backends:
         if l.mmx_set_gemm_backend(backend) != backend:
             continue
@@ -43,10 +45,21 @@ def main():
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 20
-            e0.record()
-            for _ in range(reps):
-                check(l.mmx_linear_packed(ptr(A), K, ptr(W), K, ptr(pk), ptr(bias), None, 0, ptr(Cm), N, None, 0, M, N, K, current_stream()))
-            e1.record()
+            if "--graph" in sys.argv:       # replay 20 launches from a CUDA graph: no host time (ctypes, tensor-map encodes) in the figure
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    for _ in range(reps):
+                        check(l.mmx_linear_packed(ptr(A), K, ptr(W), K, ptr(pk), ptr(bias), None, 0, ptr(Cm), N, None, 0, M, N, K, current_stream()))
+                gr.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                gr.replay()
+                e1.record()
+            else:
+                e0.record()
+                for _ in range(reps):
+                    check(l.mmx_linear_packed(ptr(A), K, ptr(W), K, ptr(pk), ptr(bias), None, 0, ptr(Cm), N, None, 0, M, N, K, current_stream()))
+                e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             ref = (A[:256].double() @ W.double().t() + bias.double())

@@ -88,9 +88,10 @@ def test_avg_heads_full_size_property(mmx):
 
 
 @pytest.mark.parametrize("B,S,Q", [(1, 50, 0), (4, 77, 0), (2, 20, 36), (2, 36, 20), (1, 100, 625), (1, 197, 0), (3, 1, 1),
-                                   (2, 256, 300), (1, 625, 0), (2, 577, 0)])
+                                   (2, 256, 300), (1, 625, 0), (2, 577, 0), (5, 130, 150), (16, 200, 0)])
 def test_self_update(mmx, B, S, Q):
-    # S >= 128 runs on the tensor cores (tcgen05 3xTF32, "+R" fused in the epilogue); smaller S on the FFMA kernel
+    # S >= 128 runs on the tensor cores (ONE batched tcgen05 3xTF32 launch, tile -> sample, "+R" fused in the epilogue; a
+    # tile's operand boxes run into the next sample's rows when S % 128 != 0); smaller S on the FFMA kernel
     tol = 1e-6 if S < 128 else 1e-5
     gen = torch.Generator().manual_seed(S)
     Ab = torch.rand(B, S, S, generator=gen) * 0.01

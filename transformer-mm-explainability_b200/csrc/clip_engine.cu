@@ -35,6 +35,8 @@ int text_embed_packed(const int*, const float*, const float*, float*, int*, int*
 int avg_heads(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int bmm_add(const float*, int, long long, int, const float*, int, long long, const float*, int, long long, float*, int, long long,
             int, int, int, int, int, cudaStream_t);
+int self_update_tc(const float* Abar, int ld_a, const float* R, float* R_out, int ld, int B, int S, int Q, cudaStream_t st,
+                   bool* taken);
 bool rule6_chain_ok(int S, int ld, int ld_out, const float* Abar, const float* R_out);
 int rule6_chain(const float* Abar, long long layer_stride, int ld, float* R_out, int ld_out, int B, int S, int L, cudaStream_t st);
 int im2col_patches(const float*, float*, int, int, int, cudaStream_t);
@@ -337,8 +339,11 @@ int tower_rules(Tower& T, int B, int start, int* r_idx) {
   int cur = 0;
   const long long sp = (long long)T.S * T.ld;
   for (int l = start; l < T.L; ++l) {
-    MMX_TRY(bmm_add(T.Abar + l * bplane, T.ld, sp, 0, T.R[cur], T.ld, sp, T.R[cur], T.ld, sp, T.R[cur ^ 1], T.ld, sp, B, T.S,
-                    T.ld, T.S, 0, st));
+    bool tc = false;   // S >= 128 (ViT-B/16 197, L/14 257, L/14@336 577): the batched tcgen05 rule GEMM
+    MMX_TRY(self_update_tc(T.Abar + l * bplane, T.ld, T.R[cur], T.R[cur ^ 1], T.ld, B, T.S, T.S, st, &tc));
+    if (!tc)
+      MMX_TRY(bmm_add(T.Abar + l * bplane, T.ld, sp, 0, T.R[cur], T.ld, sp, T.R[cur], T.ld, sp, T.R[cur ^ 1], T.ld, sp, B, T.S,
+                      T.ld, T.S, 0, st));
     cur ^= 1;
   }
   *r_idx = cur;

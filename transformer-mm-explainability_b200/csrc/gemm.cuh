@@ -54,8 +54,11 @@ int gemm_tc_tile_n(int bn);   // forced tcgen05 tile width: bn < 0 reads it, 0 =
 // Tensor-core product for the relevancy updates (no bias / activation): C = residual + A * Bt^T with N possibly not a
 // multiple of 4 as long as every row stride covers round_up(N, 4) columns (the pad columns receive zeros).  Returns
 // taken = false when the shapes / alignment / backend do not qualify.
-int gemm_nt_tc_rule(const float* A, int lda, const float* Bt, int ldb, const float* residual, int ldres, float* C, int ldc,
-                    int M, int N, int K, cudaStream_t st, bool* taken);
+// Batched over `batch` samples in ONE launch: A[b] / Bt[b] start rows_a / rows_b rows after the previous sample (same leading
+// dimension), residual / C advance by stride_res / stride_c elements.
+int gemm_nt_tc_rule(const float* A, int lda, long long rows_a, const float* Bt, int ldb, long long rows_b, const float* residual,
+                    int ldres, long long stride_res, float* C, int ldc, long long stride_c, int M, int N, int K, int batch,
+                    cudaStream_t st, bool* taken);
 int gemm_backend();
 
 }  // namespace mmx

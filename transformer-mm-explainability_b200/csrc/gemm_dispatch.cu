@@ -30,7 +30,10 @@ bool gemm_tc_shape_ok(const float* A, int lda, const float* Bt, int ldb, float* 
 int gemm_nt_tc(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
                const GemmEpilogue& ep, cudaStream_t st);
 
+int gemm_nt_tc_batched(const float* A, int lda, int rows_a, const float* Bt, int ldb, int rows_b, float* C, int ldc, long long stride_c,
+                       long long stride_res, int M, int N, int K, int batch, const GemmEpilogue& ep, cudaStream_t st);
 void gemm_tc_set_trace(long long* buf);
+void gemm_f16x3_set_trace(long long* buf);
 
 int gemm_backend() {
   int b = g_backend.load();
@@ -51,19 +54,20 @@ static int gemm_nt_impl(const float* A, int lda, const BOperand& B, float* C, in
   return gemm_nt_simt(A, lda, B.w, B.ldw, C, ldc, M, N, K, ep, st);
 }
 
-int gemm_nt_tc_rule(const float* A, int lda, const float* Bt, int ldb, const float* residual, int ldres, float* C, int ldc,
-                    int M, int N, int K, cudaStream_t st, bool* taken) {
+int gemm_nt_tc_rule(const float* A, int lda, long long rows_a, const float* Bt, int ldb, long long rows_b, const float* residual,
+                    int ldres, long long stride_res, float* C, int ldc, long long stride_c, int M, int N, int K, int batch,
+                    cudaStream_t st, bool* taken) {
   *taken = false;
   const int Np = round_up(N, 4);
   if (gemm_backend() < 1 || !gemm_tc_available()) return 0;
   if (M < 128 || N < 128 || K < 64 || (lda % 4) || (ldb % 4) || (ldc % 4) || ldc < Np) return 0;
-  if (residual && ((ldres % 4) || ldres < Np || !aligned16(residual))) return 0;
-  if (!aligned16(A) || !aligned16(Bt) || !aligned16(C)) return 0;
+  if (residual && ((ldres % 4) || ldres < Np || !aligned16(residual) || (stride_res % 4))) return 0;
+  if (!aligned16(A) || !aligned16(Bt) || !aligned16(C) || (stride_c % 4)) return 0;
   GemmEpilogue ep;
   ep.residual = residual; ep.ldres = ldres;
   *taken = true;
-  // N is passed rounded up: rows N..Np-1 of Bt do not exist for TMA (zero-filled), the pad columns of C get 0 + residual pad
-  return gemm_nt_tc(A, lda, Bt, ldb, C, ldc, M, Np, K, ep, st);
+  // N is passed rounded up: rows N..Np-1 of Bt[b] hold the transposed pad (zeros), the pad columns of C get 0 + residual pad
+  return gemm_nt_tc_batched(A, lda, (int)rows_a, Bt, ldb, (int)rows_b, C, ldc, stride_c, stride_res, M, Np, K, batch, ep, st);
 }
 
 // Optional per-launch CUDA-event timing of the GEMMs (the dominant kernel) for bench.py's roofline line.
@@ -154,6 +158,7 @@ int mmx_profile_gemm_report(double* total_ms, double* total_flops, int* launches
 
 int mmx_gemm_trace(long long* device_buf) {
   gemm_tc_set_trace(device_buf);
+  gemm_f16x3_set_trace(device_buf);
   return 0;
 }
 int mmx_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {

@@ -33,6 +33,7 @@
 //   warp 2      TMEM allocator (512 columns: BN main + BN cross accumulators + TS x 64 columns of A)
 //   warps 4-11  epilogue: tcgen05.ld main + cross/2048 -> registers, TMEM released, bias / act' / residual / act
 #include "gemm.cuh"
+#include "gemm_epilogue.cuh"
 #include "tcgen05_ptx.cuh"
 #include <cuda_fp16.h>
 #include <cudaTypedefs.h>
@@ -44,18 +45,25 @@ namespace hx {
 using namespace ::mmx::tcp;
 
 constexpr int BM = 128, BK = 64, SA = 2;      // SA: shared-memory stages of raw A
-constexpr int SPLIT_WARPS = 4, EPI_WARP0 = 4, EPI_WARPS = 8, SPLIT_WARP0 = 12;
-constexpr int THREADS = (12 + SPLIT_WARPS) * 32;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, SPLIT_WARP0 = 12;
+// G splitter warps per TMEM lane quarter (4 G in all): each converts 64 / G of a slab's 64 K-columns for its 32 rows
+constexpr int threads_for(int G) { return (12 + 4 * G) * 32; }
 constexpr int A_SUB = BM * 32 * 4;             // one 128 x 32 fp32 swizzle-128B box: 16 KB
 constexpr int A_BYTES = 2 * A_SUB;             // raw A slab 128 x 64 fp32
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+#define HX_TRACE(role, idx, slot)                                                                        \
+  do {                                                                                                   \
+    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 64) p.trace[((role) * 64 + (idx)) * 4 + (slot)] = clock64(); \
+  } while (0)
 
 template <int BN> struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 128 && BN <= 160, "UMMA N for M=128: multiple of 16; TMEM budget caps it at 160");
   static constexpr int B_BYTES = BN * BK * 2;           // per plane (hi / lo): 16-20 KB, a multiple of 1024
   static constexpr int B_STAGE = 2 * B_BYTES;           // hi plane then lo plane
-  static constexpr int SB = (227 * 1024 - 1024 - 512 - SA * A_BYTES) / B_STAGE > 5 ? 5 : (227 * 1024 - 1024 - 512 - SA * A_BYTES) / B_STAGE;
-  static constexpr int SMEM_BYTES = SA * A_BYTES + SB * B_STAGE + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int EPI_STG = EPI_WARPS * EPI_STAGE_FLOATS * 4;      // epilogue staging (gemm_epilogue.cuh): 16 KB
+  static constexpr int SB = (227 * 1024 - 1024 - 512 - EPI_STG - SA * A_BYTES) / B_STAGE > 5 ? 5 : (227 * 1024 - 1024 - 512 - EPI_STG - SA * A_BYTES) / B_STAGE;
+  static constexpr int SMEM_BYTES = SA * A_BYTES + SB * B_STAGE + 1024 /*align*/ + 512 /*barriers*/ + EPI_STG;
   static constexpr uint32_t TM_MAIN = 0, TM_CROSS = (BN + 31) / 32 * 32, TM_A = 2 * TM_CROSS;   // A slabs: hi at +64s, lo at +32
   static constexpr int TS = (512 - (int)TM_A) / 64;     // TMEM slabs of split A
   static_assert(SB >= 3 && TS >= 2, "ring depths");
@@ -68,8 +76,14 @@ struct Params {
   int M, N, K, ldc;
   float* C;
   GemmEpilogue ep;
+  long long* trace = nullptr;   // optional device buffer [4 roles][64 tiles][4]: clock64 timeline of CTA 0 (mmx_gemm_trace; profiling aid)
+  int dbg = 0;     // measurement only (MMX_F16X3_DBG): 2 no TMA (MMAs on whatever is in smem), 4 one accumulator, 8 one MMA per k-step, 16 no stores
 };
 
+__device__ __forceinline__ void tmem_st8v(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st16v(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -87,11 +101,12 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_constant__ CUtensorMap mapA,
+template <int BN, int G, bool ACT>
+__global__ void __launch_bounds__(threads_for(G), 1) gemm_f16x3_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapBhi,
                                                                 const __grid_constant__ CUtensorMap mapBlo, Params p) {
   using cfg = Cfg<BN>;
+  constexpr int SPLIT_WARPS = 4 * G;
   constexpr int B_BYTES = cfg::B_BYTES, B_STAGE = cfg::B_STAGE, SB = cfg::SB, TS = cfg::TS, CW = cfg::CW;
   constexpr uint32_t TM_MAIN = cfg::TM_MAIN, TM_CROSS = cfg::TM_CROSS, TM_A = cfg::TM_A;
   extern __shared__ uint8_t smem_raw[];
@@ -109,6 +124,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
   constexpr int NBAR = 2 * SA + 2 * SB + 2 * TS;
   const uint32_t tfull_bar = bar_base + 8u * NBAR, tempty_bar = bar_base + 8u * (NBAR + 1);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + SA * A_BYTES + SB * B_STAGE + 8 * (NBAR + 2));
+  float* stg_base = reinterpret_cast<float*>(smem_gen + SA * A_BYTES + SB * B_STAGE + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
@@ -140,12 +156,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer, A (whole warp loops, one lane issues)
     int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    int itp = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++itp) {
       const int m0 = (t % tiles_m) * BM;
       for (int kb = 0; kb < nk; ++kb) {
         mbar_wait(empty_a(stage), phase ^ 1);
         const uint32_t sa = smem_base + stage * A_BYTES;
         if (elect_one()) {
+          if (kb == 0) HX_TRACE(0, itp, 0);
+          if (kb == nk - 1) HX_TRACE(0, itp, 1);
           mbar_expect_tx(full_a(stage), A_BYTES);
           tma_load_2d(sa, &mapA, full_a(stage), kb * BK, m0);
           tma_load_2d(sa + A_SUB, &mapA, full_a(stage), kb * BK + 32, m0);
@@ -182,9 +201,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       mbar_wait(tempty_bar, (uint32_t)(it & 1) ^ 1);               // epilogue drained the accumulators
       tc_fence_after();
+      if (lane == 0) HX_TRACE(1, it, 0);
       for (int kb = 0; kb < nk; ++kb) {
         mbar_wait(split_bar(ts), pt);                             // A hi/lo of this slab are in TMEM
         mbar_wait(full_b(sb), pb);                                // W planes of this slab landed
+        if (lane == 0 && kb == 0) HX_TRACE(1, it, 1);
+        if (lane == 0 && kb == nk - 1) HX_TRACE(1, it, 2);
         tc_fence_after();
         const uint32_t sbm = b_base + sb * B_STAGE;
         const uint64_t b_hi = make_desc(sbm), b_lo = make_desc(sbm + B_BYTES);
@@ -210,8 +232,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
   } else if (warp >= SPLIT_WARP0) {
     // ------------------------------------------------------------------ splitter: A slab (smem, raw fp32) -> hi / lo' fp16 -> TMEM
     const int q = warp & 3;                                     // TMEM lane quarter this warp may write
+    const int grp = (warp - SPLIT_WARP0) >> 2;                  // which 64 / G K-columns of the slab
     const int row = q * 32 + lane;                              // tile row handled by this thread
     const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    constexpr int CH = 16 / G;                                  // 16-byte chunks (4 fp32 -> 2 TMEM columns per plane) per warp and slab
+    constexpr int RC = CH < 8 ? CH : 8;                         // chunks per round (one tcgen05.st per plane and round)
     int sa = 0; uint32_t pa = 0;
     int ts = 0; uint32_t pt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -222,20 +247,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
         const uint8_t* a_raw = smem_gen + sa * A_BYTES + row_off;
         const uint32_t t_hi = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + 64u * ts;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {                             // the two 32-wide boxes of the slab: k = 32j .. 32j+31 -> columns 16j .. 16j+15
-          uint32_t hi[16], lo[16];
+        for (int r = 0; r < CH / RC; ++r) {
+          const int cg0 = grp * CH + r * RC;                    // first chunk of the round: box cg0 >> 3 (k = 32 box ..), chunk cg0 & 7 in it
+          uint32_t hi[2 * RC], lo[2 * RC];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {                           // 16-byte chunk c of the row = k 4c .. 4c+3 (swizzled position c ^ (row & 7))
-            const float4 x = *reinterpret_cast<const float4*>(a_raw + j * A_SUB + (((uint32_t)c ^ sw) << 4));
+          for (int c = 0; c < RC; ++c) {                          // chunk c of the box row sits at swizzled position c ^ (row & 7)
+            const uint32_t cb = (uint32_t)((cg0 & 7) + c);
+            const float4 x = *reinterpret_cast<const float4*>(a_raw + (cg0 >> 3) * A_SUB + ((cb ^ sw) << 4));
             split2(x.x, x.y, hi[2 * c], lo[2 * c]);
             split2(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
           }
-          if (j == 1) {                                           // the raw slab is in registers: hand the smem stage back to the producer
+          if (r == CH / RC - 1) {                                 // this warp's share of the raw slab is in registers: hand the stage back
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_a(sa));
           }
-          tmem_st16v(t_hi + 16u * j, hi);
-          tmem_st16v(t_hi + 32u + 16u * j, lo);
+          if constexpr (RC == 8) {
+            tmem_st16v(t_hi + 2u * cg0, hi);
+            tmem_st16v(t_hi + 32u + 2u * cg0, lo);
+          } else {
+            tmem_st8v(t_hi + 2u * cg0, hi);
+            tmem_st8v(t_hi + 32u + 2u * cg0, lo);
+          }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
@@ -253,6 +285,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
       mbar_wait(tfull_bar, (uint32_t)(it & 1));
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 0);
       tc_fence_after();
       // drain main + cross accumulators into registers (one RN fma each), then hand TMEM back before any global traffic
       uint32_t acc[CW];
@@ -278,40 +311,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);                  // next tile's MMAs may start
-      const int m = m0 + q * 32 + lane;
-      if (m < p.M) {
-        float* crow = p.C + (long long)m * p.ldc;
-        const float* prow = p.ep.pre ? p.ep.pre + (long long)m * p.ep.ldpre : nullptr;
-        const float* rrow = p.ep.residual ? p.ep.residual + (long long)m * p.ep.ldres : nullptr;
-        float* arow = p.ep.C_act ? p.ep.C_act + (long long)m * p.ldc : nullptr;
-        const int nbase = n0 + ch * CW;
-#pragma unroll
-        for (int j = 0; j < CW; j += 4) {
-          const int n = nbase + j;
-          if (n >= p.N) break;                                  // N % 4 == 0 is required by the host wrapper
-          float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
-                                 __uint_as_float(acc[j + 3]));
-          if (p.ep.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          if (prow) {
-            const float4 f = *reinterpret_cast<const float4*>(prow + n);
-            v.x *= act_bwd(f.x, p.ep.act); v.y *= act_bwd(f.y, p.ep.act);
-            v.z *= act_bwd(f.z, p.ep.act); v.w *= act_bwd(f.w, p.ep.act);
-          }
-          if (rrow) {
-            const float4 b = *reinterpret_cast<const float4*>(rrow + n);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          *reinterpret_cast<float4*>(crow + n) = v;
-          if (arow) {
-            float4 a = make_float4(act_fwd(v.x, p.ep.act), act_fwd(v.y, p.ep.act), act_fwd(v.z, p.ep.act),
-                                   act_fwd(v.w, p.ep.act));
-            *reinterpret_cast<float4*>(arow + n) = a;
-          }
-        }
-      }
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 1);
+      if (!(p.dbg & 16))
+        epilogue_store_rows<CW, ACT>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C, p.ldc, 0, 0,
+                                p.ep, lane);
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 2);
     }
   }
   // ---------------------------------------------------------------------- teardown
@@ -322,6 +326,390 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f16x3_kernel(const __grid_con
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pre-split form (round 2, the default): A arrives as fp16 hi / lo' planes as well (split ONCE per GEMM by
+// split_a_planes_kernel, or by the kernel that produced A), so the main loop is TMA -> tcgen05.mma(.ss) and nothing else.
+// Why: the in-kernel split above costs 64 F2FP.PACK_AB per thread and K-slab on the XU pipe (16 lanes / clk / SM) and is
+// repeated for every one of the N / BN column tiles that share the A rows (15 x for the QKV product): ncu has the XU pipe
+// 56 % busy and 2170 clk per slab against 870 clk of MMA work (profiles/gemm_f16x3_r2_ncu.md).  Splitting once moves
+// 1 / tiles_n of that work out of the loop; TMEM then holds only accumulators, so BN = 128 gets TWO accumulator sets and
+// its epilogue (a 2000-clk TMEM drain at 64 B / clk) overlaps the next tile's main loop.
+//   warp 0      TMA producer: A_hi, A_lo (128 x 64 fp16 each), W_hi, W_lo (BN x 64)     ring: full / empty (3 stages)
+//   warp 1      MMA issuer: per k-step  cross += A_lo W_hi, cross += A_hi W_lo, main += A_hi W_hi
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue (as above)
+namespace pre {
+constexpr int THREADS_P = 12 * 32;
+constexpr int AP_BYTES = BM * BK * 2;                    // one A plane slab: 16 KB
+template <int BN> struct CfgP {
+  static_assert(BN % 16 == 0 && BN >= 128 && BN <= 256, "UMMA N for M = 128");
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE = 2 * AP_BYTES + 2 * B_BYTES;       // A_hi, A_lo, W_hi, W_lo
+  static constexpr int EPI_STG = EPI_WARPS * EPI_STAGE_FLOATS * 4;
+  static constexpr int ST = (227 * 1024 - 1024 - 512 - EPI_STG) / STAGE > 4 ? 4 : (227 * 1024 - 1024 - 512 - EPI_STG) / STAGE;
+  static constexpr int SMEM_BYTES = ST * STAGE + 1024 + 512 + EPI_STG;
+  static constexpr uint32_t CSTRIDE = (BN + 31) / 32 * 32;
+  static constexpr int ACC = 4 * CSTRIDE <= 512 ? 2 : 1;         // accumulator sets (main + cross each)
+  static constexpr int CW = BN / 2;
+  static_assert(ST >= 2, "ring depth");
+};
+
+template <int BN, bool ACT>
+__global__ void __launch_bounds__(THREADS_P, 1) gemm_f16x3p_kernel(const __grid_constant__ CUtensorMap mapAhi,
+                                                                   const __grid_constant__ CUtensorMap mapAlo,
+                                                                   const __grid_constant__ CUtensorMap mapBhi,
+                                                                   const __grid_constant__ CUtensorMap mapBlo, Params p) {
+  using cfg = CfgP<BN>;
+  constexpr int B_BYTES = cfg::B_BYTES, STAGE = cfg::STAGE, ST = cfg::ST, CW = cfg::CW, ACC = cfg::ACC;
+  constexpr uint32_t CSTRIDE = cfg::CSTRIDE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + ST * STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (ST + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * ST + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * ST + ACC + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + ST * STAGE + 8 * (2 * ST + 2 * ACC));
+  float* stg_base = reinterpret_cast<float*>(smem_gen + ST * STAGE + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0; uint32_t phase = 0;
+    int itp = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++itp) {
+      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      for (int kb = 0; kb < nk; ++kb) {
+        if (p.dbg & 2) break;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_base + stage * STAGE;
+        if (elect_one()) {
+          if (kb == 0) HX_TRACE(0, itp, 0);
+          if (kb == nk - 1) HX_TRACE(0, itp, 1);
+          mbar_expect_tx(full_bar(stage), STAGE);
+          tma_load_2d(sa, &mapAhi, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sa + AP_BYTES, &mapAlo, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sa + 2 * AP_BYTES, &mapBhi, full_bar(stage), kb * BK, n0);
+          tma_load_2d(sa + 2 * AP_BYTES + B_BYTES, &mapBlo, full_bar(stage), kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = it % ACC;
+      mbar_wait(tempty_bar(as), (uint32_t)((it / ACC) & 1) ^ 1);     // the epilogue drained this accumulator set
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + (uint32_t)as * 2u * CSTRIDE, d_cross = d_main + CSTRIDE;
+      const uint32_t d_x = (p.dbg & 4) ? d_main : d_cross;
+      if (lane == 0) HX_TRACE(1, it, 0);
+      for (int kb = 0; kb < nk; ++kb) {
+        if (!(p.dbg & 2)) mbar_wait(full_bar(stage), phase);
+        if (lane == 0 && kb == 0) HX_TRACE(1, it, 1);
+        if (lane == 0 && kb == nk - 1) HX_TRACE(1, it, 2);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * STAGE;
+        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + AP_BYTES);
+        const uint64_t b_hi = make_desc(sa + 2 * AP_BYTES), b_lo = make_desc(sa + 2 * AP_BYTES + B_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {                       // UMMA_K = 16: +32 B inside the swizzled row (+2 in the descriptor)
+            const uint64_t adv = (uint64_t)(2 * k);
+            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+            if (!(p.dbg & 8)) {
+              umma_f16_ss(d_x, a_lo + adv, b_hi + adv, idesc, first);
+              umma_f16_ss(d_x, a_hi + adv, b_lo + adv, idesc, 1u);
+            }
+            umma_f16_ss(d_main, a_hi + adv, b_hi + adv, idesc, (p.dbg & 4) && !(p.dbg & 8) ? 1u : first);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == nk - 1) umma_commit(tfull_bar(as));
+        }
+        __syncwarp();
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
+    const int q = warp & 3;
+    const int ch = (warp - EPI_WARP0) >> 2;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      const int as = it % ACC;
+      mbar_wait(tfull_bar(as), (uint32_t)((it / ACC) & 1));
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 0);
+      tc_fence_after();
+      uint32_t acc[CW];
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 2u * CSTRIDE + (uint32_t)(ch * CW);
+#pragma unroll
+      for (int c = 0; c + 16 <= CW; c += 16) {
+        uint32_t x[16];
+        tmem_ld16_nowait(trow + c, acc + c);
+        tmem_ld16_nowait(trow + CSTRIDE + c, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c + j] = __float_as_uint(fmaf(__uint_as_float(x[j]), LO_INV, __uint_as_float(acc[c + j])));
+      }
+      if constexpr (CW % 16 == 8) {
+        constexpr int c = CW - 8;
+        uint32_t x[8];
+        tmem_ld8_nowait(trow + c, acc + c);
+        tmem_ld8_nowait(trow + CSTRIDE + c, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c + j] = __float_as_uint(fmaf(__uint_as_float(x[j]), LO_INV, __uint_as_float(acc[c + j])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 1);
+      if (!(p.dbg & 16))
+        epilogue_store_rows<CW, ACT>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C, p.ldc, 0, 0,
+                                p.ep, lane);
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair form (cta_group::2): one 256 x BN output tile per PAIR of SMs.  Why: the single-CTA kernels above are bound by
+// L2 -> SM operand delivery, not by the tensor pipe - a 128 x 160 tile pulls (128 + 160) x 64 x 4 B = 72 KB per K-slab
+// and the chip-wide L2 throughput cap (~6300 B / clk, B300_MICROARCH "LTS throughput cap") gives each of 148 SMs ~43 B / clk:
+// 1700 clk per slab against 870 clk of MMA work, whatever the ring depth, the number of splitter warps or the operand
+// format (all three were measured: profiles/gemm_bench_r2.log).  In a pair each CTA loads its own 128 A rows and only HALF of
+// the W rows (the MMA reads both halves through the cluster), so a 256 x 256 tile costs 64 KB per CTA and slab for 1.6 x
+// the MACs of the 128 x 160 tile: 1.8 x fewer L2 bytes per MAC.  TMEM then holds 256 main + 256 cross columns, which is
+// why A must come from shared memory (pre-split planes), not from TMEM.
+//   both CTAs   warp 0: TMA producer (own A planes, own half of the W planes; completion bytes land on the LEADER's
+//               full barrier);  warps 4 ..: epilogue of the CTA's own 128 rows (arrive on the leader's tmem_empty)
+//   leader      warp 1: MMA issuer (M = 256 across the pair); tcgen05.commit multicast -> empty / tmem_full of both CTAs
+namespace pair2 {
+template <int BN> struct CfgQ {
+  static_assert(BN % 32 == 0 && BN >= 128 && BN <= 256, "UMMA N for M = 256: multiple of 16; each CTA holds BN / 2 rows of W");
+  static constexpr int BNH = BN / 2;
+  static constexpr int B_BYTES = BNH * BK * 2;                   // one W plane slab of this CTA
+  static constexpr int STAGE = 2 * AP_BYTES + 2 * B_BYTES;
+  static constexpr uint32_t CSTRIDE = BN;
+  static constexpr int ACC = 4 * BN <= 512 ? 2 : 1;
+  static constexpr int EG = BN > 160 ? 4 : 2;                    // epilogue column groups (x 4 lane quarters = epilogue warps)
+  static constexpr int CW = BN / EG;
+  static constexpr int EPI = 4 * EG;
+  static constexpr int EPI_STG = EPI * EPI_STAGE_FLOATS * 4;
+  static constexpr int ST = (227 * 1024 - 1024 - 512 - EPI_STG) / STAGE > 6 ? 6 : (227 * 1024 - 1024 - 512 - EPI_STG) / STAGE;
+  static constexpr int SMEM_BYTES = ST * STAGE + 1024 + 512 + EPI_STG;
+  static constexpr int THREADS = (4 + EPI) * 32;
+  static_assert(ST >= 3 && CW % 16 == 0, "ring depth / epilogue chunking");
+};
+
+template <int BN, bool ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CfgQ<BN>::THREADS, 1)
+gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                       const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, Params p) {
+  using cfg = CfgQ<BN>;
+  constexpr int B_BYTES = cfg::B_BYTES, STAGE = cfg::STAGE, ST = cfg::ST, CW = cfg::CW, ACC = cfg::ACC, EPI = cfg::EPI, BNH = cfg::BNH;
+  constexpr uint32_t CSTRIDE = cfg::CSTRIDE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + ST * STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };               // used on the leader only
+  auto empty_bar = [&](int s) { return bar_base + 8u * (ST + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * ST + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * ST + ACC + a); };   // used on the leader only
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + ST * STAGE + 8 * (2 * ST + 2 * ACC));
+  float* stg_base = reinterpret_cast<float*>(smem_gen + ST * STAGE + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
+  }
+  cluster_sync();                                                // both CTAs' barriers exist before any remote arrive
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0; uint32_t phase = 0;
+    int itp = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++itp) {
+      const int m0 = (t % tiles_m) * 2 * BM + (int)rank * BM, n0 = (t / tiles_m) * BN + (int)rank * BNH;
+      for (int kb = 0; kb < nk; ++kb) {
+        if (p.dbg & 2) break;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_base + stage * STAGE;
+        if (elect_one()) {
+          if (kb == 0) HX_TRACE(0, itp, 0);
+          if (kb == nk - 1) HX_TRACE(0, itp, 1);
+          const uint32_t fb = mapa(full_bar(stage), 0);            // the leader's barrier collects the bytes of both CTAs
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE);
+          tma_load_2d_pair(sa, &mapAhi, fb, kb * BK, m0);
+          tma_load_2d_pair(sa + AP_BYTES, &mapAlo, fb, kb * BK, m0);
+          tma_load_2d_pair(sa + 2 * AP_BYTES, &mapBhi, fb, kb * BK, n0);
+          tma_load_2d_pair(sa + 2 * AP_BYTES + B_BYTES, &mapBlo, fb, kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 across the pair
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        const int as = it % ACC;
+        mbar_wait(tempty_bar(as), (uint32_t)((it / ACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + (uint32_t)as * 2u * CSTRIDE, d_cross = d_main + CSTRIDE;
+        const uint32_t d_x = (p.dbg & 4) ? d_main : d_cross;
+        if (lane == 0) HX_TRACE(1, it, 0);
+        for (int kb = 0; kb < nk; ++kb) {
+          if (!(p.dbg & 2)) mbar_wait(full_bar(stage), phase);
+          if (lane == 0 && kb == 0) HX_TRACE(1, it, 1);
+          if (lane == 0 && kb == nk - 1) HX_TRACE(1, it, 2);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE;
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + AP_BYTES);
+          const uint64_t b_hi = make_desc(sa + 2 * AP_BYTES), b_lo = make_desc(sa + 2 * AP_BYTES + B_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(2 * k);
+              const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+              if (!(p.dbg & 8)) {
+                umma_f16_ss_pair(d_x, a_lo + adv, b_hi + adv, idesc, first);
+                umma_f16_ss_pair(d_x, a_hi + adv, b_lo + adv, idesc, 1u);
+              }
+              umma_f16_ss_pair(d_main, a_hi + adv, b_hi + adv, idesc, (p.dbg & 4) && !(p.dbg & 8) ? 1u : first);
+            }
+            umma_commit_pair(empty_bar(stage));                   // both CTAs' stage is free when these MMAs retire
+            if (kb == nk - 1) umma_commit_pair(tfull_bar(as));
+          }
+          __syncwarp();
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI) {
+    // ------------------------------------------------------------------ epilogue: this CTA's 128 rows (lane quarter x column group)
+    const int q = warp & 3;
+    const int ch = (warp - EPI_WARP0) >> 2;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int m0 = (t % tiles_m) * 2 * BM + (int)rank * BM, n0 = (t / tiles_m) * BN;
+      const int as = it % ACC;
+      mbar_wait(tfull_bar(as), (uint32_t)((it / ACC) & 1));
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 0);
+      tc_fence_after();
+      uint32_t acc[CW];
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 2u * CSTRIDE + (uint32_t)(ch * CW);
+#pragma unroll
+      for (int c = 0; c < CW; c += 16) {
+        uint32_t x[16];
+        tmem_ld16_nowait(trow + c, acc + c);
+        tmem_ld16_nowait(trow + CSTRIDE + c, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c + j] = __float_as_uint(fmaf(__uint_as_float(x[j]), LO_INV, __uint_as_float(acc[c + j])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 1);
+      if (!(p.dbg & 16))
+        epilogue_store_rows<CW, ACT>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C, p.ldc, 0, 0,
+                                p.ep, lane);
+      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 2);
+    }
+  }
+  tc_fence_before();
+  cluster_sync();                                                // the peer may read this CTA's smem / signal its barriers until here
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+}  // namespace pair2
+
+// fp32 A [M, K] (row stride lda, lda % 4 == 0) -> hi / lo' fp16 planes [M, ldp]; 4 elements per thread.  Columns K .. ldp-1
+// are never read (the tensor maps declare K columns, TMA zero-fills beyond).
+__global__ void __launch_bounds__(256) split_a_planes_kernel(const float* __restrict__ A, int lda, __half* __restrict__ hi,
+                                                             __half* __restrict__ lo, int ldp, int M, int K) {
+  const int kc = (K + 3) / 4;
+  const long long total = (long long)M * kc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / kc), k = (int)(i % kc) * 4;
+    const float* src = A + (long long)m * lda + k;
+    float4 x;
+    if (k + 4 <= K) x = *reinterpret_cast<const float4*>(src);
+    else { x.x = src[0]; x.y = k + 1 < K ? src[1] : 0.f; x.z = k + 2 < K ? src[2] : 0.f; x.w = 0.f; }
+    uint2 h, l;
+    split2(x.x, x.y, h.x, l.x);
+    split2(x.z, x.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(hi + (long long)m * ldp + k) = h;       // ldp % 8 == 0 and k % 4 == 0: 8-byte aligned, inside the row
+    *reinterpret_cast<uint2*>(lo + (long long)m * ldp + k) = l;
+  }
+}
+}  // namespace pre
 
 // fp32 [N,K] (row stride ldw) -> hi / lo' fp16 planes [N, ldp], pad columns K .. ldp-1 zero
 __global__ void __launch_bounds__(256) pack_f16x3_kernel(const float* __restrict__ W, int ldw, __half* __restrict__ hi,
@@ -338,6 +726,7 @@ __global__ void __launch_bounds__(256) pack_f16x3_kernel(const float* __restrict
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static long long* g_trace = nullptr;
 
 static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, int rows, int K, int ld, int box_k,
                     int box_rows) {
@@ -381,23 +770,152 @@ static int pick_bn(int M, int N) {
   return best;
 }
 
-template <int BN>
-static int launch_bn(const float* A, int lda, const BOperand& B, int M, int N, int K, const Params& p, cudaStream_t st) {
+template <int BN, int G>
+static int launch_bn_g(const float* A, int lda, const BOperand& B, int M, int N, int K, const Params& p, cudaStream_t st) {
   using cfg = Cfg<BN>;
   CUtensorMap mapA, mapBhi, mapBlo;
   MMX_TRY(make_map(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, 32, BM));
   MMX_TRY(make_map(&mapBhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.hi, N, K, B.ldp, BK, BN));
   MMX_TRY(make_map(&mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.lo, N, K, B.ldp, BK, BN));
   // per device: the attribute belongs to the (function, device) pair
-  MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_f16x3_kernel<BN><<<grid, THREADS, cfg::SMEM_BYTES, st>>>(mapA, mapBhi, mapBlo, p);
+  if (p.ep.pre || p.ep.C_act) {
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel<BN, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    gemm_f16x3_kernel<BN, G, true><<<grid, threads_for(G), cfg::SMEM_BYTES, st>>>(mapA, mapBhi, mapBlo, p);
+  } else {
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel<BN, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    gemm_f16x3_kernel<BN, G, false><<<grid, threads_for(G), cfg::SMEM_BYTES, st>>>(mapA, mapBhi, mapBlo, p);
+  }
   MMX_LAUNCH_CHECK();
   return 0;
 }
 
+template <int BN>
+static int launch_bn(const float* A, int lda, const BOperand& B, int M, int N, int K, const Params& p, cudaStream_t st) {
+  return launch_bn_g<BN, 1>(A, lda, B, M, N, K, p, st);   // G = 2 / 4 were measured: no gain (the split is not the limiter)
+}
+
+// 0: in-kernel split (single CTA; default); 1: pre-split planes, single CTA; 2: pre-split planes, CTA pair
+static int f16x3_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MMX_F16X3_MODE"); v = e ? atoi(e) : 0; if (v < 0 || v > 2) v = 0; }
+  return v;
+}
+static int f16x3_dbg() {      // measurement only.  1: fixed scratch, split skipped (results are garbage)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MMX_F16X3_DBG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+template <int BN>
+static int launch_pre(const __half* Ahi, const __half* Alo, int ldpa, const BOperand& B, int M, int N, int K, const Params& p,
+                      cudaStream_t st) {
+  using cfg = pre::CfgP<BN>;
+  CUtensorMap mapAhi, mapAlo, mapBhi, mapBlo;
+  MMX_TRY(make_map(&mapAhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Ahi, M, K, ldpa, BK, BM));
+  MMX_TRY(make_map(&mapAlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Alo, M, K, ldpa, BK, BM));
+  MMX_TRY(make_map(&mapBhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.hi, N, K, B.ldp, BK, BN));
+  MMX_TRY(make_map(&mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.lo, N, K, B.ldp, BK, BN));
+  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  if (p.ep.pre || p.ep.C_act) {
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(pre::gemm_f16x3p_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    pre::gemm_f16x3p_kernel<BN, true><<<grid, pre::THREADS_P, cfg::SMEM_BYTES, st>>>(mapAhi, mapAlo, mapBhi, mapBlo, p);
+  } else {
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(pre::gemm_f16x3p_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    pre::gemm_f16x3p_kernel<BN, false><<<grid, pre::THREADS_P, cfg::SMEM_BYTES, st>>>(mapAhi, mapAlo, mapBhi, mapBlo, p);
+  }
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+static int launch_pair(const __half* Ahi, const __half* Alo, int ldpa, const BOperand& B, int M, int N, int K, const Params& p,
+                       cudaStream_t st) {
+  using cfg = pre::pair2::CfgQ<BN>;
+  CUtensorMap mapAhi, mapAlo, mapBhi, mapBlo;
+  MMX_TRY(make_map(&mapAhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Ahi, M, K, ldpa, BK, BM));
+  MMX_TRY(make_map(&mapAlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Alo, M, K, ldpa, BK, BM));
+  MMX_TRY(make_map(&mapBhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.hi, N, K, B.ldp, BK, cfg::BNH));
+  MMX_TRY(make_map(&mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.lo, N, K, B.ldp, BK, cfg::BNH));
+  const int tiles = cdiv(M, 2 * BM) * cdiv(N, BN);
+  const int max_pairs = sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  if (p.ep.pre || p.ep.C_act) {      // __cluster_dims__(2,1,1)
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(pre::pair2::gemm_f16x3_pair_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    pre::pair2::gemm_f16x3_pair_kernel<BN, true><<<2 * pairs, cfg::THREADS, cfg::SMEM_BYTES, st>>>(mapAhi, mapAlo, mapBhi, mapBlo, p);
+  } else {
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(pre::pair2::gemm_f16x3_pair_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    pre::pair2::gemm_f16x3_pair_kernel<BN, false><<<2 * pairs, cfg::THREADS, cfg::SMEM_BYTES, st>>>(mapAhi, mapAlo, mapBhi, mapBlo, p);
+  }
+  MMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// Tile width of the pair kernel: estimated clocks = waves x (K-slabs x max(MMA, L2 delivery) + exposed TMEM drain).
+static int pick_bn_pair(int M, int N, int K) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MMX_PAIR_BN"); forced = e ? atoi(e) : 0; }
+  if (forced == 128 || forced == 160 || forced == 192 || forced == 256) return forced;
+  const int pairs = sm_count() / 2, tiles_m = cdiv(M, 2 * BM), nk = cdiv(K, BK);
+  int best = 128;
+  long long best_cost = 1ll << 60;
+  for (int bn : {128, 160, 192, 256}) {
+    const long long tiles = (long long)tiles_m * cdiv(N, bn);
+    const long long waves = (tiles + pairs - 1) / pairs;
+    const long long mma = 6ll * bn;                               // 12 instructions x 256 * bn / 512 clk
+    const long long l2 = (32768 + 128ll * bn) / 43;               // this CTA's bytes per slab at the chip-wide L2 cap per SM
+    const long long slab = mma > l2 ? mma : l2;
+    const long long drain = 4 * bn <= 512 ? 0 : 16ll * bn;        // one accumulator set: the TMEM drain (64 B / clk) is exposed
+    const long long cost = waves * (nk * slab + drain);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+// split A once (stream-ordered scratch, same bytes as the fp32 original), then the TMA -> MMA kernel
+static int gemm_presplit(const float* A, int lda, const BOperand& B, int M, int N, int K, const Params& p, cudaStream_t st, bool pair) {
+  const int ldpa = round_up(K, 8);
+  __half* planes = nullptr;
+  const int dbg = f16x3_dbg();
+  static __half* dbg_planes = nullptr;
+  if (dbg) {
+    if (!dbg_planes) { MMX_CHECK_CUDA(cudaMalloc((void**)&dbg_planes, (size_t)256 << 20)); MMX_CHECK_CUDA(cudaMemset(dbg_planes, 0, (size_t)256 << 20)); }
+    planes = dbg_planes;
+  } else {
+    keep_stream_scratch_cached();
+    MMX_CHECK_CUDA(cudaMallocAsync((void**)&planes, (size_t)2 * M * ldpa * sizeof(__half), st));
+  }
+  __half *Ahi = planes, *Alo = planes + (size_t)M * ldpa;
+  const long long total = (long long)M * ((K + 3) / 4);
+  const int grid = (int)((total + 255) / 256 < (long long)sm_count() * 8 ? (total + 255) / 256 : (long long)sm_count() * 8);
+  if (!dbg) {
+    pre::split_a_planes_kernel<<<grid, 256, 0, st>>>(A, lda, Ahi, Alo, ldpa, M, K);
+    MMX_LAUNCH_CHECK();
+  }
+  int rc = 0;
+  if (pair) {
+    switch (pick_bn_pair(M, N, K)) {
+      case 160: rc = launch_pair<160>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+      case 192: rc = launch_pair<192>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+      case 256: rc = launch_pair<256>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+      default: rc = launch_pair<128>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+    }
+  } else {
+    switch (pick_bn(M, N)) {
+      case 144: rc = launch_pre<144>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+      case 160: rc = launch_pre<160>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+      default: rc = launch_pre<128>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+    }
+  }
+  if (!dbg) cudaFreeAsync(planes, st);
+  return rc;
+}
+
 }  // namespace hx
+
+void gemm_f16x3_set_trace(long long* buf) { hx::g_trace = buf; }
 
 int pack_f16x3_ld(int K) { return round_up(K, 8); }
 size_t pack_f16x3_bytes(int N, int K) { return (size_t)2 * N * pack_f16x3_ld(K) * sizeof(uint16_t); }
@@ -442,6 +960,9 @@ int gemm_nt_f16x3(const float* A, int lda, const BOperand& B, float* C, int ldc,
   if (M == 0 || N == 0) return 0;
   MMX_TRY(hx::ensure_encode());
   hx::Params p{M, N, K, ldc, C, ep};
+  p.dbg = hx::f16x3_dbg();
+  p.trace = hx::g_trace;
+  if (hx::f16x3_mode() >= 1) return hx::gemm_presplit(A, lda, B, M, N, K, p, st, hx::f16x3_mode() == 2);
   switch (hx::pick_bn(M, N)) {
     case 144: return hx::launch_bn<144>(A, lda, B, M, N, K, p, st);
     case 160: return hx::launch_bn<160>(A, lda, B, M, N, K, p, st);

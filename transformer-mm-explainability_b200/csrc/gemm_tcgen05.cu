@@ -83,6 +83,11 @@ struct Params {
   int dbg;   // timing experiments only (results invalid): 1 = no MMAs, 2 = no splitter work, 4 = no TMA, 8 = no epilogue stores
   float* C;
   GemmEpilogue ep;
+  // batched form (the relevancy updates: one launch for all samples): tile t belongs to sample t / (tiles_m * tiles_n); the
+  // operand maps cover the samples stacked along their row dimension (rows_a / rows_b rows per sample), C and the residual
+  // advance by stride_c / stride_res elements per sample.  batch = 1: the plain GEMM.
+  int batch = 1, rows_a = 0, rows_b = 0;
+  long long stride_c = 0, stride_res = 0;
 };
 
 template <int BN, int STAGES>
@@ -105,7 +110,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_per = tiles_m * tiles_n;
+  const int num_tiles = tiles_per * p.batch;
   const int nk = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
@@ -137,7 +143,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     int stage = 0; uint32_t phase = 0;
     int pslab = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      const int bi = t / tiles_per, tr = t - bi * tiles_per;
+      const int m0 = (tr % tiles_m) * BM, n0 = (tr / tiles_m) * BN;
+      const int ra = bi * p.rows_a + m0, rb = bi * p.rows_b + n0;   // rows in the stacked operand maps
       for (int kb = 0; kb < nk; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         MMX_TRACE(0, pslab, 0);
@@ -146,8 +154,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
           if (p.dbg & 4) { mbar_arrive(full_bar(stage)); }
           else {
             mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
-            tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m0);
-            tma_load_2d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0);
+            tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, ra);
+            tma_load_2d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, rb);
           }
         }
         __syncwarp();
@@ -269,7 +277,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     const int ch = (warp - EPI_WARP0) >> 2;                     // column half: CW of the BN accumulator columns
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      const int bi = t / tiles_per, tr = t - bi * tiles_per;
+      const int m0 = (tr % tiles_m) * BM, n0 = (tr / tiles_m) * BN;
       mbar_wait(tfull_bar, (uint32_t)(it & 1));
       if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 0);
       tc_fence_after();
@@ -300,9 +309,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 1);
       const int m = m0 + q * 32 + lane;
       if (m < p.M && !(p.dbg & 8)) {
-        float* crow = p.C + (long long)m * p.ldc;
+        float* crow = p.C + bi * p.stride_c + (long long)m * p.ldc;
         const float* prow = p.ep.pre ? p.ep.pre + (long long)m * p.ep.ldpre : nullptr;
-        const float* rrow = p.ep.residual ? p.ep.residual + (long long)m * p.ep.ldres : nullptr;
+        const float* rrow = p.ep.residual ? p.ep.residual + bi * p.stride_res + (long long)m * p.ep.ldres : nullptr;
         float* arow = p.ep.C_act ? p.ep.C_act + (long long)m * p.ldc : nullptr;
         const int nbase = n0 + ch * CW;
 #pragma unroll
@@ -392,8 +401,8 @@ template <int BN, int STAGES>
 static int launch_bn(const float* A, int lda, const float* Bt, int ldb, int M, int N, int K, const Params& p, cudaStream_t st) {
   using cfg = Cfg<BN, STAGES>;
   CUtensorMap mapA, mapB;
-  MMX_TRY(make_map(&mapA, A, M, K, lda, BM));
-  MMX_TRY(make_map(&mapB, Bt, N, K, ldb, BN));
+  MMX_TRY(make_map(&mapA, A, p.batch > 1 ? (p.batch - 1) * p.rows_a + M : M, K, lda, BM));
+  MMX_TRY(make_map(&mapB, Bt, p.batch > 1 ? (p.batch - 1) * p.rows_b + N : N, K, ldb, BN));
   // per device: the attribute belongs to the (function, device) pair
   static std::atomic<bool> attr_set[MMX_MAX_DEVICES];
   const int dev = current_device();
@@ -402,7 +411,7 @@ static int launch_bn(const float* A, int lda, const float* Bt, int ldb, int M, i
                                         cfg::SMEM_BYTES));
     attr_set[dev].store(true, std::memory_order_release);
   }
-  const int tiles = cdiv(M, BM) * cdiv(N, BN);
+  const int tiles = cdiv(M, BM) * cdiv(N, BN) * p.batch;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tf32x3_kernel<BN, STAGES><<<grid, THREADS, cfg::SMEM_BYTES, st>>>(mapA, mapB, p);
   MMX_LAUNCH_CHECK();
@@ -410,11 +419,13 @@ static int launch_bn(const float* A, int lda, const float* Bt, int ldb, int M, i
 }
 
 static int launch(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K,
-                  const GemmEpilogue& ep, cudaStream_t st) {
+                  const GemmEpilogue& ep, cudaStream_t st, int batch = 1, int rows_a = 0, int rows_b = 0, long long stride_c = 0,
+                  long long stride_res = 0) {
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("MMX_TC_DBG"); dbg = e ? atoi(e) : 0; }
   Params p{M, N, K, ldc, g_trace, dbg, C, ep};
-  switch (pick_bn(M, N, ep.m_dev != nullptr)) {
+  p.batch = batch; p.rows_a = rows_a; p.rows_b = rows_b; p.stride_c = stride_c; p.stride_res = stride_res;
+  switch (pick_bn(M * batch, N, ep.m_dev != nullptr)) {
     case 144: return launch_bn<144, 3>(A, lda, Bt, ldb, M, N, K, p, st);
     case 160: return launch_bn<160, 3>(A, lda, Bt, ldb, M, N, K, p, st);
     default: return launch_bn<128, 4>(A, lda, Bt, ldb, M, N, K, p, st);
@@ -474,6 +485,16 @@ int gemm_nt_tc(const float* A, int lda, const float* Bt, int ldb, float* C, int 
                const GemmEpilogue& ep, cudaStream_t st) {
   if (M == 0 || N == 0) return 0;
   return tc::launch(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st);
+}
+
+// `batch` independent products in ONE launch: C[b] = A[b] Bt[b]^T (+ residual[b]); A[b] starts rows_a rows after A[b-1] (same
+// lda), Bt[b] rows_b rows after Bt[b-1]; a tile's operand boxes may run into the next sample's rows - those rows / columns
+// of the product are never stored.
+int gemm_nt_tc_batched(const float* A, int lda, int rows_a, const float* Bt, int ldb, int rows_b, float* C, int ldc, long long stride_c,
+                       long long stride_res, int M, int N, int K, int batch, const GemmEpilogue& ep, cudaStream_t st) {
+  if (M == 0 || N == 0 || batch == 0) return 0;
+  MMX_REQUIRE(ep.m_dev == nullptr && ep.pre == nullptr && ep.C_act == nullptr && ep.bias == nullptr, "batched GEMM: residual epilogue only");
+  return tc::launch(A, lda, Bt, ldb, C, ldc, M, N, K, ep, st, batch, rows_a, rows_b, stride_c, stride_res);
 }
 
 }  // namespace mmx

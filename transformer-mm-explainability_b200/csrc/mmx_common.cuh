@@ -23,6 +23,21 @@ inline int current_device() {
   return dev;
 }
 
+// Stream-ordered scratch (cudaMallocAsync) comes from the device's default pool; with the default release threshold (0) the
+// pool hands its memory back to the driver at every synchronisation point and the next step pays for real allocations.
+// Called once per device by every path that takes such scratch.
+inline void keep_stream_scratch_cached() {
+  static std::atomic<bool> pool_set[MMX_MAX_DEVICES];
+  const int dev = current_device();
+  if (pool_set[dev].load(std::memory_order_acquire)) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  pool_set[dev].store(true, std::memory_order_release);
+}
+
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 #define MMX_CHECK_CUDA(expr)                                                                     \

@@ -272,37 +272,25 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restr
 }
 
 // Rules 6/7 on the tensor cores:  C[b] = R[b] + Abar[b] * R[b]   for S >= 128 (DETR 625-850, ViT-B/16 197, ViT-L 577).
-// Per sample: transpose R into a K-major scratch, then one tcgen05 3xTF32 GEMM with the "+R" fused as the residual
-// epilogue.  Small S (CLIP 50/77, LXMERT 20/36) stays on the FFMA kernel: a 128x128 tensor tile would be mostly padding.
-static int self_update_tc(const float* Abar, int ld_a, const float* R, float* R_out, int ld, int B, int S, int Q,
-                          cudaStream_t st, bool* taken) {
+// One transpose of every sample's R into a K-major scratch, then ONE batched tcgen05 3xTF32 GEMM launch (tile -> sample,
+// row block, column block) with the "+R" fused as the residual epilogue.  Small S (CLIP 50/77, LXMERT 20/36) stays on the FFMA kernel: a 128x128 tensor tile would be mostly padding.
+int self_update_tc(const float* Abar, int ld_a, const float* R, float* R_out, int ld, int B, int S, int Q, cudaStream_t st,
+                   bool* taken) {
   *taken = false;
   if (gemm_backend() < 1 || S < 128 || Q < 128 || (ld_a % 4) || (ld % 4) || ld < round_up(Q, 4) || !aligned16(Abar) ||
       !aligned16(R) || !aligned16(R_out))
     return 0;
-  static std::atomic<bool> pool_set[MMX_MAX_DEVICES];
-  const int dev = current_device();
-  if (!pool_set[dev].load(std::memory_order_acquire)) {   // keep stream-ordered scratch cached across synchronisation points
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    pool_set[dev].store(true, std::memory_order_release);
-  }
+  keep_stream_scratch_cached();
   const int Kp = round_up(S, 4), Np = round_up(Q, 4);
   float* Rt = nullptr;
   MMX_CHECK_CUDA(cudaMallocAsync((void**)&Rt, (size_t)B * Np * Kp * sizeof(float), st));
   dim3 grid(cdiv(Np, 32), cdiv(Kp, 32), B);
   transpose_pad_kernel<<<grid, 256, 0, st>>>(R, ld, (long long)S * ld, Rt, S, Q, Kp, Np);
   count_launch();
-  int rc = 0;
-  for (int b = 0; b < B && rc == 0; ++b) {
-    bool ok = false;
-    rc = gemm_nt_tc_rule(Abar + (size_t)b * S * ld_a, ld_a, Rt + (size_t)b * Np * Kp, Kp, R + (size_t)b * S * ld, ld,
-                         R_out + (size_t)b * S * ld, ld, S, Q, S, st, &ok);
-    if (rc == 0 && !ok) { rc = 3; set_error("tensor-core rule GEMM rejected a shape it was offered"); }
-  }
+  // ONE launch for all samples: tile -> (sample, row block, column block); Abar[b] is S rows after Abar[b-1], Rt[b] Np rows
+  bool ok = false;
+  int rc = gemm_nt_tc_rule(Abar, ld_a, S, Rt, Kp, Np, R, ld, (long long)S * ld, R_out, ld, (long long)S * ld, S, Q, S, B, st, &ok);
+  if (rc == 0 && !ok) { rc = 3; set_error("tensor-core rule GEMM rejected a shape it was offered"); }
   cudaFreeAsync(Rt, st);
   *taken = rc == 0;
   return rc;
