@@ -50,8 +50,10 @@ int mmx_set_gemm_tile_n(int bn);
  * (2*M*N*K per launch) and the launch count of the window.  Used by bench.py for the roofline line. */
 int mmx_profile_gemm(int enable);
 int mmx_profile_gemm_report(double* total_ms, double* total_flops, int* launches);
-/* Profiling aid: while set, every tcgen05 GEMM launch writes CTA 0's clock64 timeline into device_buf
- * ([4 roles][256 events][4] int64: TMA producer, MMA issuer, splitter, epilogue); NULL switches it off. */
+/* Profiling aid: while set, every tcgen05 GEMM launch writes CTA 0's clock64 timeline into device_buf (4112 int64:
+ * the tf32 kernel fills [4 roles][256 events][4] - TMA producer, MMA issuer, splitter, epilogue -, the fp16x3 kernels
+ * [4 roles][64 tiles][4] from the start of the buffer, the attention forward kernel its 7 phase boundaries at
+ * device_buf[4096 ..]); NULL switches it off.  profiles/gemm_trace.py, profiles/attn_trace.py. */
 int mmx_gemm_trace(long long* device_buf);
 /* Device-to-device copy on `stream` (used by the test taps; avoids a second CUDA runtime binding on the host side). */
 int mmx_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);

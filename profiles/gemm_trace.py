@@ -26,12 +26,12 @@ def main():
     for _ in range(3):
         run()
     torch.cuda.synchronize()
-    buf = torch.zeros(4 * 64 * 4, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(4112, dtype=torch.int64, device="cuda")
     check(l.mmx_gemm_trace(ptr(buf)))
     run()
     torch.cuda.synchronize()
     check(l.mmx_gemm_trace(None))
-    t = buf.cpu().view(4, 64, 4)
+    t = buf.cpu()[:1024].view(4, 64, 4)
     if not (t > 0).any():
         print("no trace events (this kernel variant is not instrumented)")
         return

@@ -140,6 +140,14 @@ __device__ __forceinline__ void mma3(float (&main)[4], float (&cross)[4], const 
 __host__ __device__ inline int score_ld(int S) { return round_up(S, 16) + 4; }
 __host__ __device__ inline int plane_lo_off(int S) { return round_up(S, 16) + 8; }
 
+// profiling aid (mmx_gemm_trace): clock64 at the phase boundaries of block (0,0,0)
+__device__ long long* g_attn_trace = nullptr;
+#define ATT_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (g_attn_trace != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0)       \
+      g_attn_trace[slot] = clock64();                                                                     \
+  } while (0)
+
 template <int HD>
 struct AttnSmem {
   static constexpr int LDH = HD + 8;   // halves per row of an operand plane
@@ -360,80 +368,123 @@ __global__ void __launch_bounds__(TQ * 4, NP <= 2 ? 3 : 1) attention_fwd_kernel(
     }
     return;
   }
+  ATT_TRACE(0);
   load_planes_async<HD, TQ>(Qh, Ql, ldp, qrow0 * ldp + h * HD, i0, T, sQh, sQl, q_mul);     // Q tile and the first K tiles together
 #pragma unroll
   for (int pt = 0; pt < NS - 1; ++pt) issue_kv_tile<HD>(Kh, Kl, ldp, krow0 * ldp + h * HD, pt, S, sKV, NS);
+  ATT_TRACE(1);
   tile_scores<HD, MB, NS>(Kh, Kl, ldp, krow0 * ldp + h * HD, S, sQh, sQl, sKV, sP, S_pad, post_scale, T - i0);
+  ATT_TRACE(2);
 #pragma unroll
   for (int pt = 0; pt < NS - 1; ++pt) issue_kv_tile<HD>(Vh, Vl, ldp, krow0 * ldp + h * HD, pt, S, sKV, NS);   // land during the softmax
   // softmax per row (warp w owns rows w*8 .. w*8+7): the row is read once into registers, normalised there, staged to A
   // with 8-byte stores and written back as fp16 hi / lo planes for the P.V product
   const int npairs = (S + 63) >> 6;                   // pairs per lane
   const int S16 = round_up(S, 16), lo_off = plane_lo_off(S);
-  for (int rr = 0; rr < TQ / ATT_WARPS; ++rr) {
-    const int r = warp * (TQ / ATT_WARPS) + rr, i = i0 + r;
-    float* row = sP + (size_t)r * S_pad;
-    __half* prow = reinterpret_cast<__half*>(row);
-    if (i >= T) {                                     // dead row of a live tile: zero A row, zero P planes (they multiply V rows)
-      if (i < Tm) for (int j = lane; j < ldA; j += 32) A[(((long long)b * H + h) * Tm + i) * ldA + j] = 0.f;
-      for (int j = lane; j < S_pad; j += 32) row[j] = 0.f;
-      continue;
+  // Two rows per iteration (u = 0, 1), every stage written for both: the two dependency chains (shared-memory load ->
+  // max -> shuffle tree -> exp -> shuffle tree -> normalise -> split -> stores) interleave, which is what a warp with
+  // 2-6 resident neighbours per scheduler needs - the one-row loop ran at 1930 clk per row (profiles/attn_trace_r2.md).
+  constexpr int RPW = TQ / ATT_WARPS;
+  constexpr int RI = NP <= 2 ? 4 : 2;                 // rows in flight: 4 while a row is 2 registers, 2 for the long rows (32 registers each)
+  static_assert(RPW % RI == 0, "rows per iteration");
+  for (int rr = 0; rr < RPW; rr += RI) {
+    int i[RI];
+    float* row[RI];
+    bool live[RI];
+#pragma unroll
+    for (int u = 0; u < RI; ++u) {
+      const int r = warp * RPW + rr + u;
+      i[u] = i0 + r;
+      row[u] = sP + (size_t)r * S_pad;
+      live[u] = i[u] < T;
+      if (!live[u]) {                                 // dead row of a live tile: zero A row, zero P planes (they multiply V rows)
+        if (i[u] < Tm) for (int j = lane; j < ldA; j += 32) A[(((long long)b * H + h) * Tm + i[u]) * ldA + j] = 0.f;
+        for (int j = lane; j < S_pad; j += 32) row[u][j] = 0.f;
+      }
     }
-    RowRegs<NP> x;
-    float mx = -CUDART_INF_F;
+    if (!live[0]) continue;                           // rows ascend: the others are dead as well
+    RowRegs<NP> x[RI];
+    float mx[RI];
+#pragma unroll
+    for (int u = 0; u < RI; ++u) mx[u] = -CUDART_INF_F;
 #pragma unroll
     for (int m = 0; m < NP; ++m) {
       if (m < npairs) {
         const int j = 2 * lane + 64 * m;
-        float2 v = make_float2(-CUDART_INF_F, -CUDART_INF_F);
-        if (j < S) {                                  // j even, S_pad even and > S: the pair is readable; the entry S is masked
-          v = *reinterpret_cast<const float2*>(row + j);
-          if (key_bias) { v.x += key_bias[(long long)b * S + j]; if (j + 1 < S) v.y += key_bias[(long long)b * S + j + 1]; }
-          if (j + 1 >= S) v.y = -CUDART_INF_F;
-          if (flags & MMX_ATTN_CAUSAL) { if (j > i) v.x = -CUDART_INF_F; if (j + 1 > i) v.y = -CUDART_INF_F; }
+#pragma unroll
+        for (int u = 0; u < RI; ++u) {
+          float2 v = make_float2(-CUDART_INF_F, -CUDART_INF_F);
+          if (live[u] && j < S) {                     // j even, S_pad even and > S: the pair is readable; the entry S is masked
+            v = *reinterpret_cast<const float2*>(row[u] + j);
+            if (key_bias) { v.x += key_bias[(long long)b * S + j]; if (j + 1 < S) v.y += key_bias[(long long)b * S + j + 1]; }
+            if (j + 1 >= S) v.y = -CUDART_INF_F;
+            if (flags & MMX_ATTN_CAUSAL) { if (j > i[u]) v.x = -CUDART_INF_F; if (j + 1 > i[u]) v.y = -CUDART_INF_F; }
+          }
+          x[u].v[m] = v;
+          mx[u] = fmaxf(mx[u], fmaxf(v.x, v.y));
         }
-        x.v[m] = v;
-        mx = fmaxf(mx, fmaxf(v.x, v.y));
       }
     }
-    mx = warp_max(mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RI; ++u) mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], o));
+    }
     // A key whose bias is -inf is REMOVED (exp(-inf) = 0 exactly, the same bits a -10000 mask gives); a row whose keys are
     // all removed is the softmax over an empty set: A row = 0, output 0, like the reference's empty tensors when the
     // perturbation drivers drop every box (lxmert/lxmert/perturbation.py:110-117 at step 1.0).
-    const float mref = mx == -CUDART_INF_F ? 0.f : mx;
-    float sum = 0.f;
+    float mref[RI], sum[RI];
+#pragma unroll
+    for (int u = 0; u < RI; ++u) { mref[u] = mx[u] == -CUDART_INF_F ? 0.f : mx[u]; sum[u] = 0.f; }
 #pragma unroll
     for (int m = 0; m < NP; ++m) {
       if (m < npairs) {
-        x.v[m].x = expf(x.v[m].x - mref);
-        x.v[m].y = expf(x.v[m].y - mref);
-        sum += x.v[m].x + x.v[m].y;
-      }
-    }
-    sum = warp_sum(sum);
-    float* arow = A + (((long long)b * H + h) * Tm + i) * ldA;
-    __syncwarp();                                     // every lane has read its part of the fp32 row before the planes overwrite it
 #pragma unroll
-    for (int m = 0; m < NP; ++m) {
-      if (m < npairs) {
-        const int j = 2 * lane + 64 * m;
-        const float2 p = make_float2(sum > 0.f ? x.v[m].x / sum : 0.f, sum > 0.f ? x.v[m].y / sum : 0.f);   // exp(-inf) = 0 beyond S
-        if (j < ldA) *reinterpret_cast<float2*>(arow + j) = p;          // ldA % 4 == 0 and j even: the pair is inside the row
-        if (j < S16) {
-          uint32_t ph, pl;
-          split_f16(p.x, p.y, ph, pl);
-          *reinterpret_cast<uint32_t*>(prow + j) = ph;
-          *reinterpret_cast<uint32_t*>(prow + lo_off + j) = pl;
+        for (int u = 0; u < RI; ++u) {
+          x[u].v[m].x = expf(x[u].v[m].x - mref[u]);
+          x[u].v[m].y = expf(x[u].v[m].y - mref[u]);
+          sum[u] += x[u].v[m].x + x[u].v[m].y;
         }
       }
     }
-    // a ragged sample covers 64 * npairs columns only: the rest of the dense plane row is zero like everything beyond S
-    for (int j = 64 * npairs + lane; j < ldA; j += 32) arow[j] = 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RI; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+    }
+    __syncwarp();                                     // every lane has read its part of the fp32 rows before the planes overwrite them
+#pragma unroll
+    for (int u = 0; u < RI; ++u) {
+      if (!live[u]) continue;
+      float* arow = A + (((long long)b * H + h) * Tm + i[u]) * ldA;
+      __half* prow = reinterpret_cast<__half*>(row[u]);
+      const float inv = sum[u] > 0.f ? 1.f / sum[u] : 0.f;   // one reciprocal per row; exp(-inf) = 0 beyond S
+#pragma unroll
+      for (int m = 0; m < NP; ++m) {
+        if (m < npairs) {
+          const int j = 2 * lane + 64 * m;
+          const float2 p = make_float2(x[u].v[m].x * inv, x[u].v[m].y * inv);
+          if (j < ldA) *reinterpret_cast<float2*>(arow + j) = p;          // ldA % 4 == 0 and j even: the pair is inside the row
+          if (j < S16) {
+            uint32_t ph, pl;
+            split_f16(p.x, p.y, ph, pl);
+            *reinterpret_cast<uint32_t*>(prow + j) = ph;
+            *reinterpret_cast<uint32_t*>(prow + lo_off + j) = pl;
+          }
+        }
+      }
+      // a ragged sample covers 64 * npairs columns only: the rest of the dense plane row is zero like everything beyond S
+      for (int j = 64 * npairs + lane; j < ldA; j += 32) arow[j] = 0.f;
+    }
   }
+  ATT_TRACE(3);
   __syncthreads();
+  ATT_TRACE(4);
   float out[HD / 16][4];
   tile_pv<HD, MB, NS>(Vh, Vl, ldp, krow0 * ldp + h * HD, S, reinterpret_cast<const __half*>(sP), S_pad, lo_off, sKV, out, T - i0);
+  ATT_TRACE(5);
   store_pv<HD, MB>(O, ldo, qrow0, i0, T, h, out, 1.f);
+  ATT_TRACE(6);
 }
 
 // backward, query side: dA (staged), delta, dQ
@@ -475,50 +526,83 @@ __global__ void __launch_bounds__(TQ * 4, NP <= 2 ? 3 : 1) attention_bwd_q_kerne
   }
   const int npairs = (S + 63) >> 6;
   const int S16 = round_up(S, 16), lo_off = plane_lo_off(S);
-  for (int rr = 0; rr < TQ / ATT_WARPS; ++rr) {
-    const int r = warp * (TQ / ATT_WARPS) + rr, i = i0 + r;
-    float* row = sP + (size_t)r * S_pad;
-    __half* prow = reinterpret_cast<__half*>(row);
-    if (i >= T) {
-      if (i < Tm) for (int j = lane; j < ldA; j += 32) dA[(((long long)b * H + h) * Tm + i) * ldA + j] = 0.f;
-      if (dQ != nullptr) for (int j = lane; j < S_pad; j += 32) row[j] = 0.f;
-      continue;
+  constexpr int RPW = TQ / ATT_WARPS;                 // RI rows per iteration, stage by stage (see the forward kernel)
+  constexpr int RI = NP <= 2 ? 4 : 2;
+  static_assert(RPW % RI == 0, "rows per iteration");
+  for (int rr = 0; rr < RPW; rr += RI) {
+    int i[RI];
+    float* row[RI];
+    bool live[RI];
+    long long goff[RI];
+#pragma unroll
+    for (int u = 0; u < RI; ++u) {
+      const int r = warp * RPW + rr + u;
+      i[u] = i0 + r;
+      row[u] = sP + (size_t)r * S_pad;
+      live[u] = i[u] < T;
+      goff[u] = (((long long)b * H + h) * Tm + i[u]) * ldA;
+      if (!live[u]) {
+        if (i[u] < Tm) for (int j = lane; j < ldA; j += 32) dA[goff[u] + j] = 0.f;
+        if (dQ != nullptr) for (int j = lane; j < S_pad; j += 32) row[u][j] = 0.f;
+      }
     }
-    const long long goff = (((long long)b * H + h) * Tm + i) * ldA;
-    RowRegs<NP> gr, ar;
-    float dl = 0.f;
+    if (!live[0]) continue;
+    RowRegs<NP> gr[RI], ar[RI];
+    float dl[RI];
+#pragma unroll
+    for (int u = 0; u < RI; ++u) dl[u] = 0.f;
 #pragma unroll
     for (int m = 0; m < NP; ++m) {
       if (m < npairs) {
         const int j = 2 * lane + 64 * m;
-        float2 gv = make_float2(0.f, 0.f), av = make_float2(0.f, 0.f);
-        if (j < S) {
-          gv = *reinterpret_cast<const float2*>(row + j);
-          if (j + 1 >= S) gv.y = 0.f;
+#pragma unroll
+        for (int u = 0; u < RI; ++u) {
+          float2 gv = make_float2(0.f, 0.f), av = make_float2(0.f, 0.f);
+          if (live[u]) {
+            if (j < S) {
+              gv = *reinterpret_cast<const float2*>(row[u] + j);
+              if (j + 1 >= S) gv.y = 0.f;
+            }
+            if (j < ldA) {
+              av = *reinterpret_cast<const float2*>(A + goff[u] + j);           // pad columns of A are zero
+              *reinterpret_cast<float2*>(dA + goff[u] + j) = make_float2(gv.x * ginv, gv.y * ginv);   // the hooked gradient, unmasked, in TRUE units
+            }
+          }
+          gr[u].v[m] = gv; ar[u].v[m] = av;
+          dl[u] = fmaf(gv.x, av.x, dl[u]);
+          dl[u] = fmaf(gv.y, av.y, dl[u]);
         }
-        if (j < ldA) {
-          av = *reinterpret_cast<const float2*>(A + goff + j);           // pad columns of A are zero
-          *reinterpret_cast<float2*>(dA + goff + j) = make_float2(gv.x * ginv, gv.y * ginv);   // the hooked gradient, unmasked, in TRUE units
-        }
-        gr.v[m] = gv; ar.v[m] = av;
-        dl = fmaf(gv.x, av.x, dl);
-        dl = fmaf(gv.y, av.y, dl);
       }
     }
-    for (int j = 64 * npairs + lane; j < ldA; j += 32) dA[goff + j] = 0.f;   // columns a ragged sample's pairs did not reach
-    dl = warp_sum(dl);
-    if (lane == 0 && delta) delta[((long long)b * H + h) * Tm + i] = dl;
-    if (dQ != nullptr) {
-      __syncwarp();                                   // the fp32 row has been read by every lane before dS overwrites it
 #pragma unroll
-      for (int m = 0; m < NP; ++m) {
-        if (m < npairs) {
-          const int j = 2 * lane + 64 * m;
-          if (j < S16) {
-            uint32_t sh, sl;                                                      // dS = A (.) (dA - delta); A = 0 beyond S
-            split_f16(ar.v[m].x * (gr.v[m].x - dl), ar.v[m].y * (gr.v[m].y - dl), sh, sl);
-            *reinterpret_cast<uint32_t*>(prow + j) = sh;
-            *reinterpret_cast<uint32_t*>(prow + lo_off + j) = sl;
+    for (int u = 0; u < RI; ++u)
+      if (live[u]) for (int j = 64 * npairs + lane; j < ldA; j += 32) dA[goff[u] + j] = 0.f;   // columns a ragged sample's pairs did not reach
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RI; ++u) dl[u] += __shfl_xor_sync(0xffffffffu, dl[u], o);
+    }
+    if (lane == 0 && delta) {
+#pragma unroll
+      for (int u = 0; u < RI; ++u)
+        if (live[u]) delta[((long long)b * H + h) * Tm + i[u]] = dl[u];
+    }
+    if (dQ != nullptr) {
+      __syncwarp();                                   // the fp32 rows have been read by every lane before dS overwrites them
+#pragma unroll
+      for (int u = 0; u < RI; ++u) {
+        if (!live[u]) continue;
+        __half* prow = reinterpret_cast<__half*>(row[u]);
+#pragma unroll
+        for (int m = 0; m < NP; ++m) {
+          if (m < npairs) {
+            const int j = 2 * lane + 64 * m;
+            if (j < S16) {
+              uint32_t sh, sl;                                                      // dS = A (.) (dA - delta); A = 0 beyond S
+              split_f16(ar[u].v[m].x * (gr[u].v[m].x - dl[u]), ar[u].v[m].y * (gr[u].v[m].y - dl[u]), sh, sl);
+              *reinterpret_cast<uint32_t*>(prow + j) = sh;
+              *reinterpret_cast<uint32_t*>(prow + lo_off + j) = sl;
+            }
           }
         }
       }
@@ -641,6 +725,8 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
 }
 
 constexpr size_t ATT_SMEM_MAX = 227 * 1024;
+
+void attention_set_trace(long long* buf) { cudaMemcpyToSymbol(g_attn_trace, &buf, sizeof(buf)); }
 
 // scratch planes of one call (stream-ordered allocation: cached by the pool, capturable in CUDA graphs)
 struct Planes {

@@ -34,6 +34,7 @@ int gemm_nt_tc_batched(const float* A, int lda, int rows_a, const float* Bt, int
                        long long stride_res, int M, int N, int K, int batch, const GemmEpilogue& ep, cudaStream_t st);
 void gemm_tc_set_trace(long long* buf);
 void gemm_f16x3_set_trace(long long* buf);
+void attention_set_trace(long long* buf);
 
 int gemm_backend() {
   int b = g_backend.load();
@@ -159,6 +160,7 @@ int mmx_profile_gemm_report(double* total_ms, double* total_flops, int* launches
 int mmx_gemm_trace(long long* device_buf) {
   gemm_tc_set_trace(device_buf);
   gemm_f16x3_set_trace(device_buf);
+  attention_set_trace(device_buf ? device_buf + 4096 : nullptr);   // the attention forward kernel's phases: slots 4096 .. 4102
   return 0;
 }
 int mmx_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {

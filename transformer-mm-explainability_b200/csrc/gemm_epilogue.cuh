@@ -18,10 +18,10 @@ namespace mmx {
 constexpr int EPI_STAGE_FLOATS = 32 * 16;      // per epilogue warp
 
 // One copy of the activation bodies per kernel (called, not inlined at every use: see the note on code size below).
-__device__ __noinline__ float4 act_bwd4(float4 f, int act) {
+static __device__ __noinline__ float4 act_bwd4(float4 f, int act) {
   return make_float4(act_bwd(f.x, act), act_bwd(f.y, act), act_bwd(f.z, act), act_bwd(f.w, act));
 }
-__device__ __noinline__ float4 act_fwd4(float4 v, int act) {
+static __device__ __noinline__ float4 act_fwd4(float4 v, int act) {
   return make_float4(act_fwd(v.x, act), act_fwd(v.y, act), act_fwd(v.z, act), act_fwd(v.w, act));
 }
 

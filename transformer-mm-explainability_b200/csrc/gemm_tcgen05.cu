@@ -30,6 +30,7 @@
 //   warps 4-11  epilogue: tcgen05.ld (main + cross, added with RN) -> registers, TMEM released at once, then
 //               bias / act' / residual / act -> global from registers (overlaps the next tile's main loop)
 #include "gemm.cuh"
+#include "gemm_epilogue.cuh"
 #include <mutex>
 #include "tcgen05_ptx.cuh"
 #include <cuda.h>
@@ -58,7 +59,8 @@ template <int BN, int STAGES> struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 128 && BN <= 160, "UMMA N for M=128: multiple of 16; TMEM budget caps it at 160");
   static constexpr int B_BYTES = BN * BK * 4;          // per B plane (raw / lo): 16-20 KB, a multiple of 1024
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_STG = EPI_WARPS * EPI_STAGE_FLOATS * 4;     // epilogue staging: 16 KB
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_STG;
   // TMEM column map: main accumulator, cross accumulator, then the A ring (stage s: hi at TM_A+64s, lo at +32)
   static constexpr uint32_t TM_MAIN = 0, TM_CROSS = (BN + 31) / 32 * 32, TM_A = 2 * TM_CROSS;
   static_assert(TM_A + 64 * STAGES <= 512, "TMEM has 512 columns");
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   const uint32_t tfull_bar = bar_base + 8u * (3 * STAGES), tempty_bar = bar_base + 8u * (3 * STAGES + 1);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 2));
+  float* stg_base = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
@@ -307,40 +310,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);                  // next tile's MMAs may start
       if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 1);
-      const int m = m0 + q * 32 + lane;
-      if (m < p.M && !(p.dbg & 8)) {
-        float* crow = p.C + bi * p.stride_c + (long long)m * p.ldc;
-        const float* prow = p.ep.pre ? p.ep.pre + (long long)m * p.ep.ldpre : nullptr;
-        const float* rrow = p.ep.residual ? p.ep.residual + bi * p.stride_res + (long long)m * p.ep.ldres : nullptr;
-        float* arow = p.ep.C_act ? p.ep.C_act + (long long)m * p.ldc : nullptr;
-        const int nbase = n0 + ch * CW;
-#pragma unroll
-        for (int j = 0; j < CW; j += 4) {
-          const int n = nbase + j;
-          if (n >= p.N) break;                                  // N % 4 == 0 is required by the host wrapper
-          float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
-                                 __uint_as_float(acc[j + 3]));
-          if (p.ep.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          if (prow) {
-            const float4 f = *reinterpret_cast<const float4*>(prow + n);
-            v.x *= act_bwd(f.x, p.ep.act); v.y *= act_bwd(f.y, p.ep.act);
-            v.z *= act_bwd(f.z, p.ep.act); v.w *= act_bwd(f.w, p.ep.act);
-          }
-          if (rrow) {
-            const float4 b = *reinterpret_cast<const float4*>(rrow + n);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          *reinterpret_cast<float4*>(crow + n) = v;
-          if (arow) {
-            float4 a = make_float4(act_fwd(v.x, p.ep.act), act_fwd(v.y, p.ep.act), act_fwd(v.z, p.ep.act),
-                                   act_fwd(v.w, p.ep.act));
-            *reinterpret_cast<float4*>(arow + n) = a;
-          }
-        }
-      }
+      if (!(p.dbg & 8))      // coalesced through the warp's staging buffer (gemm_epilogue.cuh)
+        epilogue_store_rows<CW, true>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C,
+                                      p.ldc, bi * p.stride_c, bi * p.stride_res, p.ep, lane);
       if (warp == EPI_WARP0 && lane == 0) MMX_TRACE(3, it, 2);
     }
   }
