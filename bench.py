@@ -411,8 +411,8 @@ def clip_roofline(D: Dist, eng, inputs, B: int, cfg, steps_serial: int = 3):
     gemm_ms = tms.value / steps_serial
     tflops = tfl.value / (tms.value * 1e-3) / 1e12 if tms.value > 0 else 0.0
     names = {0: "fp32 FFMA", 1: "tcgen05 3xTF32, 1 CTA/tile", 2: "tcgen05 fp16x3 (packed fp16 hi/lo weight planes, 3 kind::f16 passes)"}
-    traffic, traffic_rec = captured_traffic("gemm_f16x3" if backend == 2 else "gemm_tf32x3")
-    ceiling = tf_sust / (3.0 if backend == 2 else 6.0)
+    traffic, traffic_rec = captured_traffic("gemm_f16x3" if backend >= 2 else "gemm_tf32x3")
+    ceiling = tf_sust / (3.0 if backend >= 2 else 6.0)
     return {"kernel": f"transformer GEMMs ({names.get(backend, '?')}, tile width 128/144/160 per launch)",
             "bound": "tensor", "achieved": tflops, "peak": tf_sust, "unit": "TFLOP/s", "frac": tflops / tf_sust,
             "traffic": traffic, "traffic_capture": traffic_rec,

@@ -33,8 +33,10 @@ int mmx_version(void);
 uint64_t mmx_launch_count(void);
 /* Selects the GEMM backend for the transformer linears: 0 = fp32 FFMA (bisecting reference), 1 = tcgen05 3xTF32
  * (raw fp32 operands split on the SM), 2 = tcgen05 fp16x3 (default when available: three kind::f16 passes over fp16
- * hi / lo planes, the weights pre-split once with mmx_pack_weight; linears whose weight is not packed run as backend 1).
- * All three are fp32-faithful (<= 2e-5 of max|C| against fp64).  Env MMX_GEMM_BACKEND overrides the default.
+ * hi / lo planes, the weights pre-split once with mmx_pack_weight; linears whose weight is not packed run as backend 1),
+ * 3 = the same arithmetic with the activations pre-split into planes by a separate pass and the product on CTA pairs
+ * (cta_group::2, 256 x BN tiles; measured alternative, see csrc/gemm_f16x3.cu).
+ * All four are fp32-faithful (<= 2e-5 of max|C| against fp64).  Env MMX_GEMM_BACKEND overrides the default.
  * Returns the backend in effect. */
 int mmx_set_gemm_backend(int backend);
 /* The backend in effect.  The LRP sweeps (use_lrp=True) switch to backend 0 for their forward, backward and relprop and

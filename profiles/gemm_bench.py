@@ -37,7 +37,7 @@ def main():
             bias = torch.randn(N, device="cuda", generator=g)
             Cm = torch.empty(M, N, device="cuda")
             pk = None
-            if backend == 2:      # fp16x3: the weight's hi / lo planes are built once (static weights)
+            if backend >= 2:      # fp16x3: the weight's hi / lo planes are built once (static weights)
                 pk = torch.empty(l.mmx_pack_weight_bytes(N, K), dtype=torch.uint8, device="cuda")
                 check(l.mmx_pack_weight(ptr(W), K, N, K, ptr(pk), current_stream()))
             for _ in range(3):

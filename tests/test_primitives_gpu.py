@@ -30,7 +30,7 @@ def _pack(lib, check, ptr, st, Wd):
 ACTS = {0: lambda x: x, 1: lambda x: x * torch.sigmoid(1.702 * x), 2: lambda x: F.gelu(x), 3: lambda x: F.relu(x)}
 
 
-@pytest.mark.parametrize("backend", [0, 1, 2])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(3200, 2304, 768), (4928, 512, 2048), (64, 512, 768), (37, 96, 64), (1, 8, 4),
                                    (130, 260, 36), (3136, 768, 3072)])
 def test_linear_and_dgrad(L, backend, M, N, K):
@@ -41,7 +41,8 @@ def test_linear_and_dgrad(L, backend, M, N, K):
     try:
         # fp32 FFMA: plain fp32 rounding.  tcgen05 3xTF32 / fp16x3: the tensor core accumulates with truncation, measured
         # ~2e-6 (K=768) .. 6e-6 (K=3072) of max|C|; all far inside the 1e-4 budget of the maps.  Backend 2 takes the
-        # packed fp16 hi / lo planes of the weight (mmx_pack_weight) beside the fp32 pointer.
+        # packed fp16 hi / lo planes of the weight (mmx_pack_weight) beside the fp32 pointer; backend 3 is the same arithmetic
+        # with A pre-split by a separate pass and the product on CTA pairs (cta_group::2, 256-row tiles).
         tol = 5e-6 if backend == 0 else 2e-5
         gen = torch.Generator().manual_seed(M + N + K)
         A = torch.randn(M, K, generator=gen)
@@ -52,7 +53,7 @@ def test_linear_and_dgrad(L, backend, M, N, K):
             Ad, Wd, bd, rd = A.cuda(), W.cuda(), bias.cuda(), res.cuda()
             Cd = torch.empty(M, N, device="cuda")
             Ca = torch.empty(M, N, device="cuda") if act else None
-            pk = _pack(lib, check, ptr, st, Wd) if backend == 2 else None
+            pk = _pack(lib, check, ptr, st, Wd) if backend >= 2 else None
             check(lib.mmx_linear_packed(ptr(Ad), K, ptr(Wd), K, ptr(pk), ptr(bd), ptr(rd), N, ptr(Cd), N, ptr(Ca), act, M, N, K,
                                         st()))
             ref = (A.double() @ W.double().t() + bias.double() + res.double())
@@ -64,7 +65,7 @@ def test_linear_and_dgrad(L, backend, M, N, K):
         pre = torch.randn(M, K, generator=gen)
         Wt = W.t().contiguous()
         dYd, Wtd, pred = dY.cuda(), Wt.cuda(), pre.cuda()      # keep device tensors alive across the call
-        pkt = _pack(lib, check, ptr, st, Wtd) if backend == 2 else None
+        pkt = _pack(lib, check, ptr, st, Wtd) if backend >= 2 else None
         for act in (0, 1, 2, 3):
             dX = torch.empty(M, K, device="cuda")
             check(lib.mmx_linear_dgrad_packed(ptr(dYd), N, ptr(Wtd), N, ptr(pkt), ptr(pred) if act else None, K, act,

@@ -618,8 +618,11 @@ int mmx_clip_interpret_host(mmx_clip* h, const float* images, int n_images, cons
     const int nb = (B - b0 < h->Bm) ? B - b0 : h->Bm;
     const int ni = (n_images == 1) ? 1 : nb;
     const float* img = (n_images == 1) ? images : images + (size_t)b0 * img_sz;
+    // The images (38.5 MB for 64 x 3 x 224^2) go up on the VISION stream: run_chunk forks both tower streams from `st`,
+    // so the text tower starts as soon as the tokens are there and runs under the image copy; the vision tower follows
+    // its own stream's copy.  (The previous chunk ended with a synchronise on `st` after joining both towers.)
     if (n_images != 1 || b0 == 0)
-      MMX_CHECK_CUDA(cudaMemcpyAsync(h->d_images, img, ni * img_sz * sizeof(float), cudaMemcpyHostToDevice, st));
+      MMX_CHECK_CUDA(cudaMemcpyAsync(h->d_images, img, ni * img_sz * sizeof(float), cudaMemcpyHostToDevice, h->v.st));
     MMX_CHECK_CUDA(cudaMemcpyAsync(h->d_tokens, tokens + (size_t)b0 * St, (size_t)nb * St * sizeof(int32_t),
                                    cudaMemcpyHostToDevice, st));
     MMX_TRY(mmx_clip_interpret_device(h, h->d_images, ni, h->d_tokens, nb, start_layer, start_layer_text, h->d_Rtext,

@@ -45,8 +45,9 @@ int pack_f16x3_ld(int K);                              // row stride (elements) 
 int pack_f16x3(const float* W, int ldw, int N, int K, void* packed, cudaStream_t st);
 BOperand packed_operand(const float* W, int ldw, const void* packed, int N, int K);
 bool gemm_f16x3_shape_ok(const float* A, int lda, const BOperand& B, float* C, int ldc, int N, int K, const GemmEpilogue& ep);
+// pair = true: backend 3 (A pre-split into planes, cta_group::2 kernel)
 int gemm_nt_f16x3(const float* A, int lda, const BOperand& B, float* C, int ldc, int M, int N, int K, const GemmEpilogue& ep,
-                  cudaStream_t st);
+                  cudaStream_t st, bool pair = false);
 
 int gemm_tc_available();
 int gemm_tc_tile_n(int bn);   // forced tcgen05 tile width: bn < 0 reads it, 0 = automatic, 128/144/160 force

@@ -41,7 +41,7 @@ int gemm_backend() {
   if (b < 0) {
     b = gemm_tc_available() ? 2 : 0;
     const char* env = getenv("MMX_GEMM_BACKEND");
-    if (env && b) b = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));   // 0 FFMA, 1 tf32x3, 2 fp16x3 (packed weights)
+    if (env && b) b = atoi(env) < 0 ? 0 : (atoi(env) > 3 ? 3 : atoi(env));   // 0 FFMA, 1 tf32x3, 2 fp16x3 (packed weights), 3 fp16x3 on CTA pairs
     g_backend.store(b);
   }
   return b;
@@ -50,7 +50,7 @@ int gemm_backend() {
 static int gemm_nt_impl(const float* A, int lda, const BOperand& B, float* C, int ldc, int M, int N, int K,
                         const GemmEpilogue& ep, cudaStream_t st) {
   const int be = gemm_backend();
-  if (be == 2 && B.hi && gemm_f16x3_shape_ok(A, lda, B, C, ldc, N, K, ep)) return gemm_nt_f16x3(A, lda, B, C, ldc, M, N, K, ep, st);
+  if (be >= 2 && B.hi && gemm_f16x3_shape_ok(A, lda, B, C, ldc, N, K, ep)) return gemm_nt_f16x3(A, lda, B, C, ldc, M, N, K, ep, st, be == 3);
   if (be >= 1 && gemm_tc_shape_ok(A, lda, B.w, B.ldw, C, ldc, N, K, ep)) return gemm_nt_tc(A, lda, B.w, B.ldw, C, ldc, M, N, K, ep, st);
   return gemm_nt_simt(A, lda, B.w, B.ldw, C, ldc, M, N, K, ep, st);
 }
@@ -117,7 +117,7 @@ int mmx_version(void) { return MMX_VERSION; }
 uint64_t mmx_launch_count(void) { return g_launches.load(); }
 int mmx_set_gemm_backend(int backend) {
   if (backend < 0) backend = 0;
-  if (backend > 2) backend = 2;
+  if (backend > 3) backend = 3;
   if (backend >= 1 && !gemm_tc_available()) backend = 0;
   g_backend.store(backend);
   return g_backend.load();

@@ -77,7 +77,6 @@ struct Params {
   float* C;
   GemmEpilogue ep;
   long long* trace = nullptr;   // optional device buffer [4 roles][64 tiles][4]: clock64 timeline of CTA 0 (mmx_gemm_trace; profiling aid)
-  int dbg = 0;     // measurement only (MMX_F16X3_DBG): 2 no TMA (MMAs on whatever is in smem), 4 one accumulator, 8 one MMA per k-step, 16 no stores
 };
 
 __device__ __forceinline__ void tmem_st8v(uint32_t taddr, const uint32_t* r) {
@@ -312,9 +311,8 @@ __global__ void __launch_bounds__(threads_for(G), 1) gemm_f16x3_kernel(const __g
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);                  // next tile's MMAs may start
       if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 1);
-      if (!(p.dbg & 16))
-        epilogue_store_rows<CW, ACT>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C, p.ldc, 0, 0,
-                                p.ep, lane);
+      epilogue_store_rows<CW, ACT>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C, p.ldc, 0, 0,
+                                   p.ep, lane);
       if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 2);
     }
   }
@@ -328,186 +326,15 @@ __global__ void __launch_bounds__(threads_for(G), 1) gemm_f16x3_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Pre-split form (round 2, the default): A arrives as fp16 hi / lo' planes as well (split ONCE per GEMM by
-// split_a_planes_kernel, or by the kernel that produced A), so the main loop is TMA -> tcgen05.mma(.ss) and nothing else.
-// Why: the in-kernel split above costs 64 F2FP.PACK_AB per thread and K-slab on the XU pipe (16 lanes / clk / SM) and is
-// repeated for every one of the N / BN column tiles that share the A rows (15 x for the QKV product): ncu has the XU pipe
-// 56 % busy and 2170 clk per slab against 870 clk of MMA work (profiles/gemm_f16x3_r2_ncu.md).  Splitting once moves
-// 1 / tiles_n of that work out of the loop; TMEM then holds only accumulators, so BN = 128 gets TWO accumulator sets and
-// its epilogue (a 2000-clk TMEM drain at 64 B / clk) overlaps the next tile's main loop.
-//   warp 0      TMA producer: A_hi, A_lo (128 x 64 fp16 each), W_hi, W_lo (BN x 64)     ring: full / empty (3 stages)
-//   warp 1      MMA issuer: per k-step  cross += A_lo W_hi, cross += A_hi W_lo, main += A_hi W_hi
-//   warp 2      TMEM allocator
-//   warps 4-11  epilogue (as above)
+// Backend 3 (selectable, mmx_set_gemm_backend(3)): A arrives as fp16 hi / lo' planes as well - split ONCE per GEMM by
+// split_a_planes_kernel instead of once per column tile inside the main loop - and the product runs on CTA PAIRS.
+// Measured (profiles/gemm_bench_r2_epilogue.log, CUDA-graph timing): the pair main loop runs at the tensor pipe's floor
+// (690 clk per 256 x 128 x 64 slab, profiles/gemm_trace_r2_after.log) and the GEMM alone beats the default kernel by 0-25 %
+// (QKV 32.3 vs 31.4 us, fc1 36.1 vs 39.7, text fc2 29.2 vs 43.2), but the separate split pass costs 6-14 us per GEMM, so
+// end to end it loses until the producers of A (layer norm, attention output, the GELU epilogue) write the planes
+// themselves.  That is the next step for this kernel; until then the in-kernel split above stays the default.
 namespace pre {
-constexpr int THREADS_P = 12 * 32;
-constexpr int AP_BYTES = BM * BK * 2;                    // one A plane slab: 16 KB
-template <int BN> struct CfgP {
-  static_assert(BN % 16 == 0 && BN >= 128 && BN <= 256, "UMMA N for M = 128");
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE = 2 * AP_BYTES + 2 * B_BYTES;       // A_hi, A_lo, W_hi, W_lo
-  static constexpr int EPI_STG = EPI_WARPS * EPI_STAGE_FLOATS * 4;
-  static constexpr int ST = (227 * 1024 - 1024 - 512 - EPI_STG) / STAGE > 4 ? 4 : (227 * 1024 - 1024 - 512 - EPI_STG) / STAGE;
-  static constexpr int SMEM_BYTES = ST * STAGE + 1024 + 512 + EPI_STG;
-  static constexpr uint32_t CSTRIDE = (BN + 31) / 32 * 32;
-  static constexpr int ACC = 4 * CSTRIDE <= 512 ? 2 : 1;         // accumulator sets (main + cross each)
-  static constexpr int CW = BN / 2;
-  static_assert(ST >= 2, "ring depth");
-};
-
-template <int BN, bool ACT>
-__global__ void __launch_bounds__(THREADS_P, 1) gemm_f16x3p_kernel(const __grid_constant__ CUtensorMap mapAhi,
-                                                                   const __grid_constant__ CUtensorMap mapAlo,
-                                                                   const __grid_constant__ CUtensorMap mapBhi,
-                                                                   const __grid_constant__ CUtensorMap mapBlo, Params p) {
-  using cfg = CfgP<BN>;
-  constexpr int B_BYTES = cfg::B_BYTES, STAGE = cfg::STAGE, ST = cfg::ST, CW = cfg::CW, ACC = cfg::ACC;
-  constexpr uint32_t CSTRIDE = cfg::CSTRIDE;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + ST * STAGE;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (ST + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * ST + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * ST + ACC + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + ST * STAGE + 8 * (2 * ST + 2 * ACC));
-  float* stg_base = reinterpret_cast<float*>(smem_gen + ST * STAGE + 512);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
-  const int nk = (p.K + BK - 1) / BK;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < ST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAhi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
-                 "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    int stage = 0; uint32_t phase = 0;
-    int itp = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++itp) {
-      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
-      for (int kb = 0; kb < nk; ++kb) {
-        if (p.dbg & 2) break;
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = smem_base + stage * STAGE;
-        if (elect_one()) {
-          if (kb == 0) HX_TRACE(0, itp, 0);
-          if (kb == nk - 1) HX_TRACE(0, itp, 1);
-          mbar_expect_tx(full_bar(stage), STAGE);
-          tma_load_2d(sa, &mapAhi, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sa + AP_BYTES, &mapAlo, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sa + 2 * AP_BYTES, &mapBhi, full_bar(stage), kb * BK, n0);
-          tma_load_2d(sa + 2 * AP_BYTES + B_BYTES, &mapBlo, full_bar(stage), kb * BK, n0);
-        }
-        __syncwarp();
-        if (++stage == ST) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    int stage = 0; uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int as = it % ACC;
-      mbar_wait(tempty_bar(as), (uint32_t)((it / ACC) & 1) ^ 1);     // the epilogue drained this accumulator set
-      tc_fence_after();
-      const uint32_t d_main = tmem_base + (uint32_t)as * 2u * CSTRIDE, d_cross = d_main + CSTRIDE;
-      const uint32_t d_x = (p.dbg & 4) ? d_main : d_cross;
-      if (lane == 0) HX_TRACE(1, it, 0);
-      for (int kb = 0; kb < nk; ++kb) {
-        if (!(p.dbg & 2)) mbar_wait(full_bar(stage), phase);
-        if (lane == 0 && kb == 0) HX_TRACE(1, it, 1);
-        if (lane == 0 && kb == nk - 1) HX_TRACE(1, it, 2);
-        tc_fence_after();
-        const uint32_t sa = smem_base + stage * STAGE;
-        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + AP_BYTES);
-        const uint64_t b_hi = make_desc(sa + 2 * AP_BYTES), b_lo = make_desc(sa + 2 * AP_BYTES + B_BYTES);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {                       // UMMA_K = 16: +32 B inside the swizzled row (+2 in the descriptor)
-            const uint64_t adv = (uint64_t)(2 * k);
-            const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-            if (!(p.dbg & 8)) {
-              umma_f16_ss(d_x, a_lo + adv, b_hi + adv, idesc, first);
-              umma_f16_ss(d_x, a_hi + adv, b_lo + adv, idesc, 1u);
-            }
-            umma_f16_ss(d_main, a_hi + adv, b_hi + adv, idesc, (p.dbg & 4) && !(p.dbg & 8) ? 1u : first);
-          }
-          umma_commit(empty_bar(stage));
-          if (kb == nk - 1) umma_commit(tfull_bar(as));
-        }
-        __syncwarp();
-        if (++stage == ST) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
-    // ------------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
-    const int q = warp & 3;
-    const int ch = (warp - EPI_WARP0) >> 2;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
-      const int as = it % ACC;
-      mbar_wait(tfull_bar(as), (uint32_t)((it / ACC) & 1));
-      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 0);
-      tc_fence_after();
-      uint32_t acc[CW];
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 2u * CSTRIDE + (uint32_t)(ch * CW);
-#pragma unroll
-      for (int c = 0; c + 16 <= CW; c += 16) {
-        uint32_t x[16];
-        tmem_ld16_nowait(trow + c, acc + c);
-        tmem_ld16_nowait(trow + CSTRIDE + c, x);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c + j] = __float_as_uint(fmaf(__uint_as_float(x[j]), LO_INV, __uint_as_float(acc[c + j])));
-      }
-      if constexpr (CW % 16 == 8) {
-        constexpr int c = CW - 8;
-        uint32_t x[8];
-        tmem_ld8_nowait(trow + c, acc + c);
-        tmem_ld8_nowait(trow + CSTRIDE + c, x);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[c + j] = __float_as_uint(fmaf(__uint_as_float(x[j]), LO_INV, __uint_as_float(acc[c + j])));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
-      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 1);
-      if (!(p.dbg & 16))
-        epilogue_store_rows<CW, ACT>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C, p.ldc, 0, 0,
-                                p.ep, lane);
-      if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 2);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
+constexpr int AP_BYTES = BM * BK * 2;                    // one A plane slab (128 x 64 fp16): 16 KB
 
 // ------------------------------------------------------------------------------------------------------------------
 // CTA-pair form (cta_group::2): one 256 x BN output tile per PAIR of SMs.  Why: the single-CTA kernels above are bound by
@@ -592,7 +419,6 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_
     for (int t = pair; t < num_tiles; t += num_pairs, ++itp) {
       const int m0 = (t % tiles_m) * 2 * BM + (int)rank * BM, n0 = (t / tiles_m) * BN + (int)rank * BNH;
       for (int kb = 0; kb < nk; ++kb) {
-        if (p.dbg & 2) break;
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t sa = smem_base + stage * STAGE;
         if (elect_one()) {
@@ -620,10 +446,9 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_
         mbar_wait(tempty_bar(as), (uint32_t)((it / ACC) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)as * 2u * CSTRIDE, d_cross = d_main + CSTRIDE;
-        const uint32_t d_x = (p.dbg & 4) ? d_main : d_cross;
         if (lane == 0) HX_TRACE(1, it, 0);
         for (int kb = 0; kb < nk; ++kb) {
-          if (!(p.dbg & 2)) mbar_wait(full_bar(stage), phase);
+          mbar_wait(full_bar(stage), phase);
           if (lane == 0 && kb == 0) HX_TRACE(1, it, 1);
           if (lane == 0 && kb == nk - 1) HX_TRACE(1, it, 2);
           tc_fence_after();
@@ -635,11 +460,9 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t adv = (uint64_t)(2 * k);
               const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-              if (!(p.dbg & 8)) {
-                umma_f16_ss_pair(d_x, a_lo + adv, b_hi + adv, idesc, first);
-                umma_f16_ss_pair(d_x, a_hi + adv, b_lo + adv, idesc, 1u);
-              }
-              umma_f16_ss_pair(d_main, a_hi + adv, b_hi + adv, idesc, (p.dbg & 4) && !(p.dbg & 8) ? 1u : first);
+              umma_f16_ss_pair(d_cross, a_lo + adv, b_hi + adv, idesc, first);
+              umma_f16_ss_pair(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16_ss_pair(d_main, a_hi + adv, b_hi + adv, idesc, first);
             }
             umma_commit_pair(empty_bar(stage));                   // both CTAs' stage is free when these MMAs retire
             if (kb == nk - 1) umma_commit_pair(tfull_bar(as));
@@ -675,9 +498,8 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
       if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 1);
-      if (!(p.dbg & 16))
-        epilogue_store_rows<CW, ACT>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C, p.ldc, 0, 0,
-                                p.ep, lane);
+      epilogue_store_rows<CW, ACT>(acc, stg_base + (warp - EPI_WARP0) * EPI_STAGE_FLOATS, m0 + q * 32, n0 + ch * CW, p.M, p.N, p.C, p.ldc, 0, 0,
+                                   p.ep, lane);
       if (warp == EPI_WARP0 && lane == 0) HX_TRACE(2, it, 2);
     }
   }
@@ -796,40 +618,6 @@ static int launch_bn(const float* A, int lda, const BOperand& B, int M, int N, i
   return launch_bn_g<BN, 1>(A, lda, B, M, N, K, p, st);   // G = 2 / 4 were measured: no gain (the split is not the limiter)
 }
 
-// 0: in-kernel split (single CTA; default); 1: pre-split planes, single CTA; 2: pre-split planes, CTA pair
-static int f16x3_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MMX_F16X3_MODE"); v = e ? atoi(e) : 0; if (v < 0 || v > 2) v = 0; }
-  return v;
-}
-static int f16x3_dbg() {      // measurement only.  1: fixed scratch, split skipped (results are garbage)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MMX_F16X3_DBG"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
-template <int BN>
-static int launch_pre(const __half* Ahi, const __half* Alo, int ldpa, const BOperand& B, int M, int N, int K, const Params& p,
-                      cudaStream_t st) {
-  using cfg = pre::CfgP<BN>;
-  CUtensorMap mapAhi, mapAlo, mapBhi, mapBlo;
-  MMX_TRY(make_map(&mapAhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Ahi, M, K, ldpa, BK, BM));
-  MMX_TRY(make_map(&mapAlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Alo, M, K, ldpa, BK, BM));
-  MMX_TRY(make_map(&mapBhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.hi, N, K, B.ldp, BK, BN));
-  MMX_TRY(make_map(&mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B.lo, N, K, B.ldp, BK, BN));
-  const int tiles = cdiv(M, BM) * cdiv(N, BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  if (p.ep.pre || p.ep.C_act) {
-    MMX_CHECK_CUDA(cudaFuncSetAttribute(pre::gemm_f16x3p_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
-    pre::gemm_f16x3p_kernel<BN, true><<<grid, pre::THREADS_P, cfg::SMEM_BYTES, st>>>(mapAhi, mapAlo, mapBhi, mapBlo, p);
-  } else {
-    MMX_CHECK_CUDA(cudaFuncSetAttribute(pre::gemm_f16x3p_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
-    pre::gemm_f16x3p_kernel<BN, false><<<grid, pre::THREADS_P, cfg::SMEM_BYTES, st>>>(mapAhi, mapAlo, mapBhi, mapBlo, p);
-  }
-  MMX_LAUNCH_CHECK();
-  return 0;
-}
-
 template <int BN>
 static int launch_pair(const __half* Ahi, const __half* Alo, int ldpa, const BOperand& B, int M, int N, int K, const Params& p,
                        cudaStream_t st) {
@@ -853,7 +641,9 @@ static int launch_pair(const __half* Ahi, const __half* Alo, int ldpa, const BOp
   return 0;
 }
 
-// Tile width of the pair kernel: estimated clocks = waves x (K-slabs x max(MMA, L2 delivery) + exposed TMEM drain).
+// Tile width of the pair kernel: estimated clocks = waves x (K-slabs x slab time + exposed accumulator hand-over).  Slab
+// time and hand-over from the clock64 timeline (profiles/gemm_trace_r2_after.log): 690 clk per slab at BN = 128 (two
+// accumulator sets: the drain is hidden), 1340 at BN = 256 plus ~5500 clk between the last MMA and the next tile's first.
 static int pick_bn_pair(int M, int N, int K) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MMX_PAIR_BN"); forced = e ? atoi(e) : 0; }
@@ -864,52 +654,33 @@ static int pick_bn_pair(int M, int N, int K) {
   for (int bn : {128, 160, 192, 256}) {
     const long long tiles = (long long)tiles_m * cdiv(N, bn);
     const long long waves = (tiles + pairs - 1) / pairs;
-    const long long mma = 6ll * bn;                               // 12 instructions x 256 * bn / 512 clk
-    const long long l2 = (32768 + 128ll * bn) / 43;               // this CTA's bytes per slab at the chip-wide L2 cap per SM
-    const long long slab = mma > l2 ? mma : l2;
-    const long long drain = 4 * bn <= 512 ? 0 : 16ll * bn;        // one accumulator set: the TMEM drain (64 B / clk) is exposed
-    const long long cost = waves * (nk * slab + drain);
+    const long long slab = 690ll * bn / 128;
+    const long long handover = 4 * bn <= 512 ? 800 : 1500 + 16ll * bn;
+    const long long cost = waves * (nk * slab + handover);
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
 
-// split A once (stream-ordered scratch, same bytes as the fp32 original), then the TMA -> MMA kernel
-static int gemm_presplit(const float* A, int lda, const BOperand& B, int M, int N, int K, const Params& p, cudaStream_t st, bool pair) {
+// split A once (stream-ordered scratch, same bytes as the fp32 original), then the TMA -> MMA pair kernel
+static int gemm_presplit_pair(const float* A, int lda, const BOperand& B, int M, int N, int K, const Params& p, cudaStream_t st) {
   const int ldpa = round_up(K, 8);
   __half* planes = nullptr;
-  const int dbg = f16x3_dbg();
-  static __half* dbg_planes = nullptr;
-  if (dbg) {
-    if (!dbg_planes) { MMX_CHECK_CUDA(cudaMalloc((void**)&dbg_planes, (size_t)256 << 20)); MMX_CHECK_CUDA(cudaMemset(dbg_planes, 0, (size_t)256 << 20)); }
-    planes = dbg_planes;
-  } else {
-    keep_stream_scratch_cached();
-    MMX_CHECK_CUDA(cudaMallocAsync((void**)&planes, (size_t)2 * M * ldpa * sizeof(__half), st));
-  }
+  keep_stream_scratch_cached();
+  MMX_CHECK_CUDA(cudaMallocAsync((void**)&planes, (size_t)2 * M * ldpa * sizeof(__half), st));
   __half *Ahi = planes, *Alo = planes + (size_t)M * ldpa;
   const long long total = (long long)M * ((K + 3) / 4);
   const int grid = (int)((total + 255) / 256 < (long long)sm_count() * 8 ? (total + 255) / 256 : (long long)sm_count() * 8);
-  if (!dbg) {
-    pre::split_a_planes_kernel<<<grid, 256, 0, st>>>(A, lda, Ahi, Alo, ldpa, M, K);
-    MMX_LAUNCH_CHECK();
-  }
+  pre::split_a_planes_kernel<<<grid, 256, 0, st>>>(A, lda, Ahi, Alo, ldpa, M, K);
+  MMX_LAUNCH_CHECK();
   int rc = 0;
-  if (pair) {
-    switch (pick_bn_pair(M, N, K)) {
-      case 160: rc = launch_pair<160>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
-      case 192: rc = launch_pair<192>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
-      case 256: rc = launch_pair<256>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
-      default: rc = launch_pair<128>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
-    }
-  } else {
-    switch (pick_bn(M, N)) {
-      case 144: rc = launch_pre<144>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
-      case 160: rc = launch_pre<160>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
-      default: rc = launch_pre<128>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
-    }
+  switch (pick_bn_pair(M, N, K)) {
+    case 160: rc = launch_pair<160>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+    case 192: rc = launch_pair<192>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+    case 256: rc = launch_pair<256>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
+    default: rc = launch_pair<128>(Ahi, Alo, ldpa, B, M, N, K, p, st); break;
   }
-  if (!dbg) cudaFreeAsync(planes, st);
+  cudaFreeAsync(planes, st);
   return rc;
 }
 
@@ -956,13 +727,12 @@ bool gemm_f16x3_shape_ok(const float* A, int lda, const BOperand& B, float* C, i
 }
 
 int gemm_nt_f16x3(const float* A, int lda, const BOperand& B, float* C, int ldc, int M, int N, int K, const GemmEpilogue& ep,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool pair) {
   if (M == 0 || N == 0) return 0;
   MMX_TRY(hx::ensure_encode());
   hx::Params p{M, N, K, ldc, C, ep};
-  p.dbg = hx::f16x3_dbg();
   p.trace = hx::g_trace;
-  if (hx::f16x3_mode() >= 1) return hx::gemm_presplit(A, lda, B, M, N, K, p, st, hx::f16x3_mode() == 2);
+  if (pair) return hx::gemm_presplit_pair(A, lda, B, M, N, K, p, st);
   switch (hx::pick_bn(M, N)) {
     case 144: return hx::launch_bn<144>(A, lda, B, M, N, K, p, st);
     case 160: return hx::launch_bn<160>(A, lda, B, M, N, K, p, st);
