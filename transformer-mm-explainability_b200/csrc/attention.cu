@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(TQ * 4, NP <= 2 ? 3 : 1) attention_fwd_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Tm = T;                                   // height of the staged plane
   long long qrow0 = (long long)b * T, krow0 = (long long)b * S;
+  pdl_wait();                                         // launched as a programmatic dependent (launch_pdl)
   if (rg.lens) { T = S = rg.lens[b]; qrow0 = krow0 = rg.offs[b]; }
   if (i0 >= T) {                                      // tile entirely past this sample's rows: zero its A rows
     for (int e = tid; e < TQ * ldA; e += ATT_THREADS) {
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(TQ * 4, NP <= 2 ? 3 : 1) attention_bwd_q_kerne
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Tm = T;
   long long qrow0 = (long long)b * T, krow0 = (long long)b * S;
+  pdl_wait();
   if (rg.lens) { T = S = rg.lens[b]; qrow0 = krow0 = rg.offs[b]; }
   if (i0 >= T) {                                      // past this sample's rows: the hooked gradient is zero there
     for (int e = tid; e < TQ * ldA; e += ATT_THREADS) {
@@ -640,6 +642,7 @@ __global__ void __launch_bounds__(KV_THREADS) attention_bwd_kv_kernel(
   const int m0 = (warp & 3) * 16, d0 = (warp >> 2) * (HD / 2);   // this warp's 16 keys and d half
   const int Tm = T;
   long long qrow0 = (long long)b * T, krow0 = (long long)b * S;
+  pdl_wait();
   if (rg.lens) { T = S = rg.lens[b]; qrow0 = krow0 = rg.offs[b]; }
   if (j0 >= S) return;
   const float gs = gscale ? gscale[b] : 1.f;           // staged dA is in true units, delta / dO / the outputs are scaled
@@ -768,8 +771,8 @@ static int launch_fwd_tq(const __half* Qh, const __half* Ql, const __half* Kh, c
   const size_t smem = AttnSmem<HD>::bytes(S, TQ, NS);
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<HD, TQ, NP, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, TQ), H, B);
-  attention_fwd_kernel<HD, TQ, NP, NS><<<grid, TQ * 4, smem, st>>>(Qh, Ql, Kh, Kl, Vh, Vl, ldp, key_bias, A, ldA, O, ldo, H, T, S, q_mul,
-                                                                  post_scale, flags, rg);
+  MMX_CHECK_CUDA(launch_pdl(attention_fwd_kernel<HD, TQ, NP, NS>, grid, dim3(TQ * 4), smem, st, Qh, Ql, Kh, Kl, Vh, Vl, ldp, key_bias, A, ldA, O,
+                            ldo, H, T, S, q_mul, post_scale, flags, rg));
   MMX_LAUNCH_CHECK();
   return 0;
 }
@@ -831,8 +834,8 @@ static int launch_bwd_q_tq(const __half* Gh, const __half* Gl, int ldg, const __
   const size_t smem = AttnSmem<HD>::bytes(S, TQ, NS);
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel<HD, TQ, NP, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, TQ), H, B);
-  attention_bwd_q_kernel<HD, TQ, NP, NS><<<grid, TQ * 4, smem, st>>>(Gh, Gl, ldg, Kh, Kl, Vh, Vl, ldp, A, dA, ldA, delta, dQ, lddq, H, T, S, scale,
-                                                            rg, gscale);
+  MMX_CHECK_CUDA(launch_pdl(attention_bwd_q_kernel<HD, TQ, NP, NS>, grid, dim3(TQ * 4), smem, st, Gh, Gl, ldg, Kh, Kl, Vh, Vl, ldp, A, dA, ldA,
+                            delta, dQ, lddq, H, T, S, scale, rg, gscale));
   MMX_LAUNCH_CHECK();
   return 0;
 }
@@ -861,8 +864,8 @@ static int launch_bwd_planes(const __half* Gh, const __half* Gl, int ldg, const 
   const size_t smem2 = sizeof(__half) * (4 * KV_ROWS * (HD + 8) + 4 * KV_ROWS * (KV_KEYS + 8));
   MMX_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   dim3 grid2(cdiv(S, KV_KEYS), H, B);
-  attention_bwd_kv_kernel<HD><<<grid2, KV_THREADS, smem2, st>>>(Gh, Gl, ldg, Qh, Ql, ldp, A, dA, ldA, delta, dK, lddk, dV, lddv, H, T, S,
-                                                                scale_k, rg, gscale);
+  MMX_CHECK_CUDA(launch_pdl(attention_bwd_kv_kernel<HD>, grid2, dim3(KV_THREADS), smem2, st, Gh, Gl, ldg, Qh, Ql, ldp, A, dA, ldA, delta, dK, lddk,
+                            dV, lddv, H, T, S, scale_k, rg, gscale));
   MMX_LAUNCH_CHECK();
   return 0;
 }

@@ -126,10 +126,6 @@ __global__ void __launch_bounds__(threads_for(G), 1) gemm_f16x3_kernel(const __g
   float* stg_base = reinterpret_cast<float*>(smem_gen + SA * A_BYTES + SB * B_STAGE + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
-  const int nk = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), SPLIT_WARPS); }
@@ -151,6 +147,14 @@ __global__ void __launch_bounds__(threads_for(G), 1) gemm_f16x3_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, tensor-map prefetch, TMEM allocation) touched no global
+  // data and may run while the kernel before this one in the stream is still draining; its results (A, the residual, the
+  // device-side row count) are read only below.  A no-op when the launch carries no programmatic dependency.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int nk = (p.K + BK - 1) / BK;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer, A (whole warp loops, one lane issues)
@@ -602,12 +606,21 @@ static int launch_bn_g(const float* A, int lda, const BOperand& B, int M, int N,
   // per device: the attribute belongs to the (function, device) pair
   const int tiles = cdiv(M, BM) * cdiv(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  // launched as a programmatic dependent of whatever precedes it in the stream: the prologue overlaps that kernel's tail
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("MMX_PDL"); pdl = e ? atoi(e) != 0 : 1; }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(threads_for(G)); lc.dynamicSmemBytes = cfg::SMEM_BYTES; lc.stream = st;
+  lc.attrs = attr; lc.numAttrs = pdl ? 1 : 0;
   if (p.ep.pre || p.ep.C_act) {
     MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel<BN, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
-    gemm_f16x3_kernel<BN, G, true><<<grid, threads_for(G), cfg::SMEM_BYTES, st>>>(mapA, mapBhi, mapBlo, p);
+    MMX_CHECK_CUDA(cudaLaunchKernelEx(&lc, gemm_f16x3_kernel<BN, G, true>, mapA, mapBhi, mapBlo, p));
   } else {
     MMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel<BN, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
-    gemm_f16x3_kernel<BN, G, false><<<grid, threads_for(G), cfg::SMEM_BYTES, st>>>(mapA, mapBhi, mapBlo, p);
+    MMX_CHECK_CUDA(cudaLaunchKernelEx(&lc, gemm_f16x3_kernel<BN, G, false>, mapA, mapBhi, mapBlo, p));
   }
   MMX_LAUNCH_CHECK();
   return 0;

@@ -1,5 +1,7 @@
 // Shared helpers for libmmx (sm_100a only).
 #pragma once
+#include <utility>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -37,6 +39,28 @@ inline void keep_stream_scratch_cached() {
   }
   pool_set[dev].store(true, std::memory_order_release);
 }
+
+// Programmatic dependent launch (sm_90+): the kernel is launched as a dependent of whatever precedes it in the stream, so
+// its launch latency (and any prologue before pdl_wait()) overlaps that kernel's tail.  Every kernel launched this way
+// calls pdl_wait() before it touches global memory.  MMX_PDL=0 switches the attribute off (pdl_wait() is then a no-op).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MMX_PDL"); v = e ? atoi(e) != 0 : 1; }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+  lc.attrs = attr; lc.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const float* __r
                                                                 const int* __restrict__ rows_dev) {
   constexpr int D = NV * 128;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_wait();                                          // launched as a programmatic dependent (launch_pdl)
   if (rows_dev) rows = min(rows, __ldg(rows_dev));
   if (r >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)(row_map ? row_map[r] : r) * ldx);
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
                                                                 const int* __restrict__ rows_dev) {
   constexpr int D = NV * 128;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_wait();                                          // launched as a programmatic dependent (launch_pdl)
   if (rows_dev) rows = min(rows, __ldg(rows_dev));
   if (r >= rows) return;
   const long long xrow = row_map ? row_map[r] : r;
@@ -163,7 +165,7 @@ int layernorm_fwd(const float* x, int ldx, const int* row_map, const float* gamm
   if (rows == 0) return 0;
   if (ln_vec_ok(D, {x, gamma, beta, y}, {ldx, ldy})) {
     const int g = cdiv(rows, 8);
-#define MMX_LN_F(NV) layernorm_fwd_vec_kernel<NV><<<g, 256, 0, st>>>(x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, eps, rows_dev)
+#define MMX_LN_F(NV) MMX_CHECK_CUDA(launch_pdl(layernorm_fwd_vec_kernel<NV>, dim3(g), dim3(256), 0, st, x, ldx, row_map, gamma, beta, y, ldy, mean, rstd, rows, eps, rows_dev))
     switch (D / 128) {
       case 1: MMX_LN_F(1); break; case 2: MMX_LN_F(2); break; case 3: MMX_LN_F(3); break; case 4: MMX_LN_F(4); break;
       case 5: MMX_LN_F(5); break; case 6: MMX_LN_F(6); break; case 7: MMX_LN_F(7); break; default: MMX_LN_F(8); break;
@@ -182,7 +184,7 @@ int layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const int*
   if (rows == 0) return 0;
   if (ln_vec_ok(D, {dy, x, gamma, resid, dx}, {lddy, ldx, lddx, resid ? ldres : 0})) {
     const int g = cdiv(rows, 8);
-#define MMX_LN_B(NV) layernorm_bwd_vec_kernel<NV><<<g, 256, 0, st>>>(dy, lddy, x, ldx, row_map, gamma, mean, rstd, resid, ldres, dx, lddx, rows, rows_dev)
+#define MMX_LN_B(NV) MMX_CHECK_CUDA(launch_pdl(layernorm_bwd_vec_kernel<NV>, dim3(g), dim3(256), 0, st, dy, lddy, x, ldx, row_map, gamma, mean, rstd, resid, ldres, dx, lddx, rows, rows_dev))
     switch (D / 128) {
       case 1: MMX_LN_B(1); break; case 2: MMX_LN_B(2); break; case 3: MMX_LN_B(3); break; case 4: MMX_LN_B(4); break;
       case 5: MMX_LN_B(5); break; case 6: MMX_LN_B(6); break; case 7: MMX_LN_B(7); break; default: MMX_LN_B(8); break;
