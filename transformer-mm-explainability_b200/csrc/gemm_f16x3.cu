@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(threads_for(G), 1) gemm_f16x3_kernel(const __g
   // data and may run while the kernel before this one in the stream is still draining; its results (A, the residual, the
   // device-side row count) are read only below.  A no-op when the launch carries no programmatic dependency.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // (No early griddepcontrol.launch_dependents: measured 8300 -> 7880 maps/s - the dependent's CTAs park on the SMs the
+  // last wave leaves idle, which the OTHER tower's stream would have used.)
   if (p.ep.m_dev) p.M = min(p.M, __ldg(p.ep.m_dev));       // ragged batch: the host-side M is only an upper bound
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
