@@ -12,15 +12,18 @@ the oracle is pinned against *outputs of the reference itself run in the build c
 of ``oracle/ref_shims.py``), runs it on seeded inputs and commits the results under ``tests/golden/``.
 ``tests/test_oracle_golden.py`` checks this restatement against those fixtures everywhere, and
 ``tests/test_oracle_vs_reference.py`` re-checks it against the live reference whenever ``/root/reference``
-is present.  Exceptions ("parity unpinned"): the ViT-B/16 *model* forward (its source is not vendored in the
-reference tree; its rule is pinned through ``avg_heads`` / ``apply_self_attention_rules``), the
-VisualBERT *embeddings* module and the perturbation driver loops (they need the mmf registry, Faster-RCNN, tokenizers
-and COCO files; the models they call are pinned).
+is present.  Nothing on the path is unpinned any more (round 2): the ViT-B/16 *model* forward - whose source is not
+vendored in the reference tree, SURVEY.md §8c - is pinned against torchvision's ``VisionTransformer`` with shared weights
+(``tests/test_vit_pin.py``: logits and every block's attention probabilities), the VisualBERT *embeddings* run the
+reference's own ``BertVisioLinguisticEmbeddings`` class loaded by file path (``ref_visualbert._import_embeddings``), and
+the LXMERT perturbation loops are the UNMODIFIED reference functions driven with a duck-typed ``self``
+(``ref_perturbation``; golden ``tests/golden/lxmert_perturbation.npz``).  VisualBERT's evaluation loop (it needs the mmf
+registry and COCO files) is checked against the oracle restatement only; the model it calls is pinned.
 
 Modules: ``rules`` (rules 5-11, rollout, Otsu masks), ``clip_oracle``, ``vit_oracle``, ``detr_oracle``,
 ``lxmert_oracle``, ``visualbert_oracle`` (forward + generators + baselines + ablations + perturbation steps), ``lrp``
-(the relprop sweep behind ``use_lrp=True`` - the product does not implement it yet, the target is pinned here),
-``ref_shims`` / ``ref_detr`` / ``ref_lxmert`` / ``ref_visualbert`` (harnesses that run the unmodified reference on CPU),
+(the relprop sweep behind ``use_lrp=True``; the product's device sweep - ``csrc/lrp.cu`` - is tested against it),
+``ref_shims`` / ``ref_detr`` / ``ref_lxmert`` / ``ref_visualbert`` / ``ref_perturbation`` (harnesses that run the unmodified reference on CPU),
 ``make_golden`` (writes ``tests/golden/*.npz`` from them).  The synthetic workload generators live in the product
 package (``mmx_b200/synthetic.py``) and are re-exported by ``clip_oracle`` so both sides see the same tensors.
 """

@@ -2,11 +2,14 @@
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
 
-PARITY UNPINNED for the model forward: the ViT the notebook uses comes from another repository
+Pinning of the model forward: the ViT the notebook uses comes from another repository
 (``hila-chefer/Transformer-Explainability``, ``baselines/ViT/ViT_new.py``, cloned at
 Transformer_MM_explainability_ViT.ipynb:47 and imported at :1212) which is NOT vendored under /root/reference, so it
 cannot be executed here.  The forward below restates the published timm ``vit_base_patch16_224`` block that file
-wraps (pre-LN, eps 1e-6, packed qkv with bias, scores = (q k^T) * scale, exact-erf GELU MLP, cls-token head).
+wraps (pre-LN, eps 1e-6, packed qkv with bias, scores = (q k^T) * scale, exact-erf GELU MLP, cls-token head) and is
+pinned against an independent implementation of the same architecture: torchvision's ``VisionTransformer``
+(``vit_b_16``) with shared weights - logits and every block's attention probabilities, tiny and full ViT-B/16 size
+(``tests/test_vit_pin.py``).
 The RULE is pinned: ``avg_heads`` / ``apply_self_attention_rules`` / ``generate_relevance`` follow
 Transformer_MM_explainability_ViT.ipynb:1169-1201 and are checked against the reference's own rule functions
 through tests/golden/rules.npz.

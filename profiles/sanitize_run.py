@@ -23,8 +23,15 @@ res = torch.randn(M, N, device="cuda"); C = torch.empty(M, N, device="cuda"); Ca
 for backend in (1, 2):
     if l.mmx_set_gemm_backend(backend) == backend:
         check(l.mmx_linear(ptr(A), K, ptr(W), K, ptr(b), ptr(res), N, ptr(C), N, ptr(Ca), 2, M, N, K, current_stream()))
+# fp16x3 kernels on packed weight planes: in-kernel split (2) and pre-split + CTA pairs (3), coalesced epilogue with every input
+pk = torch.empty(l.mmx_pack_weight_bytes(N, K), dtype=torch.uint8, device="cuda")
+check(l.mmx_pack_weight(ptr(W), K, N, K, ptr(pk), current_stream()))
+for backend in (2, 3):
+    if l.mmx_set_gemm_backend(backend) == backend:
+        check(l.mmx_linear_packed(ptr(A), K, ptr(W), K, ptr(pk), ptr(b), ptr(res), N, ptr(C), N, ptr(Ca), 2, M, N, K, current_stream()))
+        check(l.mmx_linear_packed(ptr(A), K, ptr(W), K, ptr(pk), ptr(b), None, 0, ptr(C), N, None, 0, M, N, K, current_stream()))
 l.mmx_set_gemm_backend(1)
-# tensor-core rule update (S >= 128) and the FFMA one
+# tensor-core rule update (S >= 128: one batched launch, tiles spill into the next sample's rows) and the FFMA one
 for S in (197, 50):
     R = torch.eye(S, device="cuda").repeat(2, 1, 1); Ab = torch.rand(2, S, S, device="cuda") * 0.01
     mmx_b200.self_update(R, Ab)
