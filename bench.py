@@ -65,6 +65,23 @@ def csrc_hash() -> str:
     return h.hexdigest()[:16]
 
 
+# the files a kernel family is compiled from: an ncu capture stays valid while THESE are unchanged
+KERNEL_SOURCES = {
+    "gemm_f16x3": ("gemm_f16x3.cu", "gemm_epilogue.cuh", "tcgen05_ptx.cuh", "gemm.cuh", "mmx_common.cuh"),
+    "gemm_tf32x3": ("gemm_tcgen05.cu", "gemm_epilogue.cuh", "tcgen05_ptx.cuh", "gemm.cuh", "mmx_common.cuh"),
+    "avg_heads": ("rules.cu", "mmx_common.cuh"),
+}
+
+
+def kernel_sources_hash(kernel_key: str) -> str:
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "transformer-mm-explainability_b200", "csrc")
+    for f in KERNEL_SOURCES.get(kernel_key, ()):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def captured_traffic(kernel_key: str):
     """DRAM traffic per launch from the committed `ncu --set full` capture (profiles/traffic_r2.json, written by
     profiles/capture_traffic.py); None when there is no capture for this kernel."""
@@ -78,7 +95,9 @@ def captured_traffic(kernel_key: str):
         return None, None
     rec = dict(rec)
     rec["capture_build"] = d.get("build")
-    rec["build_matches"] = d.get("build") == csrc_hash()
+    # valid for the running build when the kernel's own sources are the ones the capture was taken on
+    rec["build_matches"] = (rec.get("sources_hash") == kernel_sources_hash(kernel_key)) if rec.get("sources_hash") \
+        else d.get("build") == csrc_hash()
     return rec.get("dram_bytes"), rec
 
 
@@ -283,13 +302,22 @@ def bench_clip(D: Dist, cfg, B: int, steps: int, warm: int, max_batch: int, with
     ctx, sv = cfg.context_length, cfg.vision_tokens
     pending = []
 
+    # The one collective of the path: ONE all-gather of the packed maps per step.  In stream order by default; with
+    # MMX_BENCH_GATHER=async it overlaps the next step's forward - measured SLOWER at N = 2 (8.72 vs 7.95 ms per step): while
+    # the NCCL kernel waits for its peer it holds SMs, and the persistent GEMMs (one CTA per SM, static tile assignment)
+    # then run with a CTA missing.
+    gather_async = os.environ.get("MMX_BENCH_GATHER", "sync") == "async"
+
     def step_fn(sl):
         def step():
             rt, ri = eng.interpret(d_images, d_tokens, sl, sl, validate=False)
-            if world > 1:                                      # the one collective of the path: ONE all-gather of the packed maps,
-                pending.append(gather_maps_packed(rt, ri, n_total, async_op=True))   # overlapped with the next step's forward
-                while len(pending) > 2:
-                    pending.pop(0)[0].wait()
+            if world > 1:
+                if gather_async:
+                    pending.append(gather_maps_packed(rt, ri, n_total, async_op=True))
+                    while len(pending) > 2:
+                        pending.pop(0)[0].wait()
+                else:
+                    gather_maps_packed(rt, ri, n_total, async_op=False)
             return rt, ri
         return step
 
@@ -326,7 +354,9 @@ def bench_clip(D: Dist, cfg, B: int, steps: int, warm: int, max_batch: int, with
         D.barrier()
         res["collective"] = {"kind": "ncclAllGather (torch.distributed all_gather_into_tensor), R_text and R_image packed in one buffer",
                              "calls_per_step": 1, "bytes_per_rank": int((ctx * ctx + sv - 1) * 4 * B),
-                             "ms_alone": D.max(e0.elapsed_time(e1) / 10), "overlapped_with": "the next step's forward"}
+                             "ms_alone": D.max(e0.elapsed_time(e1) / 10),
+                             "overlapped_with": "the next step's forward" if gather_async else None,
+                             "order": "async, overlapped" if gather_async else "in stream order at the end of every step"}
 
     # ---- e2e: host buffers in, host maps out, copies inside the timed region
     if world == 1:
@@ -372,7 +402,12 @@ def bench_clip(D: Dist, cfg, B: int, steps: int, warm: int, max_batch: int, with
         for r in range(world):
             st, si = eng.interpret(g_img[r * B:(r + 1) * B], g_tok[r * B:(r + 1) * B], START_LAYER, START_LAYER, validate=False)
             ft, fi = split_packed(full[r * B:(r + 1) * B], ctx, sv - 1)
-            ok = ok and torch.equal(st, ft) and torch.equal(si, fi)
+            same = torch.equal(st, ft) and torch.equal(si, fi)
+            if not same:
+                print(f"[rank {rank}] shard {r}: recomputed != gathered: text max|d| {(st - ft).abs().max().item():.3e} "
+                      f"({int((st != ft).sum())} elements), image max|d| {(si - fi).abs().max().item():.3e} "
+                      f"({int((si != fi).sum())} elements)", file=sys.stderr)
+            ok = ok and same
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         res["sharded_equals_single"] = bool(flag.item())

@@ -267,7 +267,8 @@ int mmx_clip_finalize(mmx_clip* h);
 /* interpret() (CLIP_explainability.ipynb:151-208).  images: [n_images,3,R,R] fp32 with n_images == B or 1 (the
  * notebook's image.repeat, :153); tokens: [B,context] int32.  start_layer / start_layer_text as in the notebook
  * (-1 = last block only).  R_text: [B,ctx,ctx], R_image: [B,S_v-1].  *_device: all pointers are device memory,
- * work is enqueued on `stream` (NULL: the engine's own stream, synchronised before return).  *_host: pointers
+ * work is enqueued on `stream`, after everything already enqueued there, and later work on `stream` is ordered after it
+ * (NULL: the legacy default stream); the call does not wait for the results.  *_host: pointers
  * are host memory (pinned or pageable); copies happen inside the call, which returns after the results landed. */
 int mmx_clip_interpret_device(mmx_clip* h, const float* images, int n_images, const int32_t* tokens, int B,
                               int start_layer, int start_layer_text, float* R_text, float* R_image, void* stream);

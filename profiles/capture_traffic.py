@@ -35,6 +35,8 @@ def main(args):
     for a in args:
         key, path = a.split("=")
         out[key] = first_kernel(path)
+        out[key]["sources"] = list(bench.KERNEL_SOURCES.get(key, ()))
+        out[key]["sources_hash"] = bench.kernel_sources_hash(key)
     extra = os.environ.get("TRAFFIC_NOTE")
     if extra:
         out["note"] = extra

@@ -594,7 +594,11 @@ int mmx_clip_interpret_device(mmx_clip* h, const float* images, int n_images, co
   int sv = 0, stx = 0;
   MMX_TRY(resolve_start(start_layer, h->v.L, &sv));
   MMX_TRY(resolve_start(start_layer_text, h->t.L, &stx));
-  cudaStream_t caller = stream ? (cudaStream_t)stream : h->main;
+  // NULL is the legacy default stream, like everywhere else in this ABI: the towers fork from it (so they are ordered
+  // after whatever the caller enqueued there - an H2D copy, a collective that produced the inputs) and join it again.
+  // (Through round 2 a NULL stream meant the engine's own non-blocking stream, which does NOT wait for default-stream
+  // work: inputs still in flight on the default stream were read too early - found by bench.py's sharded == single check.)
+  cudaStream_t caller = (cudaStream_t)stream;
   const size_t img_sz = (size_t)3 * h->cfg.image_resolution * h->cfg.image_resolution;
   for (int b0 = 0; b0 < B; b0 += h->Bm) {
     const int nb = (B - b0 < h->Bm) ? B - b0 : h->Bm;
@@ -603,7 +607,6 @@ int mmx_clip_interpret_device(mmx_clip* h, const float* images, int n_images, co
                       R_text + (size_t)b0 * h->t.S * h->t.S, R_image + (size_t)b0 * (h->v.S - 1), caller));
     if (b0 == 0) { h->lastB = nb; h->last_start_v = sv; h->last_start_t = stx; }
   }
-  if (!stream) MMX_CHECK_CUDA(cudaStreamSynchronize(caller));
   return 0;
 }
 
