@@ -73,12 +73,28 @@ KERNEL_SOURCES = {
 }
 
 
-def kernel_sources_hash(kernel_key: str) -> str:
+def _code_only(text: str) -> str:
+    """Source text without `//` comments, trailing blanks and empty lines (no string literal in csrc/ contains `//`)."""
+    out = []
+    for line in text.splitlines():
+        line = line.split("//", 1)[0].rstrip()
+        if line:
+            out.append(line)
+    return "\n".join(out)
+
+
+def kernel_sources_hash(kernel_key: str, read=None) -> str:
+    """Hash of the CODE (comments stripped) of the files a kernel family is compiled from.  `read(name) -> str` overrides
+    the file reader (tests; hashing the files of another commit)."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "transformer-mm-explainability_b200", "csrc")
     for f in KERNEL_SOURCES.get(kernel_key, ()):
-        with open(os.path.join(d, f), "rb") as fh:
-            h.update(fh.read())
+        if read is None:
+            with open(os.path.join(d, f)) as fh:
+                text = fh.read()
+        else:
+            text = read(f)
+        h.update(_code_only(text).encode())
     return h.hexdigest()[:16]
 
 

@@ -3,7 +3,7 @@
 // tcgen05.ld hands every thread ONE ROW of the accumulator tile (TMEM lane = row).  Storing from that layout directly
 // (thread -> 16 B of its own row) makes each warp-wide store touch 32 different rows, 16 B each: half-filled 32-byte
 // sectors, 32 requests per instruction.  Measured on the QKV product (3200 x 2304 x 768, clock64 timeline of CTA 0,
-// profiles/gemm_trace_r2.md): 19300 clk of stores per 128 x 144 tile against 13000 clk of main loop - the epilogue, not
+// profiles/gemm_trace_r2_before.log): 19300 clk of stores per 128 x 144 tile against 13000 clk of main loop - the epilogue, not
 // the tensor pipe, L2 or the splitters, set the time of every variant of the kernel.
 //
 // Here each epilogue warp turns its 32 rows x 16 columns through a 2 KB shared-memory buffer (XOR-swizzled 16-byte chunks:
