@@ -261,3 +261,23 @@ def test_ragged_rows_leave_no_stale_columns(mmx):
         assert float(t[..., 12:, :].abs().max()) == 0.0 and float(t[..., :, 12:].abs().max()) == 0.0, what
     ot, _ = co.clip_interpret(sd, cfg, images, toks(10), 0, 0)
     assert text_rel_err(rt, ot) < TOL
+
+
+def test_inputs_still_in_flight_on_the_callers_stream(mmx, b32):
+    """The call is ordered after whatever the caller enqueued on its stream (here PyTorch's default stream = the NULL
+    stream of the C ABI): images that arrive by an asynchronous H2D copy issued right before interpret() must be the
+    images the towers see.  (Until round 2 a NULL stream meant the engine's private stream, which did not wait.)"""
+    cfg, sd, eng = b32
+    images, tokens = co.synthetic_inputs(cfg, 64, seed=71)
+    other, _ = co.synthetic_inputs(cfg, 64, seed=72)
+    tok = tokens.cuda()
+    ref_t, ref_i = eng.interpret(images.cuda(), tok, 0, 0)
+    torch.cuda.synchronize()
+    pinned, stale = images.pin_memory(), other.cuda()
+    buf = torch.empty_like(stale)
+    for _ in range(4):
+        buf.copy_(stale)                                   # what a too-early read would see
+        torch.cuda.synchronize()
+        buf.copy_(pinned, non_blocking=True)               # 38.5 MB in flight on the current stream ...
+        rt, ri = eng.interpret(buf, tok, 0, 0)             # ... when the towers are enqueued
+        assert torch.equal(rt, ref_t) and torch.equal(ri, ref_i)
